@@ -1,2 +1,15 @@
-"""B200-native TDVP backend (``backend="cuda"``) behind a PyTDSCF-style Model / Simulator API."""
+"""B200-native TDVP backend (``backend="cuda"``) behind a PyTDSCF-style Model / Simulator API.
+
+Only the MPS/MPO one-site TDVP propagation hot path of PyTDSCF is implemented; it runs
+entirely on the GPU through ``libtdvp_b200.so`` (``include/tdvp_b200.h``).  There is no CPU fallback.
+"""
+from . import units
+from .basis import Boson, Exciton, HarmonicOscillator
+from .dvr_operator_cls import TensorOperator, construct_kinetic_mpo
+from .hamiltonian_cls import TensorHamiltonian
+from .model_cls import BasInfo, Model
+from .simulator_cls import Simulator
+
 __version__ = "0.1.0"
+__all__ = ["units", "Boson", "Exciton", "HarmonicOscillator", "TensorOperator", "construct_kinetic_mpo",
+           "TensorHamiltonian", "BasInfo", "Model", "Simulator", "__version__"]

@@ -1,0 +1,34 @@
+"""Run configuration (reference: the global ``const`` of ``pytdscf/_const_cls.py:102-252``).
+
+Unlike the reference this is an explicit object owned by the ``Simulator`` (no mutable module global), but the
+field names and the rules that derive them are the same."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+
+@dataclass
+class RunConfig:
+    jobname: str = "propagate"
+    relax: bool | str = False
+    maxstep: int = 9999999
+    thresh_exp: float = 1.0e-09  # = thresh_sil
+    verbose: int = 2
+    space: str = "hilbert"
+    integrator: str = "lanczos"
+    conserve_norm: bool = True
+    display_time_unit: str = "fs"
+    time_au_init: float = 0.0
+    adaptive: bool = False
+
+    def __post_init__(self):
+        self.space = self.space.lower()
+        self.integrator = self.integrator.lower()
+        if self.space not in ("hilbert", "liouville"):
+            raise ValueError(f"space must be 'hilbert' or 'liouville' but got {self.space}")
+        if self.integrator not in ("lanczos", "arnoldi"):
+            raise ValueError(f"Invalid integrator: {self.integrator}")
+        if self.space == "liouville":  # _const_cls.py:219-224
+            self.conserve_norm = False
+        if self.adaptive:
+            raise NotImplementedError("adaptive (A1TDVP) bond dimensions are not implemented in backend='cuda' yet")

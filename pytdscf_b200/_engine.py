@@ -1,0 +1,270 @@
+"""Thin typed wrapper over the C ABI: torch tensors in, torch tensors out, every op on the GPU.
+
+One ``Engine`` = one ``tdvp_handle_t`` = one GPU / rank.  Nothing here computes on the host: the
+methods marshal device pointers and shapes into ``include/tdvp_b200.h`` calls.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import GAUGE_A, GAUGE_B, KIND_DIAG, KIND_FULL, HeffTerm, KeffTerm, check
+
+CDTYPE = torch.complex128
+
+
+@dataclass
+class DeviceCore:
+    """An MPO core resident in HBM (reference: ``OperatorCore``, pytdscf/_mpo_cls.py:166-215)."""
+
+    data: torch.Tensor | None  # (wl,d,wr) diagonal or (wl,d,d,wr) full; None = identity gap core
+    perm: torch.Tensor | None = None  # full cores: Wp[c,j,i,t] = W[c,i,j,t], made once at upload
+
+    @property
+    def kind(self) -> int:
+        if self.data is None:
+            return _lib.KIND_IDENTITY
+        return KIND_DIAG if self.data.dim() == 3 else KIND_FULL
+
+    @property
+    def wl(self) -> int:
+        return 1 if self.data is None else int(self.data.shape[0])
+
+    @property
+    def wr(self) -> int:
+        return 1 if self.data is None else int(self.data.shape[-1])
+
+
+def _ptr(t: torch.Tensor | None):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _chk_tensor(t: torch.Tensor, name: str):
+    if not (t.is_cuda and t.dtype == CDTYPE and t.is_contiguous()):
+        raise TypeError(f"{name} must be a contiguous complex128 CUDA tensor (got {t.dtype}, cuda={t.is_cuda})")
+
+
+class Engine:
+    """Owns a ``tdvp_handle_t`` bound to torch's current stream on ``device``."""
+
+    def __init__(self, device: int | None = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("backend='cuda' needs a CUDA device; there is no CPU fallback")
+        self.lib = _lib.load_library()
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        torch.cuda.set_device(self.device)
+        self.torch_device = torch.device("cuda", self.device)
+        self.stream = torch.cuda.current_stream(self.device)
+        h = C.c_void_p()
+        rc = self.lib.tdvp_create(self.device, C.c_void_p(self.stream.cuda_stream), C.byref(h))
+        if rc != 0:
+            raise _lib.TdvpError(rc, "tdvp_create failed")
+        self.h = h
+        self._keep: list = []  # tensors referenced by descriptors of the call in flight
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.tdvp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- uploads ---------------------------------------------------------------------
+    def to_device(self, a) -> torch.Tensor:
+        return torch.as_tensor(np.ascontiguousarray(a, dtype=np.complex128)).to(self.torch_device)
+
+    def upload_core(self, data) -> DeviceCore:
+        if data is None:
+            return DeviceCore(None)
+        t = self.to_device(data)
+        perm = t.permute(0, 2, 1, 3).contiguous() if t.dim() == 4 else None
+        return DeviceCore(t, perm)
+
+    def empty(self, *shape) -> torch.Tensor:
+        return torch.empty(shape, dtype=CDTYPE, device=self.torch_device)
+
+    # -- descriptors -----------------------------------------------------------------
+    def heff_terms(self, terms):
+        """terms: iterable of (L | None, DeviceCore | None, R | None, coef)."""
+        arr = (HeffTerm * len(terms))()
+        for i, (L, core, R, coef) in enumerate(terms):
+            t = arr[i]
+            t.L = None if L is None else L.data_ptr()
+            t.R = None if R is None else R.data_ptr()
+            if core is None or core.data is None:
+                t.W = None
+                t.Wp = None
+                t.w_kind = _lib.KIND_IDENTITY
+                t.wl = 1 if L is None else int(L.shape[1])
+                t.wr = 1 if R is None else int(R.shape[1])
+            else:
+                t.W = core.data.data_ptr()
+                t.Wp = None if core.perm is None else core.perm.data_ptr()
+                t.w_kind = core.kind
+                t.wl = core.wl
+                t.wr = core.wr
+                if L is not None and int(L.shape[1]) != core.wl:
+                    raise ValueError("left block / core bond dimension mismatch")
+                if R is not None and int(R.shape[1]) != core.wr:
+                    raise ValueError("right block / core bond dimension mismatch")
+            c = complex(coef)
+            t.coef_re, t.coef_im = c.real, c.imag
+        return arr
+
+    def keff_terms(self, terms):
+        """terms: iterable of (L | None, R | None, coef)."""
+        arr = (KeffTerm * len(terms))()
+        for i, (L, R, coef) in enumerate(terms):
+            t = arr[i]
+            t.L = None if L is None else L.data_ptr()
+            t.R = None if R is None else R.data_ptr()
+            if L is not None and R is not None and L.shape[1] != R.shape[1]:
+                raise ValueError("K_eff term: MPO bond dimensions of L and R differ")
+            t.w = int(L.shape[1]) if L is not None else (int(R.shape[1]) if R is not None else 1)
+            c = complex(coef)
+            t.coef_re, t.coef_im = c.real, c.imag
+        return arr
+
+    # -- contractions ----------------------------------------------------------------
+    def heff_apply(self, terms, psi: torch.Tensor) -> torch.Tensor:
+        _chk_tensor(psi, "psi")
+        Dl, d, Dr = psi.shape
+        out = torch.empty_like(psi)
+        arr = self.heff_terms(terms)
+        check(self.h, self.lib.tdvp_heff_apply(self.h, arr, len(terms), Dl, d, Dr, _ptr(psi), _ptr(out)))
+        return out
+
+    def keff_apply(self, terms, sigma: torch.Tensor) -> torch.Tensor:
+        _chk_tensor(sigma, "sigma")
+        Dl, Dr = sigma.shape
+        out = torch.empty_like(sigma)
+        arr = self.keff_terms(terms)
+        check(self.h, self.lib.tdvp_keff_apply(self.h, arr, len(terms), Dl, Dr, _ptr(sigma), _ptr(out)))
+        return out
+
+    def env_update(self, gauge: str, bra: torch.Tensor, ket: torch.Tensor, E: torch.Tensor | None,
+                   core: DeviceCore | None, out: torch.Tensor | None = None, accumulate: bool = False) -> torch.Tensor:
+        _chk_tensor(bra, "bra")
+        _chk_tensor(ket, "ket")
+        Dl, d, Dr = ket.shape
+        g = GAUGE_A if gauge == "A" else GAUGE_B
+        has_core = core is not None and core.data is not None
+        if gauge == "A":
+            w_in = core.wl if has_core else (1 if E is None else int(E.shape[1]))
+            w_out = core.wr if has_core else w_in
+            D_out = Dr
+        else:
+            w_in = core.wr if has_core else (1 if E is None else int(E.shape[1]))
+            w_out = core.wl if has_core else w_in
+            D_out = Dl
+        if E is not None and int(E.shape[1]) != w_in:
+            raise ValueError("environment block / core bond dimension mismatch")
+        if out is None:
+            out = self.empty(D_out, w_out, D_out)
+            accumulate = False
+        check(self.h, self.lib.tdvp_env_update(
+            self.h, g, Dl, d, Dr, _ptr(bra), _ptr(ket), _ptr(E), w_in,
+            _ptr(core.data) if has_core else None, core.kind if has_core else 0, w_out, _ptr(out), int(accumulate)))
+        return out
+
+    # -- Krylov ------------------------------------------------------------------------
+    def krylov_expm(self, kind: str, scale: complex, thresh: float, n_warmup: int, conserve_norm: bool,
+                    psi: torch.Tensor, *, hterms=None, kterms=None) -> int:
+        """psi <- exp(scale*Op) psi in place; returns the number of Krylov vectors used."""
+        _chk_tensor(psi, "psi")
+        k = _lib.KRYLOV_ARNOLDI if kind == "arnoldi" else _lib.KRYLOV_LANCZOS_REF
+        niter = C.c_int(0)
+        scale = complex(scale)
+        if hterms is not None:
+            Dl, d, Dr = psi.shape
+            arr = self.heff_terms(hterms)
+            rc = self.lib.tdvp_krylov_expm(self.h, k, scale.real, scale.imag, float(thresh), int(n_warmup),
+                                           int(bool(conserve_norm)), arr, None, len(hterms), Dl, d, Dr, _ptr(psi),
+                                           C.byref(niter))
+        else:
+            Dl, Dr = psi.shape
+            arr = self.keff_terms(kterms)
+            rc = self.lib.tdvp_krylov_expm(self.h, k, scale.real, scale.imag, float(thresh), int(n_warmup),
+                                           int(bool(conserve_norm)), None, arr, len(kterms), Dl, 1, Dr, _ptr(psi),
+                                           C.byref(niter))
+        check(self.h, rc)
+        return int(niter.value)
+
+    # -- gauge -------------------------------------------------------------------------
+    def qr_shift(self, gauge: str, psi: torch.Tensor):
+        """'A': psi -> (A(Dl,d,k), sigma(k,Dr));  'B': psi -> (B(k,d,Dr), sigma(Dl,k))."""
+        _chk_tensor(psi, "psi")
+        Dl, d, Dr = psi.shape
+        if gauge == "A":
+            if Dl * d < Dr:
+                raise ValueError("QR shift needs Dl*d >= Dr")
+            site, sigma = self.empty(Dl, d, Dr), self.empty(Dr, Dr)
+            g = GAUGE_A
+        else:
+            if Dr * d < Dl:
+                raise ValueError("LQ shift needs Dr*d >= Dl")
+            site, sigma = self.empty(Dl, d, Dr), self.empty(Dl, Dl)
+            g = GAUGE_B
+        check(self.h, self.lib.tdvp_qr_shift(self.h, g, Dl, d, Dr, _ptr(psi), _ptr(site), _ptr(sigma)))
+        return site, sigma
+
+    def absorb(self, gauge: str, sigma: torch.Tensor, site: torch.Tensor) -> torch.Tensor:
+        """'A': sigma(k,Dl).site(Dl,d,Dr) -> (k,d,Dr);  'B': site(Dl,d,Dr).sigma(Dr,k) -> (Dl,d,k)."""
+        _chk_tensor(sigma, "sigma")
+        _chk_tensor(site, "site")
+        Dl, d, Dr = site.shape
+        if gauge == "A":
+            k = int(sigma.shape[0])
+            out = self.empty(k, d, Dr)
+            g = GAUGE_A
+        else:
+            k = int(sigma.shape[1])
+            out = self.empty(Dl, d, k)
+            g = GAUGE_B
+        check(self.h, self.lib.tdvp_absorb(self.h, g, Dl, d, Dr, k, _ptr(sigma), _ptr(site), _ptr(out)))
+        return out
+
+    # -- observables -------------------------------------------------------------------
+    def inner(self, bra: torch.Tensor, ket: torch.Tensor, conj: bool = True) -> complex:
+        _chk_tensor(bra, "bra")
+        _chk_tensor(ket, "ket")
+        out = _lib.c128()
+        check(self.h, self.lib.tdvp_inner(self.h, bra.numel(), _ptr(bra), _ptr(ket), int(conj), C.byref(out)))
+        return complex(out.re, out.im)
+
+    def overlap_site(self, bra: torch.Tensor, ket: torch.Tensor, block: torch.Tensor, conj_bra: bool) -> torch.Tensor:
+        Dlb, d, Drb = bra.shape
+        Dlk, _, Drk = ket.shape
+        out = self.empty(Drb, Drk)
+        check(self.h, self.lib.tdvp_overlap_site(self.h, Dlb, Dlk, d, Drb, Drk, _ptr(bra), _ptr(ket), _ptr(block),
+                                                 int(conj_bra), _ptr(out)))
+        return out
+
+    def zgemm(self, A: torch.Tensor, B: torch.Tensor, transA: int = 0, transB: int = 0, alpha=1.0, beta=0.0,
+              C_out: torch.Tensor | None = None) -> torch.Tensor:
+        M = A.shape[1] if transA else A.shape[0]
+        K = A.shape[0] if transA else A.shape[1]
+        N = B.shape[0] if transB else B.shape[1]
+        if C_out is None:
+            C_out = self.empty(M, N)
+        a, b = complex(alpha), complex(beta)
+        check(self.h, self.lib.tdvp_zgemm(self.h, transA, transB, M, N, K, a.real, a.imag, _ptr(A), A.shape[1], _ptr(B),
+                                          B.shape[1], b.real, b.imag, _ptr(C_out), C_out.shape[1]))
+        return C_out
+
+    # -- statistics ----------------------------------------------------------------------
+    def stats(self) -> dict:
+        s, m, f = C.c_ulonglong(0), C.c_ulonglong(0), C.c_double(0.0)
+        self.lib.tdvp_get_stats(self.h, C.byref(s), C.byref(m), C.byref(f))
+        return {"solves": s.value, "matvecs": m.value, "flops": f.value, "launches": int(self.lib.tdvp_launch_count())}
+
+    def reset_stats(self):
+        self.lib.tdvp_reset_stats(self.h)

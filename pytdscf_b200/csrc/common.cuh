@@ -1,0 +1,88 @@
+// Shared declarations of libtdvp_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+namespace tdvp {
+
+typedef double2 c128;  // complex128, interleaved (re, im): what NumPy / torch hold
+
+// ---- error plumbing: every entry point returns int, never throws (include/tdvp_b200.h) -------
+enum : int {
+  TDVP_OK = 0,
+  TDVP_ERR_ARG = -1,
+  TDVP_ERR_SHAPE = -2,
+  TDVP_ERR_NOT_CONVERGED = -3,
+  TDVP_ERR_UNSUPPORTED = -4,
+  TDVP_ERR_ZERO_NORM = -5,
+};
+
+struct Handle;
+void set_error(Handle* h, const std::string& msg);
+int cuda_fail(Handle* h, cudaError_t e, const char* what, const char* file, int line);
+
+#define TDVP_CUDA(h, expr)                                              \
+  do {                                                                  \
+    cudaError_t _e = (expr);                                            \
+    if (_e != cudaSuccess) return tdvp::cuda_fail((h), _e, #expr, __FILE__, __LINE__); \
+  } while (0)
+
+#define TDVP_TRY(expr)            \
+  do {                            \
+    int _rc = (expr);             \
+    if (_rc != 0) return _rc;     \
+  } while (0)
+
+// ---- generalised GEMM descriptor -------------------------------------------------------------
+// C[m,n] = alpha * sum_k opA[m,k] * opB[k,n] + beta * C[m,n], batched.
+// Row / column indices may be two-level (m = m1*m_inner + m0) so that tensor contractions run on
+// their natural layouts without transposes.  All strides are in complex128 elements.
+struct GemmDesc {
+  int M = 0, N = 0, K = 0, batch = 1;
+  const c128* A = nullptr;
+  long long a_batch = 0;   // batch stride
+  int a_m_inner = 1;       // m = m1 * a_m_inner + m0
+  long long a_m1 = 0, a_m0 = 0, a_k = 0;
+  int a_conj = 0;          // use conj(A[m,k])
+  const c128* B = nullptr;
+  long long b_batch = 0;
+  int b_n_inner = 1;
+  long long b_n1 = 0, b_n0 = 0, b_k = 0;
+  int b_conj = 0;
+  c128* C = nullptr;
+  long long c_batch = 0;
+  int c_m_inner = 1;
+  long long c_m1 = 0, c_m0 = 0, c_n = 1;
+  c128 alpha = {1.0, 0.0};
+  c128 beta = {0.0, 0.0};
+};
+
+// Launch the DMMA ZGEMM on `stream`.  Returns cudaGetLastError() of the launch.
+cudaError_t zgemm_launch(const GemmDesc& d, cudaStream_t stream);
+// Number of kernel launches issued through this library since load (bench.py's gpu_launches claim).
+extern unsigned long long g_launch_count;
+
+// Plain row-major helpers
+inline GemmDesc gemm_rowmajor(int M, int N, int K, const c128* A, long long lda, bool transA, bool conjA,
+                              const c128* B, long long ldb, bool transB, c128* C, long long ldc,
+                              c128 alpha = {1.0, 0.0}, c128 beta = {0.0, 0.0}) {
+  GemmDesc g;
+  g.M = M; g.N = N; g.K = K;
+  g.A = A; g.a_m_inner = 1; g.a_m0 = 0;
+  if (!transA) { g.a_m1 = lda; g.a_k = 1; } else { g.a_m1 = 1; g.a_k = lda; }
+  g.a_conj = conjA ? 1 : 0;
+  g.B = B; g.b_n_inner = 1; g.b_n0 = 0;
+  if (!transB) { g.b_n1 = 1; g.b_k = ldb; } else { g.b_n1 = ldb; g.b_k = 1; }
+  g.C = C; g.c_m_inner = 1; g.c_m1 = ldc; g.c_m0 = 0; g.c_n = 1;
+  g.alpha = alpha; g.beta = beta;
+  return g;
+}
+
+__host__ __device__ inline c128 cmul(c128 a, c128 b) { return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+__host__ __device__ inline c128 cadd(c128 a, c128 b) { return {a.x + b.x, a.y + b.y}; }
+__host__ __device__ inline c128 cconj(c128 a) { return {a.x, -a.y}; }
+
+}  // namespace tdvp

@@ -1,0 +1,36 @@
+// Per-GPU handle of libtdvp_b200: stream, error string, device workspace (bump allocator) and a
+// pinned host mailbox for the few scalars the host control flow needs (Krylov alpha/beta/err).
+#pragma once
+#include "common.cuh"
+
+#include <vector>
+
+namespace tdvp {
+
+struct Handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  // device workspace (grown on demand; calls on a handle are serialised by the caller)
+  unsigned char* ws = nullptr;
+  size_t ws_bytes = 0;
+  size_t ws_top = 0;
+  // small device scratch for reductions + pinned host mirror
+  double* d_scal = nullptr;   // 4096 doubles
+  double* h_scal = nullptr;   // pinned, 4096 doubles
+  double* d_partial = nullptr;  // reduction partials: 1024 blocks x 64 doubles
+  unsigned int* d_counter = nullptr;  // "last block done" tickets
+  // statistics
+  unsigned long long krylov_matvecs = 0;
+  unsigned long long krylov_solves = 0;
+  double heff_flops = 0.0;  // algorithmic flops of H_eff/K_eff/env contractions issued (SURVEY 8(d) formulas)
+};
+
+// Make sure the workspace holds at least `bytes`; resets the bump pointer.
+int ws_reserve(Handle* h, size_t bytes);
+// Bump allocation inside the reserved workspace (256-byte aligned). nullptr if it does not fit.
+void* ws_alloc(Handle* h, size_t bytes);
+inline void ws_reset(Handle* h) { h->ws_top = 0; }
+inline size_t align256(size_t b) { return (b + 255) & ~size_t(255); }
+
+}  // namespace tdvp

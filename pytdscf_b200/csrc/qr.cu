@@ -1,0 +1,379 @@
+// Blocked Householder QR with LAPACK zgeqrf / zungqr conventions for the TDVP gauge shift.
+//
+// Replaces scipy.linalg.qr(mode="economic") inside SiteCoef.gauge_trf (pytdscf/_site_cls.py:264-272, :279-291)
+// and the sigma absorb of trans_next_psite_APsiB (pytdscf/_mps_cls.py:1187-1206).
+//
+// Why Householder with LAPACK's sign rule and not CholeskyQR/TSQR (SURVEY "hard parts"): the initial MPS is a
+// Hartree product zero-padded to D, so early site tensors have EXACT zero columns; zlarfg returns tau = 0
+// (identity reflector) for them and the null-space completion of Q is then a deterministic function of the
+// leading reflectors.  One-site TDVP evolves inside the tangent space spanned by those completions, so the
+// device QR reproduces zlarfg (beta = -sign(Re alpha)*norm, tau = (beta-alpha)/beta, v = x/(alpha-beta)),
+// zlarft and the zlarfb block applications; only summation order differs from LAPACK.
+//
+// Panel factorisation (k_qr_panel): a cooperative kernel, one CTA per slab of <= SLAB_ROWS rows, the slab of
+// the 32-column panel lives in shared memory for the whole panel.  Per column ONE grid-wide reduction gives
+// both |x|^2 and every v^H a_j: with g_j = sum_{i>c} conj(a_ic) a_ij,  w_j = a_cj + conj(s) g_j where
+// s = 1/(alpha - beta).  Partials are combined in fixed CTA order (deterministic).  Trailing updates and the
+// formation of Q are DMMA ZGEMMs on explicit unit-lower-trapezoidal V panels.
+#include <cooperative_groups.h>
+
+#include "contract.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace tdvp {
+
+namespace {
+
+constexpr int NB = 32;           // panel width
+constexpr int SLAB_ROWS = 256;   // rows of the panel held per CTA (256*32*16 B = 128 KiB)
+constexpr int PT = 256;          // threads per CTA, arranged (32, 8)
+constexpr int PTY = PT / 32;
+
+struct PanelArgs {
+  c128* A; int lda; int m; int n; int j0; int jb;
+  double* tau;     // complex tau per column of the whole matrix (2 doubles each)
+  c128* Vall;      // explicit V, same shape as A (ld = lda)
+  c128* Tall;      // per panel NB x NB upper triangular T (row-major), panel p at Tall + p*NB*NB
+  double* gpart;   // 2 buffers x G x (2*NB complex): [buf][cta][0..NB) partial g, [NB..2NB) diagonal row broadcast
+  double* zpart;   // G x NB x NB complex partial Gram for T
+  int rows_per_cta;
+};
+
+__device__ __forceinline__ double dlapy3(double x, double y, double z) {
+  const double w = fmax(fabs(x), fmax(fabs(y), fabs(z)));
+  if (w == 0.0) return 0.0;
+  const double a = x / w, b = y / w, c = z / w;
+  return w * sqrt(a * a + b * b + c * c);
+}
+
+__global__ void __launch_bounds__(PT, 1) k_qr_panel(PanelArgs p) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  c128* S = reinterpret_cast<c128*>(smraw);                 // [rows_per_cta][NB]
+  __shared__ c128 red[PTY][NB];
+  __shared__ c128 gtot[NB];     // reduced g_j
+  __shared__ c128 rowc[NB];     // row c of the panel (broadcast)
+  __shared__ c128 wv[NB];       // w_j
+  __shared__ double s_tau[2], s_scal[2], s_beta;
+  cg::grid_group grid = cg::this_grid();
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int G = gridDim.x, b = blockIdx.x;
+  const int jb = p.jb, j0 = p.j0;
+  const int r0 = j0 + b * p.rows_per_cta;                   // first global row of this slab
+  int nrow = p.m - r0;
+  if (nrow > p.rows_per_cta) nrow = p.rows_per_cta;
+  if (nrow < 0) nrow = 0;
+
+  // ---- load slab ----
+  for (int i = ty; i < nrow; i += PTY) {
+    if (tx < jb) S[i * NB + tx] = p.A[(long long)(r0 + i) * p.lda + j0 + tx];
+    else S[i * NB + tx] = {0.0, 0.0};
+  }
+  __syncthreads();
+
+  for (int c = 0; c < jb; ++c) {
+    const int grow = j0 + c;                                 // global row of the diagonal element
+    double* gp = p.gpart + (size_t)(c & 1) * G * (4 * NB);
+    // (a) partial g_j = sum_{rows > grow} conj(a_ic) a_ij   for j = tx >= c
+    c128 acc = {0.0, 0.0};
+    if (tx >= c && tx < jb) {
+      for (int i = ty; i < nrow; i += PTY) {
+        if (r0 + i > grow) {
+          const c128 x = S[i * NB + c], y = S[i * NB + tx];
+          acc.x += x.x * y.x + x.y * y.y;
+          acc.y += x.x * y.y - x.y * y.x;
+        }
+      }
+    }
+    red[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0) {
+      c128 t = {0.0, 0.0};
+#pragma unroll
+      for (int q = 0; q < PTY; ++q) { t.x += red[q][tx].x; t.y += red[q][tx].y; }
+      gp[(size_t)b * (4 * NB) + 2 * tx] = t.x;
+      gp[(size_t)b * (4 * NB) + 2 * tx + 1] = t.y;
+      // owner of the diagonal row broadcasts it
+      if (grow >= r0 && grow < r0 + nrow) {
+        const c128 v = S[(grow - r0) * NB + tx];
+        gp[2 * NB + 2 * tx] = v.x;          // slot of CTA 0, upper half: shared broadcast area
+        gp[2 * NB + 2 * tx + 1] = v.y;
+      }
+    }
+    __threadfence();
+    if (G > 1) grid.sync(); else __syncthreads();
+    // (c) total g and the diagonal row
+    if (ty == 0) {
+      c128 t = {0.0, 0.0};
+      for (int q = 0; q < G; ++q) {
+        t.x += __ldcg(&gp[(size_t)q * (4 * NB) + 2 * tx]);
+        t.y += __ldcg(&gp[(size_t)q * (4 * NB) + 2 * tx + 1]);
+      }
+      gtot[tx] = t;
+      rowc[tx] = {__ldcg(&gp[2 * NB + 2 * tx]), __ldcg(&gp[2 * NB + 2 * tx + 1])};
+    }
+    __syncthreads();
+    // (d) zlarfg
+    if (tx == 0 && ty == 0) {
+      const double xnorm = sqrt(fmax(gtot[c].x, 0.0));
+      const double alphr = rowc[c].x, alphi = rowc[c].y;
+      if (xnorm == 0.0 && alphi == 0.0) {
+        s_tau[0] = 0.0; s_tau[1] = 0.0; s_scal[0] = 1.0; s_scal[1] = 0.0; s_beta = alphr;
+      } else {
+        double beta = dlapy3(alphr, alphi, xnorm);
+        beta = (alphr >= 0.0) ? -beta : beta;               // -SIGN(norm, alphr)
+        s_tau[0] = (beta - alphr) / beta;
+        s_tau[1] = -alphi / beta;
+        // s = 1 / (alpha - beta)   (zladiv)
+        const double dr = alphr - beta, di = alphi;
+        const double den = dr * dr + di * di;
+        s_scal[0] = dr / den; s_scal[1] = -di / den;
+        s_beta = beta;
+      }
+      if (b == 0) { p.tau[2 * (j0 + c)] = s_tau[0]; p.tau[2 * (j0 + c) + 1] = s_tau[1]; }
+    }
+    __syncthreads();
+    const c128 tau = {s_tau[0], s_tau[1]};
+    const c128 sc = {s_scal[0], s_scal[1]};
+    const bool trivial = (tau.x == 0.0 && tau.y == 0.0);
+    if (ty == 0 && tx > c && tx < jb) {
+      // w_j = a_cj + conj(s) g_j
+      const c128 cs = {sc.x, -sc.y};
+      wv[tx] = cadd(rowc[tx], cmul(cs, gtot[tx]));
+    }
+    __syncthreads();
+    // (e) scale x, apply H^H = I - conj(tau) v v^H to the remaining panel columns, set the diagonal
+    if (!trivial) {
+      const c128 ctau = {tau.x, -tau.y};
+      for (int i = ty; i < nrow; i += PTY) {
+        const int gr = r0 + i;
+        if (gr < grow) continue;
+        c128 v;
+        if (gr == grow) v = {1.0, 0.0};
+        else v = cmul(S[i * NB + c], sc);
+        if (tx > c && tx < jb) {
+          const c128 f = cmul(ctau, cmul(v, wv[tx]));
+          S[i * NB + tx].x -= f.x;
+          S[i * NB + tx].y -= f.y;
+        }
+        __syncwarp();
+        if (tx == c) S[i * NB + c] = (gr == grow) ? c128{s_beta, 0.0} : v;
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- write back: R / v into A, explicit V into Vall, partial Gram Z = V^H V for T ----
+  for (int i = ty; i < nrow; i += PTY) {
+    const int gr = r0 + i;
+    if (tx < jb) {
+      const c128 a = S[i * NB + tx];
+      p.A[(long long)gr * p.lda + j0 + tx] = a;
+      c128 v;
+      const int dcol = gr - j0;                              // column whose diagonal sits in this row
+      if (tx < dcol) v = a;
+      else if (tx == dcol) v = {1.0, 0.0};
+      else v = {0.0, 0.0};
+      p.Vall[(long long)gr * p.lda + j0 + tx] = v;
+      S[i * NB + tx] = v;
+    }
+  }
+  __syncthreads();
+  // Z[a, c] = sum_i conj(V[i,a]) V[i,c], a < c: thread (ty, tx) owns column c = tx, rows a = ty, ty+8, ...
+  for (int a = ty; a < jb; a += PTY) {
+    c128 z = {0.0, 0.0};
+    if (tx < jb && a < tx) {
+      for (int i = 0; i < nrow; ++i) {
+        const c128 x = S[i * NB + a], y = S[i * NB + tx];
+        z.x += x.x * y.x + x.y * y.y;
+        z.y += x.x * y.y - x.y * y.x;
+      }
+    }
+    p.zpart[((size_t)b * NB + a) * NB * 2 + 2 * tx] = z.x;
+    p.zpart[((size_t)b * NB + a) * NB * 2 + 2 * tx + 1] = z.y;
+  }
+  __threadfence();
+  if (G > 1) grid.sync(); else __syncthreads();
+  if (b != 0) return;
+  // ---- T (zlarft, forward/columnwise) by CTA 0 ----
+  c128* Z = S;               // reuse: [NB][NB]
+  c128* T = S + NB * NB;
+  for (int a = ty; a < NB; a += PTY) {
+    c128 z = {0.0, 0.0};
+    for (int q = 0; q < G; ++q) {
+      z.x += __ldcg(&p.zpart[((size_t)q * NB + a) * NB * 2 + 2 * tx]);
+      z.y += __ldcg(&p.zpart[((size_t)q * NB + a) * NB * 2 + 2 * tx + 1]);
+    }
+    Z[a * NB + tx] = z;
+    T[a * NB + tx] = {0.0, 0.0};
+  }
+  __syncthreads();
+  for (int c = 0; c < jb; ++c) {
+    const c128 tau = {__ldcg(&p.tau[2 * (j0 + c)]), __ldcg(&p.tau[2 * (j0 + c) + 1])};
+    // T[0:c, c] = -tau * T[0:c, 0:c] @ Z[0:c, c]
+    if (ty == 0 && tx < c) {
+      c128 s = {0.0, 0.0};
+      for (int q = tx; q < c; ++q) s = cadd(s, cmul(T[tx * NB + q], Z[q * NB + c]));
+      const c128 r = cmul(tau, s);
+      T[tx * NB + c] = {-r.x, -r.y};
+    }
+    if (ty == 0 && tx == c) T[c * NB + c] = tau;
+    __syncthreads();
+  }
+  c128* Tout = p.Tall + (size_t)(j0 / NB) * NB * NB;
+  for (int a = ty; a < NB; a += PTY) Tout[a * NB + tx] = T[a * NB + tx];
+}
+
+__global__ void k_set_identity(c128* Q, int m, int n, int ld) {
+  const long long tot = (long long)m * n;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
+    const int i = e / n, j = e % n;
+    Q[(long long)i * ld + j] = {i == j ? 1.0 : 0.0, 0.0};
+  }
+}
+
+__global__ void k_extract_r(const c128* A, int lda, int k, int n, c128* R, int ldr, int transpose) {
+  // R (k x n upper trapezoidal) from A; transpose != 0 writes R^T (n x k, ld = ldr)
+  const long long tot = (long long)k * n;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
+    const int i = e / n, j = e % n;
+    const c128 v = (j >= i) ? A[(long long)i * lda + j] : c128{0.0, 0.0};
+    if (transpose) R[(long long)j * ldr + i] = v; else R[(long long)i * ldr + j] = v;
+  }
+}
+
+int lq(Handle* h, const char* what) {
+  ++g_launch_count;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(h, e, what, __FILE__, __LINE__);
+  return 0;
+}
+
+int gemmq(Handle* h, const GemmDesc& g) {
+  cudaError_t e = zgemm_launch(g, h->stream);
+  if (e != cudaSuccess) return cuda_fail(h, e, "zgemm_launch", __FILE__, __LINE__);
+  return 0;
+}
+
+}  // namespace
+
+size_t qr_ws_elems(int m, int n) {
+  const size_t np = (n + NB - 1) / NB;
+  return 3 * (size_t)m * n + np * NB * NB + 2 * (size_t)NB * n + 4096 + (size_t)148 * NB * NB + 148 * 4 * NB;
+}
+
+// In-place economic QR of the row-major m x n matrix A (m >= n): on return Q (m x n, ld = ldq) and the upper
+// triangle of A hold the factors.  Workspace comes from the handle's bump allocator.
+int qr_factor(Handle* h, c128* A, int m, int n, int lda, c128* Q, int ldq) {
+  if (m < n) { set_error(h, "qr_factor: needs m >= n"); return TDVP_ERR_SHAPE; }
+  static bool configured = false;
+  static int max_coop = 0;
+  if (!configured) {
+    cudaFuncSetAttribute(k_qr_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, SLAB_ROWS * NB * (int)sizeof(c128));
+    int nsm = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    max_coop = nsm;
+    configured = true;
+  }
+  const int np = (n + NB - 1) / NB;
+  c128* Vall = (c128*)ws_alloc(h, sizeof(c128) * (size_t)m * lda);
+  c128* Tall = (c128*)ws_alloc(h, sizeof(c128) * (size_t)np * NB * NB);
+  c128* W = (c128*)ws_alloc(h, sizeof(c128) * (size_t)NB * n);
+  c128* W2 = (c128*)ws_alloc(h, sizeof(c128) * (size_t)NB * n);
+  double* tau = (double*)ws_alloc(h, sizeof(double) * 2 * (size_t)n);
+  double* gpart = (double*)ws_alloc(h, sizeof(double) * 2 * (size_t)max_coop * 4 * NB);
+  double* zpart = (double*)ws_alloc(h, sizeof(double) * 2 * (size_t)max_coop * NB * NB);
+  if (!Vall || !Tall || !W || !W2 || !tau || !gpart || !zpart) { set_error(h, "qr_factor: workspace"); return TDVP_ERR_ARG; }
+  TDVP_CUDA(h, cudaMemsetAsync(Vall, 0, sizeof(c128) * (size_t)m * lda, h->stream));
+  const c128 one = {1.0, 0.0}, zero = {0.0, 0.0}, mone = {-1.0, 0.0};
+
+  for (int pnl = 0; pnl < np; ++pnl) {
+    const int j0 = pnl * NB;
+    const int jb = (n - j0) < NB ? (n - j0) : NB;
+    const int mp = m - j0;
+    int rpc = SLAB_ROWS;
+    int G = (mp + rpc - 1) / rpc;
+    if (G > max_coop) { set_error(h, "qr_factor: matrix too tall for the cooperative panel kernel"); return TDVP_ERR_UNSUPPORTED; }
+    if (G < 1) G = 1;
+    // spread rows evenly
+    rpc = (mp + G - 1) / G;
+    PanelArgs pa{A, lda, m, n, j0, jb, tau, Vall, Tall, gpart, zpart, rpc};
+    void* args[] = {&pa};
+    const size_t smem = sizeof(c128) * (size_t)(rpc > 2 * NB ? rpc : 2 * NB) * NB;
+    cudaError_t e = cudaLaunchCooperativeKernel((void*)k_qr_panel, dim3(G), dim3(32, PTY), args, smem, h->stream);
+    ++g_launch_count;
+    if (e != cudaSuccess) return cuda_fail(h, e, "cudaLaunchCooperativeKernel(k_qr_panel)", __FILE__, __LINE__);
+    const int nc = n - j0 - jb;
+    if (nc > 0) {
+      // C <- (I - V T^H V^H) C,  C = A[j0:, j0+jb:]
+      c128* Vp = Vall + (long long)j0 * lda + j0;
+      c128* C = A + (long long)j0 * lda + j0 + jb;
+      c128* T = Tall + (size_t)pnl * NB * NB;
+      TDVP_TRY(gemmq(h, gemm_rowmajor(jb, nc, mp, Vp, lda, true, true, C, lda, false, W, nc, one, zero)));     // W = V^H C
+      TDVP_TRY(gemmq(h, gemm_rowmajor(jb, nc, jb, T, NB, true, true, W, nc, false, W2, nc, one, zero)));      // W2 = T^H W
+      TDVP_TRY(gemmq(h, gemm_rowmajor(mp, nc, jb, Vp, lda, false, false, W2, nc, false, C, lda, mone, one))); // C -= V W2
+    }
+  }
+  // ---- form Q = H_1 ... H_k [I; 0]  (zungqr, blocked, backward) ----
+  k_set_identity<<<148 * 2, 256, 0, h->stream>>>(Q, m, n, ldq);
+  TDVP_TRY(lq(h, "k_set_identity"));
+  for (int pnl = np - 1; pnl >= 0; --pnl) {
+    const int j0 = pnl * NB;
+    const int jb = (n - j0) < NB ? (n - j0) : NB;
+    const int mp = m - j0;
+    const int nc = n - j0;
+    c128* Vp = Vall + (long long)j0 * lda + j0;
+    c128* C = Q + (long long)j0 * ldq + j0;
+    c128* T = Tall + (size_t)pnl * NB * NB;
+    TDVP_TRY(gemmq(h, gemm_rowmajor(jb, nc, mp, Vp, lda, true, true, C, ldq, false, W, nc, one, zero)));      // W = V^H C
+    TDVP_TRY(gemmq(h, gemm_rowmajor(jb, nc, jb, T, NB, false, false, W, nc, false, W2, nc, one, zero)));     // W2 = T W
+    TDVP_TRY(gemmq(h, gemm_rowmajor(mp, nc, jb, Vp, lda, false, false, W2, nc, false, C, ldq, mone, one)));  // C -= V W2
+  }
+  return 0;
+}
+
+// Gauge shift of the centre tensor (see tdvp_qr_shift in include/tdvp_b200.h).
+int qr_shift_exec(Handle* h, int gauge, int Dl, int d, int Dr, const c128* psi, c128* site, c128* sigma) {
+  const long long N = (long long)Dl * d * Dr;
+  const int m = (gauge == TDVP_GAUGE_A) ? Dl * d : Dr * d;
+  const int n = (gauge == TDVP_GAUGE_A) ? Dr : Dl;
+  if (m < n) { set_error(h, "qr_shift: matricisation has fewer rows than columns (bond dimension rule violated)"); return TDVP_ERR_SHAPE; }
+  TDVP_TRY(ws_reserve(h, sizeof(c128) * (qr_ws_elems(m, n) + 2 * (size_t)N) + 4096));
+  c128* Awork = (c128*)ws_alloc(h, sizeof(c128) * (size_t)N);
+  if (!Awork) { set_error(h, "qr_shift: workspace"); return TDVP_ERR_ARG; }
+  if (gauge == TDVP_GAUGE_A) {
+    TDVP_CUDA(h, cudaMemcpyAsync(Awork, psi, sizeof(c128) * N, cudaMemcpyDeviceToDevice, h->stream));
+    TDVP_TRY(qr_factor(h, Awork, m, n, n, site, n));                       // site(Dl,d,k=n) = Q
+    k_extract_r<<<64, 256, 0, h->stream>>>(Awork, n, n, n, sigma, n, 0);   // sigma(k, Dr) = R
+    TDVP_TRY(lq(h, "k_extract_r"));
+  } else if (gauge == TDVP_GAUGE_B) {
+    // QR of psi^T viewed as (Dr*d) x Dl;  B = Q reshaped (Dr,d,k) -> (k,d,Dr);  sigma = R^T (Dl, k)
+    c128* Qt = (c128*)ws_alloc(h, sizeof(c128) * (size_t)N);
+    if (!Qt) { set_error(h, "qr_shift: workspace"); return TDVP_ERR_ARG; }
+    TDVP_TRY(permute_site(h, psi, Awork, Dl, d, Dr));                      // Awork[r,j,l] = psi[l,j,r]
+    TDVP_TRY(qr_factor(h, Awork, m, n, n, Qt, n));
+    TDVP_TRY(permute_site(h, Qt, site, Dr, d, n));                         // site[k,j,r] = Qt[r,j,k]
+    k_extract_r<<<64, 256, 0, h->stream>>>(Awork, n, n, n, sigma, n, 1);   // sigma(Dl, k) = R^T
+    TDVP_TRY(lq(h, "k_extract_r"));
+  } else {
+    set_error(h, "qr_shift: bad gauge");
+    return TDVP_ERR_ARG;
+  }
+  return 0;
+}
+
+int absorb_exec(Handle* h, int gauge, int Dl, int d, int Dr, int k, const c128* sigma, const c128* site, c128* out) {
+  TDVP_TRY(ws_reserve(h, 4096));
+  if (gauge == TDVP_GAUGE_A) {
+    // out(k, d*Dr) = sigma(k, Dl) . site(Dl, d*Dr)
+    return gemmq(h, gemm_rowmajor(k, d * Dr, Dl, sigma, Dl, false, false, site, (long long)d * Dr, false, out, (long long)d * Dr));
+  } else if (gauge == TDVP_GAUGE_B) {
+    // out(Dl*d, k) = site(Dl*d, Dr) . sigma(Dr, k)
+    return gemmq(h, gemm_rowmajor(Dl * d, k, Dr, site, Dr, false, false, sigma, k, false, out, k));
+  }
+  set_error(h, "absorb: bad gauge");
+  return TDVP_ERR_ARG;
+}
+
+}  // namespace tdvp

@@ -1,0 +1,272 @@
+// Complex128 GEMM on the FP64 tensor-core path of sm_100a (DMMA.8x8x4), the workhorse behind the
+// H_eff / K_eff application, the environment updates, the bond absorb and the blocked QR.
+//
+// Replaces: opt_einsum.contract -> np.tensordot -> OpenBLAS ZGEMM in the reference
+//           (pytdscf/_contraction.py:1162-1174, :1340-1352, :389-394; pytdscf/_mps_cls.py:1187-1206).
+//
+// Design notes (DESIGN.md "zgemm_dmma"):
+//  * tcgen05/UMMA has no f64 kind; on sm_100a every mma.sync f64 shape lowers to DMMA.8x8x4
+//    (cuobjdump of scripts/microbench/dmma_bench.cu), measured peak 37.0 TFLOP/s = 64 FMA/clk/SM
+//    (profiles/r1_fp64_pipe_microbench.jsonl); cuBLAS ZGEMM 8192^3 reaches 36.97 TFLOP/s.
+//  * complex product = 4 real DMMAs per (A-tile, B-tile) pair on fragments loaded as one LDS.128 per
+//    complex element (re, im together), so HBM/L2/SMEM all keep the interleaved layout of the ABI.
+//  * the FP64 pipe is ~30x slower than the SMEM crossbar needs, so the kernel is organised around
+//    keeping 8 warps x 64 independent DMMAs in flight: CTA tile 128x64, warp tile 32x32, BK = 8,
+//    4-stage cp.async (LDGSTS.128) ring, one __syncthreads per k-tile, XOR-swizzled SMEM so that
+//    every fragment LDS.128 is bank-conflict free for both operand majors.
+//  * rows of A/C and columns of B may be two-level indices (GemmDesc) so contractions such as
+//    T2[a,i,t,s] = sum_{c,j} T1[a,c,j,s] W[c,i,j,t] run on their natural layouts (no transposes).
+#include "common.cuh"
+
+namespace tdvp {
+
+unsigned long long g_launch_count = 0;
+
+namespace {
+
+constexpr int BM = 128, BN = 64, BK = 8, STAGES = 4, THREADS = 256;
+constexpr int A_STAGE = BM * BK;  // c128 elements per stage
+constexpr int B_STAGE = BN * BK;
+constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) * (int)sizeof(c128);  // 96 KiB
+
+__device__ __forceinline__ void cp_async16(c128* smem, const c128* gmem, bool pred) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  int sz = pred ? 16 : 0;  // src-size 0 => zero fill, nothing is read
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// SMEM chunk (16 B) index of tile element; the XOR keeps the 8 lanes of every LDS.128 phase on
+// distinct 16-byte bank groups (see DESIGN.md for the bank arithmetic).
+template <bool KMAJOR, int ROWS>
+__device__ __forceinline__ int tile_chunk(int r, int k) {  // r: m or n inside the tile, k in [0, BK)
+  if (KMAJOR) return r * BK + (k ^ ((r & 1) << 2));
+  return k * ROWS + (r ^ ((k & 3) << 1));
+}
+
+template <bool A_KMAJOR, bool B_KMAJOR>
+__global__ void __launch_bounds__(THREADS, 1) zgemm_dmma_kernel(const GemmDesc d) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  c128* As = reinterpret_cast<c128*>(smem_raw);
+  c128* Bs = As + STAGES * A_STAGE;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, q = lane & 3;
+  const int wm = warp & 3, wn = warp >> 2;
+  const int tile_m = blockIdx.y * BM, tile_n = blockIdx.x * BN;
+  const long long bz = blockIdx.z;
+  const c128* __restrict__ Ag = d.A + bz * d.a_batch;
+  const c128* __restrict__ Bg = d.B + bz * d.b_batch;
+  c128* __restrict__ Cg = d.C + bz * d.c_batch;
+
+  // ---- per-thread global->shared assignments (fixed for the whole k loop) ----
+  // A, K-major: 4 rows x 1 k-chunk ; A, M-major: 1 row x 4 k's
+  long long a_off[4];
+  bool a_ok[4];
+  int a_sm[4];
+  int a_kl[4];
+  if (A_KMAJOR) {
+    const int kc = tid & 7;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = (tid >> 3) + 32 * i;
+      const int m = tile_m + r;
+      a_ok[i] = m < d.M;
+      const int mm = a_ok[i] ? m : 0;
+      a_off[i] = (long long)(mm / d.a_m_inner) * d.a_m1 + (long long)(mm % d.a_m_inner) * d.a_m0;
+      a_sm[i] = tile_chunk<true, BM>(r, kc);
+      a_kl[i] = kc;
+    }
+  } else {
+    const int r = tid & 127;
+    const int m = tile_m + r;
+    const bool ok = m < d.M;
+    const int mm = ok ? m : 0;
+    const long long off = (long long)(mm / d.a_m_inner) * d.a_m1 + (long long)(mm % d.a_m_inner) * d.a_m0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = (tid >> 7) + 2 * i;
+      a_ok[i] = ok;
+      a_off[i] = off;
+      a_sm[i] = tile_chunk<false, BM>(r, k);
+      a_kl[i] = k;
+    }
+  }
+  long long b_off[2];
+  bool b_ok[2];
+  int b_sm[2];
+  int b_kl[2];
+  if (B_KMAJOR) {
+    const int kc = tid & 7;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int r = (tid >> 3) + 32 * i;
+      const int n = tile_n + r;
+      b_ok[i] = n < d.N;
+      const int nn = b_ok[i] ? n : 0;
+      b_off[i] = (long long)(nn / d.b_n_inner) * d.b_n1 + (long long)(nn % d.b_n_inner) * d.b_n0;
+      b_sm[i] = tile_chunk<true, BN>(r, kc);
+      b_kl[i] = kc;
+    }
+  } else {
+    const int r = tid & 63;
+    const int n = tile_n + r;
+    const bool ok = n < d.N;
+    const int nn = ok ? n : 0;
+    const long long off = (long long)(nn / d.b_n_inner) * d.b_n1 + (long long)(nn % d.b_n_inner) * d.b_n0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int k = (tid >> 6) + 4 * i;
+      b_ok[i] = ok;
+      b_off[i] = off;
+      b_sm[i] = tile_chunk<false, BN>(r, k);
+      b_kl[i] = k;
+    }
+  }
+
+  auto load_stage = [&](int stage, int k0) {
+    c128* as = As + stage * A_STAGE;
+    c128* bs = Bs + stage * B_STAGE;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = k0 + a_kl[i];
+      const bool p = a_ok[i] && (k < d.K);
+      cp_async16(as + a_sm[i], p ? (Ag + a_off[i] + (long long)k * d.a_k) : Ag, p);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int k = k0 + b_kl[i];
+      const bool p = b_ok[i] && (k < d.K);
+      cp_async16(bs + b_sm[i], p ? (Bg + b_off[i] + (long long)k * d.b_k) : Bg, p);
+    }
+  };
+
+  double cre[4][4][2], cim[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      cre[i][j][0] = cre[i][j][1] = 0.0;
+      cim[i][j][0] = cim[i][j][1] = 0.0;
+    }
+
+  const int KT = (d.K + BK - 1) / BK;
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < KT) load_stage(s, s * BK);
+    cp_async_commit();
+  }
+
+  const double sa = d.a_conj ? -1.0 : 1.0;
+  const double sb = d.b_conj ? -1.0 : 1.0;
+
+  for (int kt = 0; kt < KT; ++kt) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      const int nk = kt + STAGES - 1;
+      if (nk < KT) load_stage(nk % STAGES, nk * BK);
+      cp_async_commit();
+    }
+    const c128* as = As + (kt % STAGES) * A_STAGE;
+    const c128* bs = Bs + (kt % STAGES) * B_STAGE;
+#pragma unroll
+    for (int k4 = 0; k4 < BK / 4; ++k4) {
+      const int kk = k4 * 4 + q;
+      double are[4], aim[4], naim[4], bre[4], bim[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = wm * 32 + 8 * i + g;
+        const c128 v = as[tile_chunk<A_KMAJOR, BM>(r, kk)];
+        are[i] = v.x;
+        aim[i] = sa * v.y;
+        naim[i] = -aim[i];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = wn * 32 + 8 * j + g;
+        const c128 v = bs[tile_chunk<B_KMAJOR, BN>(r, kk)];
+        bre[j] = v.x;
+        bim[j] = sb * v.y;
+      }
+      // two passes so that dependent accumulations into the same tile are 32 DMMAs apart
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          dmma(cre[i][j][0], cre[i][j][1], are[i], bre[j]);
+          dmma(cim[i][j][0], cim[i][j][1], are[i], bim[j]);
+        }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          dmma(cre[i][j][0], cre[i][j][1], naim[i], bim[j]);
+          dmma(cim[i][j][0], cim[i][j][1], aim[i], bre[j]);
+        }
+    }
+  }
+  cp_async_wait<0>();
+
+  // ---- epilogue: C = alpha * acc + beta * C ----
+  const c128 alpha = d.alpha, beta = d.beta;
+  const bool use_beta = (beta.x != 0.0) || (beta.y != 0.0);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = tile_m + wm * 32 + 8 * i + g;
+    if (m >= d.M) continue;
+    const long long roff = (long long)(m / d.c_m_inner) * d.c_m1 + (long long)(m % d.c_m_inner) * d.c_m0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int n = tile_n + wn * 32 + 8 * j + 2 * q + e;
+        if (n >= d.N) continue;
+        c128* p = Cg + roff + (long long)n * d.c_n;
+        c128 acc = {cre[i][j][e], cim[i][j][e]};
+        c128 out = cmul(alpha, acc);
+        if (use_beta) out = cadd(out, cmul(beta, *p));
+        *p = out;
+      }
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t zgemm_launch(const GemmDesc& d, cudaStream_t stream) {
+  if (d.M <= 0 || d.N <= 0 || d.batch <= 0) return cudaSuccess;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(zgemm_dmma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(zgemm_dmma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(zgemm_dmma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(zgemm_dmma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    configured = true;
+  }
+  dim3 grid((d.N + BN - 1) / BN, (d.M + BM - 1) / BM, d.batch);
+  const bool ak = (d.a_k == 1), bk = (d.b_k == 1);
+  if (ak && bk)
+    zgemm_dmma_kernel<true, true><<<grid, THREADS, SMEM_BYTES, stream>>>(d);
+  else if (ak && !bk)
+    zgemm_dmma_kernel<true, false><<<grid, THREADS, SMEM_BYTES, stream>>>(d);
+  else if (!ak && bk)
+    zgemm_dmma_kernel<false, true><<<grid, THREADS, SMEM_BYTES, stream>>>(d);
+  else
+    zgemm_dmma_kernel<false, false><<<grid, THREADS, SMEM_BYTES, stream>>>(d);
+  ++g_launch_count;
+  return cudaGetLastError();
+}
+
+}  // namespace tdvp

@@ -9,11 +9,19 @@ from __future__ import annotations
 import numpy as np
 
 
+def _op_id(site: int, op: np.ndarray) -> tuple:
+    return (site, op.shape, np.ascontiguousarray(op).tobytes())
+
+
 def sop_to_mpo(dims: list[int], terms: list[tuple[complex, dict[int, np.ndarray]]]) -> list[np.ndarray]:
     """Finite-state-machine MPO of ``sum_t coef_t * prod_{p in t} O_t[p]``.
 
-    Bond channels: "not started", "done", and one channel per product term that crosses the bond.
-    Terms sharing the same left factor at the same starting site share a channel until they differ.
+    Bond channels: "not started", "done", plus shared channels for the terms crossing a bond.  Two-operator
+    terms (site a < site b) share a channel either with every term that has the same LEFT factor (a, O_a)
+    ("prefix" channel; the coefficient is applied when the term ends) or with every term that has the same
+    RIGHT factor (b, O_b) ("suffix" channel; the coefficient is applied when the term starts) -- whichever
+    factor is shared by more terms.  Star-shaped couplings (many sites to one hub) therefore cost one channel
+    per hub operator instead of one per term.  Terms with 3+ operators get a private channel.
     """
     n = len(dims)
     cleaned = []
@@ -28,8 +36,25 @@ def sop_to_mpo(dims: list[int], terms: list[tuple[complex, dict[int, np.ndarray]
                 raise ValueError(f"operator on site {s} has shape {ops[s].shape}, expected {(dims[s],) * 2}")
         cleaned.append((complex(coef), {s: np.asarray(ops[s], dtype=np.complex128) for s in sites}, sites[0], sites[-1]))
 
-    # channel lists per bond b (between site b and b+1); index into `cleaned`
-    crossing = [[t for t, (_, _, lo, hi) in enumerate(cleaned) if lo <= b < hi] for b in range(n - 1)]
+    # channel identity of each multi-site term
+    pre_count: dict = {}
+    suf_count: dict = {}
+    for coef, ops, lo, hi in cleaned:
+        if len(ops) == 2:
+            pre_count[_op_id(lo, ops[lo])] = pre_count.get(_op_id(lo, ops[lo]), 0) + 1
+            suf_count[_op_id(hi, ops[hi])] = suf_count.get(_op_id(hi, ops[hi]), 0) + 1
+    chan_of = []  # per term: (channel id, mode)
+    for t, (coef, ops, lo, hi) in enumerate(cleaned):
+        if lo == hi:
+            chan_of.append((None, "single"))
+        elif len(ops) == 2:
+            pid, sid = _op_id(lo, ops[lo]), _op_id(hi, ops[hi])
+            if suf_count[sid] >= pre_count[pid]:
+                chan_of.append((("suf",) + sid, "suffix"))
+            else:
+                chan_of.append((("pre",) + pid, "prefix"))
+        else:
+            chan_of.append((("own", t), "own"))
 
     def chan(b: int) -> dict:
         if b < 0:
@@ -37,8 +62,10 @@ def sop_to_mpo(dims: list[int], terms: list[tuple[complex, dict[int, np.ndarray]
         if b >= n - 1:
             return {"done": 0}
         m = {"start": 0, "done": 1}
-        for k, t in enumerate(crossing[b]):
-            m[t] = 2 + k
+        for t, (coef, ops, lo, hi) in enumerate(cleaned):
+            cid = chan_of[t][0]
+            if cid is not None and lo <= b < hi and cid not in m:
+                m[cid] = len(m)
         return m
 
     cores = []
@@ -50,18 +77,34 @@ def sop_to_mpo(dims: list[int], terms: list[tuple[complex, dict[int, np.ndarray]
             W[left["start"], :, :, right["start"]] = eye
         if "done" in left and "done" in right:
             W[left["done"], :, :, right["done"]] = eye
+        passed = set()
+        opened = set()
+        closed = set()
         for t, (coef, ops, lo, hi) in enumerate(cleaned):
             if p < lo or p > hi:
                 continue
+            cid, mode = chan_of[t]
             O = ops.get(p, eye)
-            if lo == hi:
+            if mode == "single":
                 W[left["start"], :, :, right["done"]] += coef * O
             elif p == lo:
-                W[left["start"], :, :, right[t]] += coef * O
+                if mode == "suffix":
+                    W[left["start"], :, :, right[cid]] += coef * O
+                elif (cid, "open") not in opened:  # prefix / own: the shared left factor is placed once
+                    W[left["start"], :, :, right[cid]] += O
+                    opened.add((cid, "open"))
             elif p == hi:
-                W[left[t], :, :, right["done"]] += O
+                if mode == "prefix":
+                    W[left[cid], :, :, right["done"]] += coef * O
+                elif mode == "own":
+                    W[left[cid], :, :, right["done"]] += coef * O
+                elif (cid, "close") not in closed:  # suffix: the shared right factor is placed once
+                    W[left[cid], :, :, right["done"]] += O
+                    closed.add((cid, "close"))
             else:
-                W[left[t], :, :, right[t]] += O
+                if (cid, p) not in passed:
+                    W[left[cid], :, :, right[cid]] += O
+                    passed.add((cid, p))
         cores.append(W)
     return cores
 
@@ -81,3 +124,14 @@ def mpo_to_dense(cores: list[np.ndarray]) -> np.ndarray:
         else:
             acc = np.einsum("ijc,ckls->ikjls", acc, W).reshape(acc.shape[0] * W.shape[1], acc.shape[1] * W.shape[2], W.shape[3])
     return acc[:, :, 0]
+
+
+def sop_to_dense(dims: list[int], terms) -> np.ndarray:
+    """Dense matrix of the operator sum (tests only)."""
+    total = None
+    for coef, ops in terms:
+        mat = np.array([[1.0 + 0j]])
+        for p, d in enumerate(dims):
+            mat = np.kron(mat, np.asarray(ops.get(p, np.eye(d)), dtype=np.complex128))
+        total = coef * mat if total is None else total + coef * mat
+    return total

@@ -1,0 +1,230 @@
+"""``Simulator``: the user-facing driver with the reference's signature plus ``backend="cuda"``.
+
+Reference: ``pytdscf/simulator_cls.py:34-592`` (constructor :58-75, ``propagate`` :160-284, time loop
+``_execute`` :332-467), ``pytdscf/wavefunction.py`` (``WFunc``) and ``pytdscf/properties.py`` (per-step
+observables and the ``<jobname>_prop/*.dat`` files).  Differences by design: there is exactly one backend
+("cuda", no dispatch, no CPU fallback), the run configuration is an explicit object instead of a mutable
+global, and the checkpoint is a plain pickle of NumPy cores instead of a ``dill`` dump of live objects.
+"""
+from __future__ import annotations
+
+import os
+import pickle
+import time as _time
+
+import numpy as np
+
+from . import units
+from ._const_cls import RunConfig
+from ._engine import Engine
+from ._mps_cuda import DeviceMPO, MPSCoefCuda
+from .model_cls import Model
+
+
+class WFunc:
+    """Wavefunction = device MPS + the operators it is measured against (reference ``wavefunction.py:34-598``)."""
+
+    def __init__(self, ci_coef: MPSCoefCuda, eng: Engine):
+        self.ci_coef = ci_coef
+        self.eng = eng
+        self._dev_ops: dict[int, DeviceMPO] = {}
+
+    def device_op(self, op) -> DeviceMPO:
+        key = id(op)
+        if key not in self._dev_ops:
+            self._dev_ops[key] = DeviceMPO(self.eng, op)
+        return self._dev_ops[key]
+
+    def expectation(self, op) -> float:
+        """Real part of <Psi|Op|Psi> (reference ``wavefunction.py:90-114`` also returns ``.real``)."""
+        return self.ci_coef.expectation(self.device_op(op)).real
+
+    def autocorr(self) -> complex:
+        return self.ci_coef.autocorr()
+
+    def norm(self) -> float:
+        return self.ci_coef.norm()
+
+    def pop_states(self) -> list[float]:
+        return self.ci_coef.pop_states()
+
+    def bonddim(self) -> list[int]:
+        return self.ci_coef.bonddim()
+
+    def propagate_SM(self, matH, stepsize: float, cfg: RunConfig):
+        self.ci_coef.propagate(stepsize, self.device_op(matH), cfg)
+
+
+class _DatFile:
+    def __init__(self, path: str):
+        self.f = open(path, "w")
+
+    def write(self, line: str):
+        self.f.write(line + "\n")
+        self.f.flush()
+
+    def close(self):
+        self.f.close()
+
+
+class Simulator:
+    """The simulator of the PyTDSCF-style API, running on one B200 through libtdvp_b200.
+
+    Args:
+        jobname (str): prefix of the output directory ``<jobname>_prop`` and of ``wf_<jobname>.pkl``.
+        model (Model): basis + operators.
+        ci_type (str): only ``"mps"``.
+        backend (str): only ``"cuda"`` -- there is no NumPy/JAX path in this package.
+        t2_trick (bool): autocorrelation by <Psi(t/2)*|Psi(t/2)> (the only implemented form).
+        verbose (int): 0..4 as in the reference (>= 2 prints per-step lines to main.log).
+        device (int | None): CUDA device ordinal (default: torch's current device).
+    """
+
+    def __init__(self, jobname: str, model: Model, ci_type: str = "mps", backend: str = "cuda", proj_gs: bool = False,
+                 t2_trick: bool = True, verbose: int = 2, device: int | None = None):
+        if backend.lower() != "cuda":
+            raise ValueError(f"backend must be 'cuda' in pytdscf_b200 (got {backend!r}); there is no NumPy/JAX dispatch")
+        if ci_type.lower() != "mps":
+            raise ValueError(f"ci_type must be 'mps' (MCTDH / full-CI coefficients are out of scope), got {ci_type}")
+        if proj_gs:
+            raise NotImplementedError("proj_gs belongs to the SPF layer, which is out of scope")
+        if not t2_trick:
+            raise NotImplementedError("only the t/2-trick autocorrelation is implemented")
+        self.jobname = jobname
+        self.model = model
+        self.model.apply_backend("cuda")
+        self.verbose = verbose
+        self.device = device
+        self.eng: Engine | None = None
+        self.history: list[dict] = []  # full-precision per-step observables (state BEFORE each step)
+        self.cfg: RunConfig | None = None
+
+    # -----------------------------------------------------------------------------------------------
+    def _engine(self) -> Engine:
+        if self.eng is None:
+            self.eng = Engine(self.device)
+        return self.eng
+
+    def save_wavefunction(self, wf: WFunc, ext: str = ""):
+        path = f"wf_{self.jobname}{ext}.pkl"
+        with open(path, "wb") as f:
+            pickle.dump({"cores": wf.ci_coef.to_numpy(), "gauges": [s.gauge for s in wf.ci_coef.sites]}, f)
+        return path
+
+    def load_wavefunction(self, ext: str = "") -> WFunc:
+        path = f"wf_{self.jobname}{ext}.pkl"
+        with open(path, "rb") as f:
+            d = pickle.load(f)
+        eng = self._engine()
+        return WFunc(MPSCoefCuda(eng, [eng.to_device(c) for c in d["cores"]], d["gauges"]), eng)
+
+    def set_initial_mps(self, cores: list, gauges: list[str] | None = None):
+        """Lower-level entry: start from explicit site tensors (site 0 = centre, the rest right-canonical)."""
+        self._initial_mps = ([np.asarray(c, dtype=np.complex128) for c in cores], gauges)
+
+    def get_initial_wavefunction(self, restart: bool = False, loadfile_ext: str = "") -> WFunc:
+        if restart:
+            return self.load_wavefunction(loadfile_ext)
+        eng = self._engine()
+        if getattr(self, "_initial_mps", None) is not None:
+            cores, gauges = self._initial_mps
+            return WFunc(MPSCoefCuda(eng, [eng.to_device(c) for c in cores], gauges), eng)
+        return WFunc(MPSCoefCuda.alloc_random(eng, self.model), eng)
+
+    # -----------------------------------------------------------------------------------------------
+    def propagate(self, stepsize: float = 0.1, maxstep: int = 5000, restart: bool = False, savefile_ext: str = "",
+                  loadfile_ext: str = "_operate", backup_interval: int = 1000, autocorr: bool = True,
+                  energy: bool = True, norm: bool = True, populations: bool = True, observables: bool = False,
+                  reduced_density=None, Δt: float | None = None, thresh_sil: float = 1.0e-09,
+                  autocorr_per_step: int = 1, observables_per_step: int = 1, energy_per_step: int = 1,
+                  norm_per_step: int = 1, populations_per_step: int = 1, parallel_split_indices=None,
+                  adaptive: bool = False, adaptive_Dmax: int = 20, adaptive_dD: int = 5,
+                  adaptive_p_proj: float = 1.0e-04, adaptive_p_svd: float = 1.0e-07, integrator: str = "lanczos",
+                  display_time_unit: str = "fs", conserve_norm: bool = True, write_files: bool = True,
+                  record_trace: bool = False):
+        """Real-time propagation; returns ``(energy, wf)`` like the reference (energy of the last evaluated step)."""
+        if reduced_density is not None:
+            raise NotImplementedError("reduced densities are a 'next' row (SURVEY 8(f1)); not in backend='cuda' yet")
+        if parallel_split_indices is not None:
+            raise NotImplementedError("site-parallel propagation is driven by pytdscf_b200.parallel (torchrun), not by this argument")
+        stepsize_au = (Δt if Δt is not None else stepsize) / units.au_in_fs
+        cfg = RunConfig(jobname=self.jobname + "_prop", relax=False, maxstep=maxstep, thresh_exp=thresh_sil,
+                        verbose=self.verbose, space=self.model.space, integrator=integrator, conserve_norm=conserve_norm,
+                        display_time_unit=display_time_unit, adaptive=adaptive)
+        self.cfg = cfg
+        wf = self.get_initial_wavefunction(restart, loadfile_ext)
+        wf.ci_coef.record_trace = record_trace
+        self.history = []
+        files = self._open_files(cfg) if write_files else None
+        if write_files:
+            self.save_wavefunction(wf, savefile_ext)
+        ham = self.model.hamiltonian
+        time_au = cfg.time_au_init
+        last_energy = None
+        elapsed = 0.0
+        for istep in range(maxstep):
+            if write_files and istep % backup_interval == backup_interval - 1:
+                self.save_wavefunction(wf, savefile_ext)
+            rec: dict = {"time_au": time_au}
+            if autocorr and istep % autocorr_per_step == 0:
+                rec["autocorr"] = wf.autocorr()
+            if energy and istep % energy_per_step == 0:
+                rec["energy"] = last_energy = wf.expectation(ham)
+            if norm and istep % norm_per_step == 0:
+                rec["norm"] = wf.norm()
+            if populations and istep % populations_per_step == 0:
+                rec["pops"] = wf.pop_states()
+            if observables and istep % observables_per_step == 0:
+                rec["expectations"] = {k: wf.expectation(op) for k, op in self.model.observables.items()}
+            self.history.append(rec)
+            if files is not None:
+                self._export(files, cfg, rec, elapsed)
+            t0 = _time.perf_counter()
+            wf.propagate_SM(ham, stepsize_au, cfg)
+            elapsed += _time.perf_counter() - t0
+            time_au += stepsize_au
+        if files is not None:
+            self.save_wavefunction(wf, savefile_ext)
+            for f in files.values():
+                f.close()
+        return (last_energy, wf)
+
+    def relax(self, *args, **kwargs):
+        raise NotImplementedError("relaxation is not implemented in backend='cuda' yet (SURVEY 3.5)")
+
+    def operate(self, *args, **kwargs):
+        raise NotImplementedError("operator application is outside the TDVP hot-path scope")
+
+    # -- output files in the reference's layout (properties.py:287-356) -----------------------------
+    def _open_files(self, cfg: RunConfig) -> dict:
+        os.makedirs(cfg.jobname, exist_ok=True)
+        return {name: _DatFile(os.path.join(cfg.jobname, fn)) for name, fn in
+                (("main", "main.log"), ("auto", "autocorr.dat"), ("pop", "populations.dat"), ("exp", "expectations.dat"))}
+
+    def _export(self, files: dict, cfg: RunConfig, rec: dict, elapsed: float):
+        unit = cfg.display_time_unit
+        t = rec["time_au"] * {"au": 1.0, "fs": units.au_in_fs, "ps": units.au_in_fs * 1e-3}[unit]
+        first = rec["time_au"] == cfg.time_au_init
+        if "autocorr" in rec:
+            if first:
+                files["auto"].write(f"# time [{unit}]\t auto-correlation")
+            a = rec["autocorr"]
+            files["auto"].write(f"{2 * t:6.9f}\t{a.real: 6.9f}{a.imag:+6.9f}j")
+        if "pops" in rec:
+            if first:
+                files["pop"].write(f"# time [{unit}]\t" + "\t".join(f"pop_{i}".ljust(11) for i in range(len(rec["pops"]))))
+            files["pop"].write(f"{t:6.9f}\t" + "".join(f"{p:6.9f}\t" for p in rec["pops"]))
+        if rec.get("expectations"):
+            if first:
+                files["exp"].write(f"# time [{unit}]\t" + "\t".join(str(k).ljust(11) for k in rec["expectations"]))
+            files["exp"].write(f"{t:6.9f}\t" + "".join(f"{v:6.9f}\t" for v in rec["expectations"].values()))
+        if cfg.verbose > 1:
+            msg = ""
+            if "autocorr" in rec:
+                msg += f"| autocorr: {rec['autocorr'].real: 6.4f}{rec['autocorr'].imag:+6.4f}i"
+            if "pops" in rec:
+                msg += "| pop" + "".join(f" {p:6.4f} " for p in rec["pops"][:3])
+            if "energy" in rec:
+                msg += f"| ene[eV]: {np.real(rec['energy']) * units.au_in_eV:10.7f} "
+            msg += f"| time[{unit}]: {t:8.3f} | elapsed[sec]:{elapsed:9.2f} "
+            files["main"].write(msg)

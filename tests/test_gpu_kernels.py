@@ -1,0 +1,292 @@
+"""GPU parity tests, kernel level: every C-ABI entry point against the oracle / golden vectors of the
+reference on the same seeded inputs.  Tolerances: complex128, relative 1e-12 per element (summation
+order differs from BLAS; the north-star bar of 1e-10 is on propagated observables, see test_gpu_propagation)."""
+import numpy as np
+import pytest
+import scipy.linalg
+
+from oracle import tdvp_oracle as orc
+from tests.golden_io import load_kernels
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from pytdscf_b200._engine import Engine
+
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def K():
+    return load_kernels()
+
+
+def crand(rng, *shape):
+    return (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)) / np.sqrt(2)
+
+
+def relerr(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def core_of(data, left=False, right=False):
+    return orc.SiteCore((0, 1, 2), 1, data, left, right)
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K_", [(1, 1, 1), (7, 5, 3), (128, 64, 8), (129, 65, 9), (200, 150, 77), (512, 384, 256), (33, 700, 130)])
+@pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (2, 0), (1, 0), (2, 1), (0, 2)])
+def test_zgemm(eng, M, N, K_, ta, tb):
+    rng = np.random.default_rng(M * 1000 + N * 10 + K_ + ta * 7 + tb)
+    A = crand(rng, *((K_, M) if ta else (M, K_)))
+    B = crand(rng, *((N, K_) if tb else (K_, N)))
+    C0 = crand(rng, M, N)
+    opA = {0: A, 1: A.T, 2: A.conj().T}[ta]
+    opB = {0: B, 1: B.T, 2: B.conj().T}[tb]
+    alpha, beta = 0.7 - 0.2j, -0.3 + 0.5j
+    ref = alpha * (opA @ opB) + beta * C0
+    Cd = eng.to_device(C0)
+    eng.zgemm(eng.to_device(A), eng.to_device(B), ta, tb, alpha, beta, Cd)
+    assert relerr(Cd.cpu().numpy(), ref) < 1e-13
+
+
+HEFF_CASES = {
+    "h_343": ("L", "Wf", "R"), "h_333": ("L", "Wd", "R"), "h_143": (None, "W_l1", "R"),
+    "h_133": (None, "Wd_l1", "R"), "h_341": ("L", "W_r1", None), "h_331": ("L", "Wd_r1", None),
+    "h_311": ("L1", None, None), "h_113": (None, None, "R1"), "h_313": ("L1", None, "R1"),
+    "h_111": (None, None, None),
+}
+
+
+@pytest.mark.parametrize("name", sorted(HEFF_CASES))
+def test_heff_term_golden(eng, K, name):
+    l_, w_, r_ = HEFF_CASES[name]
+    L = None if l_ is None else eng.to_device(K[l_])
+    R = None if r_ is None else eng.to_device(K[r_])
+    core = None if w_ is None else eng.upload_core(K[w_])
+    out = eng.heff_apply([(L, core, R, 1.0)], eng.to_device(K["psi"]))
+    assert relerr(out.cpu().numpy(), K[name]) < 1e-13
+
+
+def test_heff_term_sum_and_coef(eng, K):
+    terms_np = {"ovlp": (None, None, None), "a": (K["L"], core_of(K["Wf"]), K["R"]), "b": (K["L"], core_of(K["Wd"]), K["R"]),
+                "c": (K["L1"], None, None)}
+    ref = orc.heff_apply(terms_np, 0.37 - 0.11j, K["psi"])
+    dev = [(None, None, None, 0.37 - 0.11j),
+           (eng.to_device(K["L"]), eng.upload_core(K["Wf"]), eng.to_device(K["R"]), 1.0),
+           (eng.to_device(K["L"]), eng.upload_core(K["Wd"]), eng.to_device(K["R"]), 1.0),
+           (eng.to_device(K["L1"]), None, None, 1.0)]
+    out = eng.heff_apply(dev, eng.to_device(K["psi"]))
+    assert relerr(out.cpu().numpy(), ref) < 1e-13
+
+
+@pytest.mark.parametrize("Dl,d,Dr,wl,wr", [(37, 5, 29, 3, 4), (64, 10, 64, 6, 6), (130, 4, 131, 9, 2), (1, 8, 4, 1, 3), (4, 2, 1, 3, 1)])
+@pytest.mark.parametrize("diag", [False, True])
+def test_heff_random_shapes(eng, Dl, d, Dr, wl, wr, diag):
+    rng = np.random.default_rng(Dl + 7 * d + 13 * Dr + wl + wr + diag)
+    psi = crand(rng, Dl, d, Dr)
+    L = crand(rng, Dl, wl, Dl)
+    R = crand(rng, Dr, wr, Dr)
+    W = crand(rng, wl, d, wr) if diag else crand(rng, wl, d, d, wr)
+    ref = orc.heff_term(L, core_of(W), R, psi)
+    out = eng.heff_apply([(eng.to_device(L), eng.upload_core(W), eng.to_device(R), 1.0)], eng.to_device(psi))
+    assert relerr(out.cpu().numpy(), ref) < 1e-12
+
+
+def test_keff_golden(eng, K):
+    sig = eng.to_device(K["sig"])
+    Lk, Rk = eng.to_device(K["Lk"]), eng.to_device(K["Rk"])
+    assert relerr(eng.keff_apply([(Lk, Rk, 1.0)], sig).cpu().numpy(), K["k_33"]) < 1e-13
+    out = eng.keff_apply([(None, None, 0.5j), (Lk, Rk, 1.0)], sig).cpu().numpy()
+    assert relerr(out, 0.5j * K["sig"] + K["k_33"]) < 1e-13
+    # one-sided terms exist only with w == 1 ("summed" blocks)
+    L1 = K["Lk"][:, :1, :].copy()
+    ref = orc.keff_term(L1, None, K["sig"])
+    assert relerr(eng.keff_apply([(eng.to_device(L1), None, 1.0)], sig).cpu().numpy(), ref) < 1e-13
+    ref = orc.keff_term(None, L1, K["sig"])
+    assert relerr(eng.keff_apply([(None, eng.to_device(L1), 1.0)], sig).cpu().numpy(), ref) < 1e-13
+
+
+ENV_CASES = {
+    "e_A32f": ("A", "L", "Wf"), "e_A32d": ("A", "L", "Wd"), "e_A31f": ("A", None, "W_l1"),
+    "e_A31d": ("A", None, "Wd_l1"), "e_A11": ("A", None, None),
+    "e_B32f": ("B", "R", "Wf"), "e_B32d": ("B", "R", "Wd"), "e_B31f": ("B", None, "W_r1"),
+    "e_B31d": ("B", None, "Wd_r1"), "e_B11": ("B", None, None),
+}
+
+
+@pytest.mark.parametrize("name", sorted(ENV_CASES))
+def test_env_update_golden(eng, K, name):
+    gauge, e_, w_ = ENV_CASES[name]
+    A = eng.to_device(K["A"])
+    E = None if e_ is None else eng.to_device(K[e_])
+    core = None if w_ is None else eng.upload_core(K[w_])
+    out = eng.env_update(gauge, A, A, E, core)
+    assert out.shape == K[name].shape
+    assert relerr(out.cpu().numpy(), K[name]) < 1e-13
+
+
+def test_env_update_summed_block_and_accumulate(eng, K):
+    A = eng.to_device(K["A"])
+    L1 = K["L"][:, :1, :].copy()
+    ref = orc.env_update_term("A", K["A"], K["A"], L1, None)
+    out = eng.env_update("A", A, A, eng.to_device(L1), None)
+    assert relerr(out.cpu().numpy(), ref) < 1e-13
+    ref2 = ref + orc.env_update_term("A", K["A"], K["A"], None, core_of(K["W_l1"][..., :1].copy()))
+    eng.env_update("A", A, A, None, eng.upload_core(K["W_l1"][..., :1].copy()), out=out, accumulate=True)
+    assert relerr(out.cpu().numpy(), ref2) < 1e-13
+    R1 = K["R"][:, :1, :].copy()
+    ref = orc.env_update_term("B", K["A"], K["A"], R1, None)
+    out = eng.env_update("B", A, A, eng.to_device(R1), None)
+    assert relerr(out.cpu().numpy(), ref) < 1e-13
+
+
+@pytest.mark.parametrize("gauge", ["A", "B"])
+@pytest.mark.parametrize("Dl,d,Dr,wi,wo", [(37, 5, 29, 3, 4), (64, 10, 48, 6, 6), (130, 4, 70, 2, 5)])
+def test_env_update_random_shapes(eng, gauge, Dl, d, Dr, wi, wo):
+    rng = np.random.default_rng(Dl + 3 * d + 5 * Dr + wi + wo)
+    A = crand(rng, Dl, d, Dr)
+    if gauge == "A":
+        E, W = crand(rng, Dl, wi, Dl), crand(rng, wi, d, d, wo)
+    else:
+        E, W = crand(rng, Dr, wi, Dr), crand(rng, wo, d, d, wi)
+    ref = orc.env_update_term(gauge, A, A, E, core_of(W))
+    out = eng.env_update(gauge, eng.to_device(A), eng.to_device(A), eng.to_device(E), eng.upload_core(W))
+    assert relerr(out.cpu().numpy(), ref) < 1e-12
+
+
+# ---------------------------------------------------------------------------------------------
+def _check_qr(eng, psi, atol=1e-12):
+    A, s = orc.shift_qr(psi)
+    Ad, sd = eng.qr_shift("A", eng.to_device(psi))
+    np.testing.assert_allclose(Ad.cpu().numpy(), A, atol=atol)
+    np.testing.assert_allclose(sd.cpu().numpy(), s, atol=atol * max(1.0, np.abs(s).max()))
+    s, B = orc.shift_lq(psi)
+    Bd, sd = eng.qr_shift("B", eng.to_device(psi))
+    np.testing.assert_allclose(Bd.cpu().numpy(), B, atol=atol)
+    np.testing.assert_allclose(sd.cpu().numpy(), s, atol=atol * max(1.0, np.abs(s).max()))
+
+
+def test_qr_shift_golden(eng, K):
+    Ad, sd = eng.qr_shift("A", eng.to_device(K["g_psi"]))
+    np.testing.assert_allclose(Ad.cpu().numpy(), K["g_A"], atol=1e-13)
+    np.testing.assert_allclose(sd.cpu().numpy(), K["g_Asig"], atol=1e-13)
+    Bd, sd = eng.qr_shift("B", eng.to_device(K["g_psi"]))
+    np.testing.assert_allclose(Bd.cpu().numpy(), K["g_B"], atol=1e-13)
+    np.testing.assert_allclose(sd.cpu().numpy(), K["g_Bsig"], atol=1e-13)
+
+
+def test_qr_shift_zero_padded_matches_lapack_completion(eng, K):
+    """Exact zero columns: tau = 0 reflectors, LAPACK's null-space completion (SURVEY hard part)."""
+    Ad, sd = eng.qr_shift("A", eng.to_device(K["g_pad"]))
+    np.testing.assert_allclose(Ad.cpu().numpy(), K["g_padA"], atol=1e-14)
+    np.testing.assert_allclose(sd.cpu().numpy(), K["g_padAsig"], atol=1e-14)
+    Bd, sd = eng.qr_shift("B", eng.to_device(K["g_pad"]))
+    np.testing.assert_allclose(Bd.cpu().numpy(), K["g_padB"], atol=1e-14)
+    np.testing.assert_allclose(sd.cpu().numpy(), K["g_padBsig"], atol=1e-14)
+
+
+@pytest.mark.parametrize("Dl,d,Dr", [(1, 8, 4), (4, 8, 4), (16, 5, 16), (40, 6, 40), (64, 10, 64), (100, 7, 90), (128, 16, 128)])
+def test_qr_shift_random(eng, Dl, d, Dr):
+    rng = np.random.default_rng(Dl * 100 + d * 10 + Dr)
+    _check_qr(eng, crand(rng, Dl, d, Dr))
+
+
+def test_qr_shift_partial_rank(eng):
+    """Columns beyond the numerical rank are exactly zero (as after the padded initial sweep)."""
+    rng = np.random.default_rng(5)
+    psi = np.zeros((12, 5, 40), dtype=complex)
+    psi[:, :, :7] = crand(rng, 12, 5, 7)
+    A, s = orc.shift_qr(psi)
+    Ad, sd = eng.qr_shift("A", eng.to_device(psi))
+    np.testing.assert_allclose(Ad.cpu().numpy(), A, atol=1e-12)
+    np.testing.assert_allclose(sd.cpu().numpy(), s, atol=1e-12)
+    Q = Ad.cpu().numpy().reshape(60, 40)
+    np.testing.assert_allclose(Q.conj().T @ Q, np.eye(40), atol=1e-13)
+
+
+def test_absorb(eng):
+    rng = np.random.default_rng(11)
+    sig, site = crand(rng, 6, 9), crand(rng, 9, 4, 7)
+    np.testing.assert_allclose(eng.absorb("A", eng.to_device(sig), eng.to_device(site)).cpu().numpy(),
+                               np.tensordot(sig, site, axes=(1, 0)), atol=1e-13)
+    sig2 = crand(rng, 7, 5)
+    np.testing.assert_allclose(eng.absorb("B", eng.to_device(sig2), eng.to_device(site)).cpu().numpy(),
+                               np.tensordot(site, sig2, axes=(2, 0)), atol=1e-13)
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,kind,mat,cn,hist,scale0", [
+    ("sil_cn", "lanczos", "H", True, 0, 1.0), ("sil_free", "lanczos", "H", False, 0, 1.7),
+    ("sil_warm", "lanczos", "H", True, 9, 1.0), ("sil_nonherm", "lanczos", "Hd", False, 0, 1.7),
+    ("sia_free", "arnoldi", "G", False, 0, 1.7), ("sia_warm", "arnoldi", "G", False, 8, 1.7)])
+def test_krylov_golden(eng, K, tag, kind, mat, cn, hist, scale0):
+    """Dense operator through the H_eff interface (L = M as a (n,1,n) block, identity core and R)."""
+    n = K["kr_H"].shape[0]
+    M = {"H": K["kr_H"], "G": K["kr_G"], "Hd": K["kr_H"] + 0.05j * np.diag(np.arange(n))}[mat]
+    L = eng.to_device(M.reshape(n, 1, n))
+    psi = eng.to_device((K["kr_x0"] * scale0).reshape(n, 1, 1))
+    _, n_warm = orc.krylov_warmup(n, hist)
+    niter = eng.krylov_expm(kind, -0.05j, 1e-9, n_warm, cn, psi, hterms=[(L, None, None, 1.0)])
+    assert niter == int(K[f"kr_{tag}_niter"])
+    assert relerr(psi.cpu().numpy().reshape(-1), K[f"kr_{tag}"]) < 1e-12
+
+
+def test_krylov_exhausted_space(eng):
+    """N <= 20: the Krylov space equals the full space -> exact exponential, niter == N."""
+    rng = np.random.default_rng(3)
+    n = 6
+    H = crand(rng, n, n)
+    H = (H + H.conj().T) / 2
+    x = crand(rng, n)
+    x /= np.linalg.norm(x)
+    ref, nref = orc.sil_reference(-0.3j, lambda v: H @ v, x, 1e-9)
+    psi = eng.to_device(x.reshape(n, 1, 1))
+    niter = eng.krylov_expm("lanczos", -0.3j, 1e-9, 0, True, psi, hterms=[(eng.to_device(H.reshape(n, 1, n)), None, None, 1.0)])
+    assert niter == nref
+    np.testing.assert_allclose(psi.cpu().numpy().reshape(-1), ref, atol=1e-12)
+    # (the reference recurrence is NOT exact even when the space is exhausted: its basis is not orthonormal)
+    assert np.abs(psi.cpu().numpy().reshape(-1) - scipy.linalg.expm(-0.3j * H) @ x).max() < 1e-2
+
+
+def test_krylov_keff(eng, K):
+    D, w = 24, 3
+    rng = np.random.default_rng(8)
+    L = crand(rng, D, w, D)
+    L = (L + L.conj().transpose(2, 1, 0)) / 2
+    R = crand(rng, D, w, D)
+    R = (R + R.conj().transpose(2, 1, 0)) / 2
+    s = crand(rng, D, D)
+    s /= np.linalg.norm(s)
+    ref, nref = orc.sil_reference(+0.02j, lambda v: orc.keff_term(L, R, v), s, 1e-9)
+    sd = eng.to_device(s)
+    niter = eng.krylov_expm("lanczos", +0.02j, 1e-9, 0, True, sd, kterms=[(eng.to_device(L), eng.to_device(R), 1.0)])
+    assert niter == nref
+    assert relerr(sd.cpu().numpy(), ref) < 1e-12
+
+
+def test_inner_and_overlap(eng):
+    rng = np.random.default_rng(21)
+    a, b = crand(rng, 5, 3, 7), crand(rng, 5, 3, 7)
+    got = eng.inner(eng.to_device(a), eng.to_device(b), True)
+    assert abs(got - np.vdot(a, b)) < 1e-12
+    got = eng.inner(eng.to_device(a), eng.to_device(b), False)
+    assert abs(got - np.sum(a * b)) < 1e-12
+    blk = crand(rng, 5, 5)
+    for conj in (False, True):
+        bra = np.conj(a) if conj else a
+        ref = np.einsum("abc,abk->ck", bra, np.einsum("ibk,ai->abk", b, blk))
+        out = eng.overlap_site(eng.to_device(a), eng.to_device(b), eng.to_device(blk), conj)
+        assert relerr(out.cpu().numpy(), ref) < 1e-13
+
+
+def test_argument_errors_do_not_crash(eng, K):
+    from pytdscf_b200._lib import TdvpError
+
+    L = eng.to_device(K["L"])  # w = 3 with an identity core -> unsupported, as in the reference (gap cores crash there)
+    with pytest.raises(TdvpError):
+        eng.heff_apply([(L, None, None, 1.0)], eng.to_device(K["psi"]))
