@@ -65,6 +65,10 @@ int tdvp_abi_version(void);
 unsigned long long tdvp_launch_count(void);
 int tdvp_get_stats(tdvp_handle_t h, unsigned long long* solves, unsigned long long* matvecs, double* flops);
 int tdvp_reset_stats(tdvp_handle_t h);
+/* Per-launch CUDA-event timing of the DMMA ZGEMM kernel on its launching stream (bench.py roofline): collects what
+ * was recorded so far into (ms, 8*M*N*K flops, launches), optionally resets the totals, then switches recording
+ * on/off.  Synchronises on the recorded events. */
+int tdvp_gemm_profile(int enable, int reset, double* ms, double* flops, unsigned long long* launches);
 
 /* ---- contractions ------------------------------------------------------------------------------ */
 /* out(Dl,d,Dr) = sum_terms coef * L.W.R.psi  -- replaces multiplyH_MPS_direct_MPO.dot

@@ -268,3 +268,9 @@ class Engine:
 
     def reset_stats(self):
         self.lib.tdvp_reset_stats(self.h)
+
+    def gemm_profile(self, enable: bool, reset: bool = False) -> dict:
+        """Collect the per-launch GEMM timings recorded so far, then switch recording on/off."""
+        ms, fl, n = C.c_double(0.0), C.c_double(0.0), C.c_ulonglong(0)
+        self.lib.tdvp_gemm_profile(int(enable), int(reset), C.byref(ms), C.byref(fl), C.byref(n))
+        return {"ms": ms.value, "flops": fl.value, "launches": n.value}

@@ -116,6 +116,12 @@ int tdvp_reset_stats(tdvp_handle_t h) {
   return 0;
 }
 
+int tdvp_gemm_profile(int enable, int reset, double* ms, double* flops, unsigned long long* launches) {
+  tdvp::gemm_profile_collect(ms, flops, launches, reset != 0);
+  tdvp::gemm_profile_enable(enable != 0);
+  return 0;
+}
+
 int tdvp_heff_apply(tdvp_handle_t h, const tdvp_heff_term* terms, int nterms, int Dl, int d, int Dr,
                     const tdvp_c128* psi, tdvp_c128* out) {
   H_CHECK(h);

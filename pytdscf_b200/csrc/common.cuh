@@ -64,6 +64,9 @@ struct GemmDesc {
 cudaError_t zgemm_launch(const GemmDesc& d, cudaStream_t stream);
 // Number of kernel launches issued through this library since load (bench.py's gpu_launches claim).
 extern unsigned long long g_launch_count;
+// Per-launch CUDA-event timing of the GEMM kernel (off by default; used by bench.py for the roofline).
+void gemm_profile_enable(bool on);
+void gemm_profile_collect(double* ms, double* flops, unsigned long long* launches, bool reset);
 
 // Plain row-major helpers
 inline GemmDesc gemm_rowmajor(int M, int N, int K, const c128* A, long long lda, bool transA, bool conjA,

@@ -16,11 +16,50 @@
 //    every fragment LDS.128 is bank-conflict free for both operand majors.
 //  * rows of A/C and columns of B may be two-level indices (GemmDesc) so contractions such as
 //    T2[a,i,t,s] = sum_{c,j} T1[a,c,j,s] W[c,i,j,t] run on their natural layouts (no transposes).
+#include <utility>
+#include <vector>
+
 #include "common.cuh"
 
 namespace tdvp {
 
 unsigned long long g_launch_count = 0;
+
+// ---- optional per-launch timing of the GEMM kernel (bench.py roofline): CUDA events on the launching stream ----
+namespace {
+struct GemmProfile {
+  bool enabled = false;
+  std::vector<cudaEvent_t> pool;   // recycled events
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+  double flops = 0.0;
+  double ms = 0.0;
+  unsigned long long launches = 0;
+  cudaEvent_t get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+  }
+} g_prof;
+}  // namespace
+
+void gemm_profile_enable(bool on) { g_prof.enabled = on; }
+
+void gemm_profile_collect(double* ms, double* flops, unsigned long long* launches, bool reset) {
+  for (auto& pr : g_prof.pending) {
+    cudaEventSynchronize(pr.second);
+    float t = 0.f;
+    cudaEventElapsedTime(&t, pr.first, pr.second);
+    g_prof.ms += t;
+    g_prof.pool.push_back(pr.first);
+    g_prof.pool.push_back(pr.second);
+  }
+  g_prof.pending.clear();
+  if (ms) *ms = g_prof.ms;
+  if (flops) *flops = g_prof.flops;
+  if (launches) *launches = g_prof.launches;
+  if (reset) { g_prof.ms = 0.0; g_prof.flops = 0.0; g_prof.launches = 0; }
+}
 
 namespace {
 
@@ -257,6 +296,12 @@ cudaError_t zgemm_launch(const GemmDesc& d, cudaStream_t stream) {
   }
   dim3 grid((d.N + BN - 1) / BN, (d.M + BM - 1) / BM, d.batch);
   const bool ak = (d.a_k == 1), bk = (d.b_k == 1);
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (g_prof.enabled) {
+    ev0 = g_prof.get();
+    ev1 = g_prof.get();
+    cudaEventRecord(ev0, stream);
+  }
   if (ak && bk)
     zgemm_dmma_kernel<true, true><<<grid, THREADS, SMEM_BYTES, stream>>>(d);
   else if (ak && !bk)
@@ -266,6 +311,12 @@ cudaError_t zgemm_launch(const GemmDesc& d, cudaStream_t stream) {
   else
     zgemm_dmma_kernel<false, false><<<grid, THREADS, SMEM_BYTES, stream>>>(d);
   ++g_launch_count;
+  if (g_prof.enabled) {
+    cudaEventRecord(ev1, stream);
+    g_prof.pending.emplace_back(ev0, ev1);
+    g_prof.flops += 8.0 * (double)d.M * (double)d.N * (double)d.K * (double)d.batch;
+    ++g_prof.launches;
+  }
   return cudaGetLastError();
 }
 
