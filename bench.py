@@ -331,6 +331,7 @@ def run_cuda(args):
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop()
     prof = eng.gemm_profile(False)
+    breakdown = eng.profile_breakdown()
     st = eng.stats()
     launches = st["launches"] - launches0
     trace = np.array(mps.trace)
@@ -417,6 +418,17 @@ def run_cuda(args):
                      "peak_source": "measured FP64 DMMA peak of this pool's B200 (profiles/r1_fp64_pipe_microbench.jsonl; "
                                     "MEASURED_PEAKS.json has no FP64 entry; cuBLAS ZGEMM 8192^3 = 36.97 TFLOP/s)"},
     }
+    # per-label CUDA-event breakdown of the timed region (share of the step per kernel family)
+    top = sorted(breakdown.items(), key=lambda kv: -kv[1]["ms"])
+    out["breakdown_top"] = {k: {"share": round(v["ms"] / ms, 4), "launches": v["launches"],
+                                "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["ms"] > 0 and v["flops"] > 0 else None}
+                            for k, v in top[:12]}
+    try:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", f"breakdown_{wl.name}.json"), "w") as f:
+            json.dump({"ms_timed_region": ms, "steps": args.steps, "labels": breakdown}, f, indent=1)
+    except OSError:
+        pass
     if e2e is not None:
         out["e2e"] = e2e
     if world == 1 and not args.no_cpu_baseline:

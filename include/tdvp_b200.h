@@ -69,6 +69,9 @@ int tdvp_reset_stats(tdvp_handle_t h);
  * was recorded so far into (ms, 8*M*N*K flops, launches), optionally resets the totals, then switches recording
  * on/off.  Synchronises on the recorded events. */
 int tdvp_gemm_profile(int enable, int reset, double* ms, double* flops, unsigned long long* launches);
+/* Per-label breakdown of everything recorded while profiling was on, as a JSON object written to `out`
+ * (truncated to cap); returns the size needed. */
+size_t tdvp_profile_json(char* out, size_t cap);
 
 /* ---- contractions ------------------------------------------------------------------------------ */
 /* out(Dl,d,Dr) = sum_terms coef * L.W.R.psi  -- replaces multiplyH_MPS_direct_MPO.dot

@@ -274,3 +274,11 @@ class Engine:
         ms, fl, n = C.c_double(0.0), C.c_double(0.0), C.c_ulonglong(0)
         self.lib.tdvp_gemm_profile(int(enable), int(reset), C.byref(ms), C.byref(fl), C.byref(n))
         return {"ms": ms.value, "flops": fl.value, "launches": n.value}
+
+    def profile_breakdown(self) -> dict:
+        """Per-label totals (ms, flops, launches) of everything recorded since the last reset."""
+        import json
+
+        buf = C.create_string_buffer(1 << 16)
+        self.lib.tdvp_profile_json(buf, len(buf))
+        return json.loads(buf.value.decode())

@@ -117,9 +117,16 @@ int tdvp_reset_stats(tdvp_handle_t h) {
 }
 
 int tdvp_gemm_profile(int enable, int reset, double* ms, double* flops, unsigned long long* launches) {
-  tdvp::gemm_profile_collect(ms, flops, launches, reset != 0);
-  tdvp::gemm_profile_enable(enable != 0);
+  tdvp::prof_collect(false);
+  tdvp::prof_gemm_totals(ms, flops, launches);
+  if (reset) tdvp::prof_collect(true);
+  tdvp::prof_enable(enable != 0);
   return 0;
+}
+
+size_t tdvp_profile_json(char* out, size_t cap) {
+  tdvp::prof_collect(false);
+  return tdvp::prof_json(out, cap);
 }
 
 int tdvp_heff_apply(tdvp_handle_t h, const tdvp_heff_term* terms, int nterms, int Dl, int d, int Dr,

@@ -58,15 +58,29 @@ struct GemmDesc {
   long long c_m1 = 0, c_m0 = 0, c_n = 1;
   c128 alpha = {1.0, 0.0};
   c128 beta = {0.0, 0.0};
+  const char* tag = "gemm";   // profiling label (static string)
 };
 
 // Launch the DMMA ZGEMM on `stream`.  Returns cudaGetLastError() of the launch.
 cudaError_t zgemm_launch(const GemmDesc& d, cudaStream_t stream);
 // Number of kernel launches issued through this library since load (bench.py's gpu_launches claim).
 extern unsigned long long g_launch_count;
-// Per-launch CUDA-event timing of the GEMM kernel (off by default; used by bench.py for the roofline).
-void gemm_profile_enable(bool on);
-void gemm_profile_collect(double* ms, double* flops, unsigned long long* launches, bool reset);
+// Per-launch CUDA-event timing (off by default; used by bench.py for the roofline and the per-kernel breakdown).
+// Every launch site brackets its kernel with prof_begin/prof_end on the launching stream; totals are kept per label.
+void prof_enable(bool on);
+bool prof_enabled();
+void prof_begin(cudaStream_t stream, const char* label, double flops, bool is_gemm);
+void prof_end(cudaStream_t stream);
+void prof_collect(bool reset);                         // resolve pending events into the per-label totals
+void prof_gemm_totals(double* ms, double* flops, unsigned long long* launches);
+size_t prof_json(char* out, size_t cap);               // {"label": {"ms":..,"flops":..,"launches":..}, ...}
+struct ProfScope {
+  cudaStream_t s; bool on;
+  ProfScope(cudaStream_t stream, const char* label, double flops = 0.0, bool is_gemm = false) : s(stream), on(prof_enabled()) {
+    if (on) prof_begin(s, label, flops, is_gemm);
+  }
+  ~ProfScope() { if (on) prof_end(s); }
+};
 
 // Plain row-major helpers
 inline GemmDesc gemm_rowmajor(int M, int N, int K, const c128* A, long long lda, bool transA, bool conjA,
@@ -83,6 +97,8 @@ inline GemmDesc gemm_rowmajor(int M, int N, int K, const c128* A, long long lda,
   g.alpha = alpha; g.beta = beta;
   return g;
 }
+
+inline GemmDesc tagged(GemmDesc g, const char* tag) { g.tag = tag; return g; }
 
 __host__ __device__ inline c128 cmul(c128 a, c128 b) { return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
 __host__ __device__ inline c128 cadd(c128 a, c128 b) { return {a.x + b.x, a.y + b.y}; }

@@ -122,19 +122,19 @@ int gemm(Handle* h, const GemmDesc& g) {
 }
 
 int axpby(Handle* h, const c128* x, c128* y, long long n, c128 alpha, c128 beta) {
-  axpby_kernel<<<grid_for(n, 256), 256, 0, h->stream>>>(x, y, n, alpha, beta);
+  { ProfScope _ps(h->stream, "aux.axpby_kernel"); axpby_kernel<<<grid_for(n, 256), 256, 0, h->stream>>>(x, y, n, alpha, beta); }
   return launch_check(h, "axpby_kernel");
 }
 
 // stage 2 with a full core: T2[a,i,t,s] = alpha * sum_{c,j} Wp[(c,j),(i,t)] T1[a,c,j,s] + beta*T2
 int stage2_full(Handle* h, const c128* T1, const c128* Wp, c128* T2, int Dl, int wl, int d, int wr, int Dr,
-                c128 alpha, c128 beta) {
+                c128 alpha, c128 beta, const char* tag) {
   GemmDesc g;
   g.M = Dl * Dr; g.N = d * wr; g.K = wl * d;
   g.A = T1; g.a_m_inner = Dr; g.a_m1 = (long long)wl * d * Dr; g.a_m0 = 1; g.a_k = Dr;
   g.B = Wp; g.b_n_inner = 1; g.b_n1 = 1; g.b_n0 = 0; g.b_k = (long long)d * wr;
   g.C = T2; g.c_m_inner = Dr; g.c_m1 = (long long)d * wr * Dr; g.c_m0 = 1; g.c_n = Dr;
-  g.alpha = alpha; g.beta = beta;
+  g.alpha = alpha; g.beta = beta; g.tag = tag;
   return gemm(h, g);
 }
 
@@ -142,7 +142,7 @@ int stage2_diag(Handle* h, const c128* T1, const c128* Wd, c128* T2, int Dl, int
                 c128 alpha, c128 beta) {
   const int threads = Dr >= 256 ? 256 : (Dr >= 128 ? 128 : (Dr >= 64 ? 64 : 32));
   dim3 grid((Dr + threads - 1) / threads, d, Dl);
-  diag_mid_kernel<<<grid, threads, sizeof(c128) * wl * wr, h->stream>>>(T1, Wd, T2, Dl, wl, d, wr, Dr, alpha, beta);
+  { ProfScope _ps(h->stream, "aux.diag_mid_kernel"); diag_mid_kernel<<<grid, threads, sizeof(c128) * wl * wr, h->stream>>>(T1, Wd, T2, Dl, wl, d, wr, Dr, alpha, beta); }
   return launch_check(h, "diag_mid_kernel");
 }
 
@@ -212,6 +212,7 @@ int heff_term_exec(Handle* h, const tdvp_heff_term& t, int Dl, int d, int Dr, co
     if (!dst) { set_error(h, "workspace exhausted (heff T1)"); return TDVP_ERR_ARG; }
     GemmDesc g = gemm_rowmajor(Dl * wl, d * Dr, Dl, L, Dl, false, false, cur, (long long)d * Dr, false, dst,
                                (long long)d * Dr, last ? coef : one, last ? beta_out : zero);
+    g.tag = "heff.s1";
     if ((rc = gemm(h, g))) return rc;
     cur = dst;
   }
@@ -225,11 +226,11 @@ int heff_term_exec(Handle* h, const tdvp_heff_term& t, int Dl, int d, int Dr, co
       if (!Wp) {
         c128* tmp = (c128*)ws_alloc(h, sizeof(c128) * (size_t)wl * d * d * wr);
         if (!tmp) { set_error(h, "workspace exhausted (Wp)"); return TDVP_ERR_ARG; }
-        permute_w_kernel<<<grid_for((long long)wl * d * d * wr, 128, 64), 128, 0, h->stream>>>(W, tmp, wl, d, wr, 0);
+        { ProfScope _ps(h->stream, "aux.permute_w_kernel"); permute_w_kernel<<<grid_for((long long)wl * d * d * wr, 128, 64), 128, 0, h->stream>>>(W, tmp, wl, d, wr, 0); }
         if ((rc = launch_check(h, "permute_w_kernel"))) return rc;
         Wp = tmp;
       }
-      rc = stage2_full(h, cur, Wp, dst, Dl, wl, d, wr, Dr, last ? coef : one, last ? beta_out : zero);
+      rc = stage2_full(h, cur, Wp, dst, Dl, wl, d, wr, Dr, last ? coef : one, last ? beta_out : zero, "heff.s2");
     } else {
       rc = stage2_diag(h, cur, W, dst, Dl, wl, d, wr, Dr, last ? coef : one, last ? beta_out : zero);
     }
@@ -240,6 +241,7 @@ int heff_term_exec(Handle* h, const tdvp_heff_term& t, int Dl, int d, int Dr, co
   if (R) {
     GemmDesc g = gemm_rowmajor(Dl * d, Dr, wr * Dr, cur, (long long)wr * Dr, false, false, R, (long long)wr * Dr, true,
                                out, Dr, coef, beta_out);
+    g.tag = "heff.s3";
     if ((rc = gemm(h, g))) return rc;
   } else if (!L && !W) {
     if ((rc = axpby(h, psi, out, N, coef, beta_out))) return rc;
@@ -268,8 +270,10 @@ int keff_term_exec(Handle* h, const tdvp_keff_term& t, int Dl, int Dr, const c12
     c128* T = (c128*)ws_alloc(h, sizeof(c128) * (size_t)Dl * w * Dr);
     if (!T) { set_error(h, "workspace exhausted (keff T)"); return TDVP_ERR_ARG; }
     GemmDesc g1 = gemm_rowmajor(Dl * w, Dr, Dl, L, Dl, false, false, sigma, Dr, false, T, Dr);
+    g1.tag = "keff.g1";
     if ((rc = gemm(h, g1))) return rc;
     GemmDesc g2 = gemm_rowmajor(Dl, Dr, w * Dr, T, (long long)w * Dr, false, false, R, (long long)w * Dr, true, out, Dr, coef, beta_out);
+    g2.tag = "keff.g2";
     if ((rc = gemm(h, g2))) return rc;
   } else if (L || R) {
     if (w != 1) {
@@ -278,11 +282,11 @@ int keff_term_exec(Handle* h, const tdvp_keff_term& t, int Dl, int Dr, const c12
     }
     if (L) {
       h->heff_flops += 8.0 * (double)Dl * Dl * Dr;
-      GemmDesc g = gemm_rowmajor(Dl, Dr, Dl, L, Dl, false, false, sigma, Dr, false, out, Dr, coef, beta_out);
+      GemmDesc g = tagged(gemm_rowmajor(Dl, Dr, Dl, L, Dl, false, false, sigma, Dr, false, out, Dr, coef, beta_out), "keff.one");
       if ((rc = gemm(h, g))) return rc;
     } else {
       h->heff_flops += 8.0 * (double)Dl * Dr * Dr;
-      GemmDesc g = gemm_rowmajor(Dl, Dr, Dr, sigma, Dr, false, false, R, Dr, true, out, Dr, coef, beta_out);
+      GemmDesc g = tagged(gemm_rowmajor(Dl, Dr, Dr, sigma, Dr, false, false, R, Dr, true, out, Dr, coef, beta_out), "keff.one");
       if ((rc = gemm(h, g))) return rc;
     }
   } else {
@@ -300,7 +304,7 @@ int keff_apply_exec(Handle* h, const tdvp_keff_term* terms, int nterms, int Dl, 
 
 int permute_site(Handle* h, const c128* in, c128* out, int Dl, int d, int Dr) {
   dim3 grid((Dr + 31) / 32, (Dl + 31) / 32, d), block(32, 8);
-  permute_site_kernel<<<grid, block, 0, h->stream>>>(in, out, Dl, d, Dr);
+  { ProfScope _ps(h->stream, "aux.permute_site_kernel"); permute_site_kernel<<<grid, block, 0, h->stream>>>(in, out, Dl, d, Dr); }
   return launch_check(h, "permute_site_kernel");
 }
 
@@ -323,14 +327,14 @@ static int env_update_A(Handle* h, int Dl, int d, int Dr, const c128* bra, const
   if (E) {
     c128* X = (c128*)ws_alloc(h, sizeof(c128) * (size_t)Dl * w_in * d * Dr);
     if (!X) { set_error(h, "workspace exhausted (env X)"); return TDVP_ERR_ARG; }
-    GemmDesc g = gemm_rowmajor(Dl * w_in, d * Dr, Dl, E, Dl, false, false, ket, (long long)d * Dr, false, X, (long long)d * Dr);
+    GemmDesc g = tagged(gemm_rowmajor(Dl * w_in, d * Dr, Dl, E, Dl, false, false, ket, (long long)d * Dr, false, X, (long long)d * Dr), "env.s1");
     if ((rc = gemm(h, g))) return rc;
     cur = X;
   }
   if (W) {
     c128* Y = (c128*)ws_alloc(h, sizeof(c128) * (size_t)Dl * d * w_out * Dr);
     if (!Y) { set_error(h, "workspace exhausted (env Y)"); return TDVP_ERR_ARG; }
-    if (w_kind == TDVP_KIND_FULL) rc = stage2_full(h, cur, Wp, Y, Dl, w_in, d, w_out, Dr, one, zero);
+    if (w_kind == TDVP_KIND_FULL) rc = stage2_full(h, cur, Wp, Y, Dl, w_in, d, w_out, Dr, one, zero, "env.s2");
     else rc = stage2_diag(h, cur, W, Y, Dl, w_in, d, w_out, Dr, one, zero);
     if (rc) return rc;
     cur = Y;
@@ -338,6 +342,7 @@ static int env_update_A(Handle* h, int Dl, int d, int Dr, const c128* bra, const
   // out[i,(q,j)] = sum_{(m,r)} conj(bra[(m,r), i]) * cur[(m,r),(q,j)]
   GemmDesc g = gemm_rowmajor(Dr, w_out * Dr, Dl * d, bra, Dr, true, true, cur, (long long)w_out * Dr, false, out,
                              (long long)w_out * Dr, one, accumulate ? one : zero);
+  g.tag = "env.s3";
   return gemm(h, g);
 }
 
@@ -351,7 +356,7 @@ int env_update_exec(Handle* h, int gauge, int Dl, int d, int Dr, const c128* bra
     if (W && w_kind == TDVP_KIND_FULL) {
       c128* tmp = (c128*)ws_alloc(h, sizeof(c128) * (size_t)w_in * d * d * w_out);
       if (!tmp) { set_error(h, "workspace exhausted (env Wp)"); return TDVP_ERR_ARG; }
-      permute_w_kernel<<<grid_for((long long)w_in * d * d * w_out, 128, 64), 128, 0, h->stream>>>(W, tmp, w_in, d, w_out, 0);
+      { ProfScope _ps(h->stream, "aux.permute_w_kernel"); permute_w_kernel<<<grid_for((long long)w_in * d * d * w_out, 128, 64), 128, 0, h->stream>>>(W, tmp, w_in, d, w_out, 0); }
       if ((rc = launch_check(h, "permute_w_kernel"))) return rc;
       Wp = tmp;
     }
@@ -373,12 +378,12 @@ int env_update_exec(Handle* h, int gauge, int Dl, int d, int Dr, const c128* bra
       c128* tmp = (c128*)ws_alloc(h, sizeof(c128) * (size_t)w_in * d * d * w_out);
       if (!tmp) { set_error(h, "workspace exhausted (env Wrev)"); return TDVP_ERR_ARG; }
       if (w_kind == TDVP_KIND_FULL) {
-        permute_w_kernel<<<grid_for((long long)w_in * d * d * w_out, 128, 64), 128, 0, h->stream>>>(W, tmp, w_in, d, w_out, 1);
+        { ProfScope _ps(h->stream, "aux.permute_w_kernel"); permute_w_kernel<<<grid_for((long long)w_in * d * d * w_out, 128, 64), 128, 0, h->stream>>>(W, tmp, w_in, d, w_out, 1); }
         if ((rc = launch_check(h, "permute_w_kernel"))) return rc;
         Wmp = tmp;
         Wm = tmp;  // only the permuted form is consumed for full cores
       } else {
-        permute_wd_rev_kernel<<<grid_for((long long)w_in * d * w_out, 128, 64), 128, 0, h->stream>>>(W, tmp, w_in, d, w_out);
+        { ProfScope _ps(h->stream, "aux.permute_wd_rev_kernel"); permute_wd_rev_kernel<<<grid_for((long long)w_in * d * w_out, 128, 64), 128, 0, h->stream>>>(W, tmp, w_in, d, w_out); }
         if ((rc = launch_check(h, "permute_wd_rev_kernel"))) return rc;
         Wm = tmp;
       }
@@ -398,8 +403,10 @@ int overlap_site_exec(Handle* h, int Dlb, int Dlk, int d, int Drb, int Drk, cons
   c128* X = (c128*)ws_alloc(h, sizeof(c128) * (size_t)Dlb * d * Drk);
   if (!X) { set_error(h, "workspace exhausted (overlap)"); return TDVP_ERR_ARG; }
   GemmDesc g1 = gemm_rowmajor(Dlb, d * Drk, Dlk, block, Dlk, false, false, ket, (long long)d * Drk, false, X, (long long)d * Drk);
+  g1.tag = "ovlp.g1";
   TDVP_TRY(gemm(h, g1));
   GemmDesc g2 = gemm_rowmajor(Drb, Drk, Dlb * d, bra, Drb, true, conj_bra != 0, X, Drk, false, out, Drk);
+  g2.tag = "ovlp.g2";
   TDVP_TRY(gemm(h, g2));
   h->ws_top = top;
   return 0;

@@ -376,7 +376,7 @@ int lc(Handle* h, const char* what) {
 }  // namespace
 
 int inner_exec(Handle* h, long long n, const c128* bra, const c128* ket, int conj, c128* host_out) {
-  k_dot<<<red_blocks(n), RED_THREADS, 0, h->stream>>>(bra, ket, n, conj, h->d_partial, h->d_counter, h->d_scal + S_TMP);
+  { ProfScope _ps(h->stream, "vec.k_dot"); k_dot<<<red_blocks(n), RED_THREADS, 0, h->stream>>>(bra, ket, n, conj, h->d_partial, h->d_counter, h->d_scal + S_TMP); }
   TDVP_TRY(lc(h, "k_dot"));
   TDVP_CUDA(h, cudaMemcpyAsync(h->h_scal + S_TMP, h->d_scal + S_TMP, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   TDVP_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -416,16 +416,16 @@ int krylov_expm_exec(Handle* h, int kind, double scale_re, double scale_im, doub
   };
 
   // ---- v0 ----
-  k_set_scalars<<<1, 32, 0, st>>>(S + S_AREAL, 1, 1.0);
+  { ProfScope _ps(st, "vec.k_set_scalars"); k_set_scalars<<<1, 32, 0, st>>>(S + S_AREAL, 1, 1.0); }
   TDVP_TRY(lc(h, "k_set_scalars"));
   TDVP_CUDA(h, cudaMemcpyAsync(V, psi, sizeof(c128) * N, cudaMemcpyDeviceToDevice, st));
   if (!conserve_norm) {
-    k_norm<<<nb, RED_THREADS, 0, st>>>(V, N, h->d_partial, h->d_counter, S + S_B0);
+    { ProfScope _ps(st, "vec.k_norm"); k_norm<<<nb, RED_THREADS, 0, st>>>(V, N, h->d_partial, h->d_counter, S + S_B0); }
     TDVP_TRY(lc(h, "k_norm"));
     TDVP_CUDA(h, cudaMemcpyAsync(h->h_scal + S_B0, S + S_B0, sizeof(double), cudaMemcpyDeviceToHost, st));
     TDVP_CUDA(h, cudaStreamSynchronize(st));
     if (h->h_scal[S_B0] == 0.0) { set_error(h, "Initial psi has zero norm."); return TDVP_ERR_ZERO_NORM; }
-    k_scale_dev<<<vb, RED_THREADS, 0, st>>>(V, V, N, S + S_B0, 0, 0.0);
+    { ProfScope _ps(st, "vec.k_scale_dev"); k_scale_dev<<<vb, RED_THREADS, 0, st>>>(V, V, N, S + S_B0, 0, 0.0); }
     TDVP_TRY(lc(h, "k_scale_dev"));
   }
   ++h->krylov_solves;
@@ -438,29 +438,29 @@ int krylov_expm_exec(Handle* h, int kind, double scale_re, double scale_im, doub
     const c128* src = (l == 0) ? psi : (kind == TDVP_KRYLOV_ARNOLDI ? V + (size_t)(nvec - 1) * N : V + (size_t)l * N);
     TDVP_TRY(matvec(src, w));
     if (!conserve_norm && l == 0) {
-      k_scale_dev<<<vb, RED_THREADS, 0, st>>>(w, w, N, S + S_B0, 0, 0.0);
+      { ProfScope _ps(st, "vec.k_scale_dev"); k_scale_dev<<<vb, RED_THREADS, 0, st>>>(w, w, N, S + S_B0, 0, 0.0); }
       TDVP_TRY(lc(h, "k_scale_dev"));
     }
     if (kind == TDVP_KRYLOV_LANCZOS_REF) {
-      k_dot<<<nb, RED_THREADS, 0, st>>>(V, w, N, 1, h->d_partial, h->d_counter, S + S_ALPHA + 2 * l);
+      { ProfScope _ps(st, "vec.k_dot"); k_dot<<<nb, RED_THREADS, 0, st>>>(V, w, N, 1, h->d_partial, h->d_counter, S + S_ALPHA + 2 * l); }
       TDVP_TRY(lc(h, "k_dot"));
-      k_lanczos_update<<<nb, RED_THREADS, 0, st>>>(w, V + (size_t)l * N, l > 0 ? V + (size_t)(l - 1) * N : nullptr, N,
+      { ProfScope _ps(st, "vec.k_lanczos_update"); k_lanczos_update<<<nb, RED_THREADS, 0, st>>>(w, V + (size_t)l * N, l > 0 ? V + (size_t)(l - 1) * N : nullptr, N,
                                                      S + S_ALPHA + 2 * l, S + S_BETA + (l > 0 ? l - 1 : 0), h->d_partial,
-                                                     h->d_counter, S + S_BETA + l, S + S_AREAL);
+                                                     h->d_counter, S + S_BETA + l, S + S_AREAL); }
       TDVP_TRY(lc(h, "k_lanczos_update"));
     } else {
       double* hcol = S + S_HESS + 2 * (l * HLD);
-      k_arnoldi_dots<<<nb, RED_THREADS, 0, st>>>(V, N, nvec, w, N, h->d_partial, h->d_counter, hcol);
+      { ProfScope _ps(st, "vec.k_arnoldi_dots"); k_arnoldi_dots<<<nb, RED_THREADS, 0, st>>>(V, N, nvec, w, N, h->d_partial, h->d_counter, hcol); }
       TDVP_TRY(lc(h, "k_arnoldi_dots"));
-      k_arnoldi_update<<<nb, RED_THREADS, 0, st>>>(V, N, nvec, w, N, hcol, h->d_partial, h->d_counter, S + S_BETA + l);
+      { ProfScope _ps(st, "vec.k_arnoldi_update"); k_arnoldi_update<<<nb, RED_THREADS, 0, st>>>(V, N, nvec, w, N, hcol, h->d_partial, h->d_counter, S + S_BETA + l); }
       TDVP_TRY(lc(h, "k_arnoldi_update"));
       if (l + 1 < HLD) {
-        k_store_beta_hess<<<1, 1, 0, st>>>(S + S_HESS, l, S + S_BETA + l);
+        { ProfScope _ps(st, "vec.k_store_beta_hess"); k_store_beta_hess<<<1, 1, 0, st>>>(S + S_HESS, l, S + S_BETA + l); }
         TDVP_TRY(lc(h, "k_store_beta_hess"));
       }
     }
     // w /= beta when beta >= EPS (Lanczos) / > EPS (Arnoldi): decided on device, mirrored on host below
-    k_scale_dev<<<vb, RED_THREADS, 0, st>>>(w, w, N, S + S_BETA + l, 0, kind == TDVP_KRYLOV_ARNOLDI ? nextafter(EPS_K, 1.0) : EPS_K);
+    { ProfScope _ps(st, "vec.k_scale_dev"); k_scale_dev<<<vb, RED_THREADS, 0, st>>>(w, w, N, S + S_BETA + l, 0, kind == TDVP_KRYLOV_ARNOLDI ? nextafter(EPS_K, 1.0) : EPS_K); }
     TDVP_TRY(lc(h, "k_scale_dev"));
     TDVP_CUDA(h, cudaMemcpyAsync(h->h_scal + S_BETA + l, S + S_BETA + l, sizeof(double), cudaMemcpyDeviceToHost, st));
     TDVP_CUDA(h, cudaStreamSynchronize(st));
@@ -473,13 +473,13 @@ int krylov_expm_exec(Handle* h, int kind, double scale_re, double scale_im, doub
     // ---- Ritz step on device ----
     const int k = l + 1;
     if (kind == TDVP_KRYLOV_LANCZOS_REF)
-      k_krylov_small_expm<<<1, 512, 0, st>>>(0, k, S + S_ALPHA, S + S_BETA, S + S_AREAL, nullptr, scale_re, scale_im, S + S_COEF);
+      { ProfScope _ps(st, "vec.k_krylov_small_expm"); k_krylov_small_expm<<<1, 512, 0, st>>>(0, k, S + S_ALPHA, S + S_BETA, S + S_AREAL, nullptr, scale_re, scale_im, S + S_COEF); }
     else
-      k_krylov_small_expm<<<1, 512, 0, st>>>(1, k, nullptr, nullptr, nullptr, S + S_HESS, scale_re, scale_im, S + S_COEF);
+      { ProfScope _ps(st, "vec.k_krylov_small_expm"); k_krylov_small_expm<<<1, 512, 0, st>>>(1, k, nullptr, nullptr, nullptr, S + S_HESS, scale_re, scale_im, S + S_COEF); }
     TDVP_TRY(lc(h, "k_krylov_small_expm"));
     c128* y = ybuf[cur];
     const c128* prev = have_prev ? ybuf[cur ^ 1] : nullptr;
-    k_combine<<<nb, RED_THREADS, 0, st>>>(V, N, k, S + S_COEF, y, prev, N, h->d_partial, h->d_counter, S + S_ERR, S + S_YNORM);
+    { ProfScope _ps(st, "vec.k_combine"); k_combine<<<nb, RED_THREADS, 0, st>>>(V, N, k, S + S_COEF, y, prev, N, h->d_partial, h->d_counter, S + S_ERR, S + S_YNORM); }
     TDVP_TRY(lc(h, "k_combine"));
     bool done = conv;
     if (!done && have_prev) {
@@ -489,8 +489,8 @@ int krylov_expm_exec(Handle* h, int kind, double scale_re, double scale_im, doub
     }
     if (done) {
       // rescale: y / |y| (conserve_norm) or y * b0, written back into psi
-      if (conserve_norm) k_scale_dev<<<vb, RED_THREADS, 0, st>>>(y, psi, N, S + S_YNORM, 0, 0.0);
-      else k_scale_dev<<<vb, RED_THREADS, 0, st>>>(y, psi, N, S + S_B0, 1, 0.0);
+      if (conserve_norm) { ProfScope _ps(st, "vec.k_scale_dev"); k_scale_dev<<<vb, RED_THREADS, 0, st>>>(y, psi, N, S + S_YNORM, 0, 0.0); }
+      else { ProfScope _ps(st, "vec.k_scale_dev"); k_scale_dev<<<vb, RED_THREADS, 0, st>>>(y, psi, N, S + S_B0, 1, 0.0); }
       TDVP_TRY(lc(h, "k_scale_dev"));
       if (niter) *niter = l + 1;
       return 0;

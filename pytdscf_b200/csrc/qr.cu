@@ -301,7 +301,8 @@ int qr_factor(Handle* h, c128* A, int m, int n, int lda, c128* Q, int ldq) {
     PanelArgs pa{A, lda, m, n, j0, jb, tau, Vall, Tall, gpart, zpart, rpc};
     void* args[] = {&pa};
     const size_t smem = sizeof(c128) * (size_t)(rpc > 2 * NB ? rpc : 2 * NB) * NB;
-    cudaError_t e = cudaLaunchCooperativeKernel((void*)k_qr_panel, dim3(G), dim3(32, PTY), args, smem, h->stream);
+    cudaError_t e;
+    { ProfScope _ps(h->stream, "qr.k_qr_panel"); e = cudaLaunchCooperativeKernel((void*)k_qr_panel, dim3(G), dim3(32, PTY), args, smem, h->stream); }
     ++g_launch_count;
     if (e != cudaSuccess) return cuda_fail(h, e, "cudaLaunchCooperativeKernel(k_qr_panel)", __FILE__, __LINE__);
     const int nc = n - j0 - jb;
@@ -310,13 +311,13 @@ int qr_factor(Handle* h, c128* A, int m, int n, int lda, c128* Q, int ldq) {
       c128* Vp = Vall + (long long)j0 * lda + j0;
       c128* C = A + (long long)j0 * lda + j0 + jb;
       c128* T = Tall + (size_t)pnl * NB * NB;
-      TDVP_TRY(gemmq(h, gemm_rowmajor(jb, nc, mp, Vp, lda, true, true, C, lda, false, W, nc, one, zero)));     // W = V^H C
-      TDVP_TRY(gemmq(h, gemm_rowmajor(jb, nc, jb, T, NB, true, true, W, nc, false, W2, nc, one, zero)));      // W2 = T^H W
-      TDVP_TRY(gemmq(h, gemm_rowmajor(mp, nc, jb, Vp, lda, false, false, W2, nc, false, C, lda, mone, one))); // C -= V W2
+      TDVP_TRY(gemmq(h, tagged(gemm_rowmajor(jb, nc, mp, Vp, lda, true, true, C, lda, false, W, nc, one, zero), "qr.VhC")));     // W = V^H C
+      TDVP_TRY(gemmq(h, tagged(gemm_rowmajor(jb, nc, jb, T, NB, true, true, W, nc, false, W2, nc, one, zero), "qr.TW")));      // W2 = T^H W
+      TDVP_TRY(gemmq(h, tagged(gemm_rowmajor(mp, nc, jb, Vp, lda, false, false, W2, nc, false, C, lda, mone, one), "qr.VW"))); // C -= V W2
     }
   }
   // ---- form Q = H_1 ... H_k [I; 0]  (zungqr, blocked, backward) ----
-  k_set_identity<<<148 * 2, 256, 0, h->stream>>>(Q, m, n, ldq);
+  { ProfScope _ps(h->stream, "qr.k_set_identity"); k_set_identity<<<148 * 2, 256, 0, h->stream>>>(Q, m, n, ldq); }
   TDVP_TRY(lq(h, "k_set_identity"));
   for (int pnl = np - 1; pnl >= 0; --pnl) {
     const int j0 = pnl * NB;
@@ -326,9 +327,9 @@ int qr_factor(Handle* h, c128* A, int m, int n, int lda, c128* Q, int ldq) {
     c128* Vp = Vall + (long long)j0 * lda + j0;
     c128* C = Q + (long long)j0 * ldq + j0;
     c128* T = Tall + (size_t)pnl * NB * NB;
-    TDVP_TRY(gemmq(h, gemm_rowmajor(jb, nc, mp, Vp, lda, true, true, C, ldq, false, W, nc, one, zero)));      // W = V^H C
-    TDVP_TRY(gemmq(h, gemm_rowmajor(jb, nc, jb, T, NB, false, false, W, nc, false, W2, nc, one, zero)));     // W2 = T W
-    TDVP_TRY(gemmq(h, gemm_rowmajor(mp, nc, jb, Vp, lda, false, false, W2, nc, false, C, ldq, mone, one)));  // C -= V W2
+    TDVP_TRY(gemmq(h, tagged(gemm_rowmajor(jb, nc, mp, Vp, lda, true, true, C, ldq, false, W, nc, one, zero), "ungqr.VhC")));      // W = V^H C
+    TDVP_TRY(gemmq(h, tagged(gemm_rowmajor(jb, nc, jb, T, NB, false, false, W, nc, false, W2, nc, one, zero), "ungqr.TW")));     // W2 = T W
+    TDVP_TRY(gemmq(h, tagged(gemm_rowmajor(mp, nc, jb, Vp, lda, false, false, W2, nc, false, C, ldq, mone, one), "ungqr.VW")));  // C -= V W2
   }
   return 0;
 }
@@ -345,7 +346,7 @@ int qr_shift_exec(Handle* h, int gauge, int Dl, int d, int Dr, const c128* psi, 
   if (gauge == TDVP_GAUGE_A) {
     TDVP_CUDA(h, cudaMemcpyAsync(Awork, psi, sizeof(c128) * N, cudaMemcpyDeviceToDevice, h->stream));
     TDVP_TRY(qr_factor(h, Awork, m, n, n, site, n));                       // site(Dl,d,k=n) = Q
-    k_extract_r<<<64, 256, 0, h->stream>>>(Awork, n, n, n, sigma, n, 0);   // sigma(k, Dr) = R
+    { ProfScope _ps(h->stream, "qr.k_extract_r"); k_extract_r<<<64, 256, 0, h->stream>>>(Awork, n, n, n, sigma, n, 0); }   // sigma(k, Dr) = R
     TDVP_TRY(lq(h, "k_extract_r"));
   } else if (gauge == TDVP_GAUGE_B) {
     // QR of psi^T viewed as (Dr*d) x Dl;  B = Q reshaped (Dr,d,k) -> (k,d,Dr);  sigma = R^T (Dl, k)
@@ -354,7 +355,7 @@ int qr_shift_exec(Handle* h, int gauge, int Dl, int d, int Dr, const c128* psi, 
     TDVP_TRY(permute_site(h, psi, Awork, Dl, d, Dr));                      // Awork[r,j,l] = psi[l,j,r]
     TDVP_TRY(qr_factor(h, Awork, m, n, n, Qt, n));
     TDVP_TRY(permute_site(h, Qt, site, Dr, d, n));                         // site[k,j,r] = Qt[r,j,k]
-    k_extract_r<<<64, 256, 0, h->stream>>>(Awork, n, n, n, sigma, n, 1);   // sigma(Dl, k) = R^T
+    { ProfScope _ps(h->stream, "qr.k_extract_r"); k_extract_r<<<64, 256, 0, h->stream>>>(Awork, n, n, n, sigma, n, 1); }   // sigma(Dl, k) = R^T
     TDVP_TRY(lq(h, "k_extract_r"));
   } else {
     set_error(h, "qr_shift: bad gauge");
@@ -367,10 +368,10 @@ int absorb_exec(Handle* h, int gauge, int Dl, int d, int Dr, int k, const c128* 
   TDVP_TRY(ws_reserve(h, 4096));
   if (gauge == TDVP_GAUGE_A) {
     // out(k, d*Dr) = sigma(k, Dl) . site(Dl, d*Dr)
-    return gemmq(h, gemm_rowmajor(k, d * Dr, Dl, sigma, Dl, false, false, site, (long long)d * Dr, false, out, (long long)d * Dr));
+    return gemmq(h, tagged(gemm_rowmajor(k, d * Dr, Dl, sigma, Dl, false, false, site, (long long)d * Dr, false, out, (long long)d * Dr), "absorb"));
   } else if (gauge == TDVP_GAUGE_B) {
     // out(Dl*d, k) = site(Dl*d, Dr) . sigma(Dr, k)
-    return gemmq(h, gemm_rowmajor(Dl * d, k, Dr, site, Dr, false, false, sigma, k, false, out, k));
+    return gemmq(h, tagged(gemm_rowmajor(Dl * d, k, Dr, site, Dr, false, false, sigma, k, false, out, k), "absorb"));
   }
   set_error(h, "absorb: bad gauge");
   return TDVP_ERR_ARG;

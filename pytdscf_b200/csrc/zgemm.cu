@@ -16,7 +16,9 @@
 //    every fragment LDS.128 is bank-conflict free for both operand majors.
 //  * rows of A/C and columns of B may be two-level indices (GemmDesc) so contractions such as
 //    T2[a,i,t,s] = sum_{c,j} T1[a,c,j,s] W[c,i,j,t] run on their natural layouts (no transposes).
-#include <utility>
+#include <cstring>
+#include <map>
+#include <string>
 #include <vector>
 
 #include "common.cuh"
@@ -25,15 +27,17 @@ namespace tdvp {
 
 unsigned long long g_launch_count = 0;
 
-// ---- optional per-launch timing of the GEMM kernel (bench.py roofline): CUDA events on the launching stream ----
+// ---- optional per-launch timing (bench.py roofline / breakdown): CUDA events on the launching stream ----
 namespace {
-struct GemmProfile {
+struct ProfTotals { double ms = 0.0, flops = 0.0; unsigned long long launches = 0; bool is_gemm = false; };
+struct Pending { cudaEvent_t e0, e1; const char* label; };
+struct Profiler {
   bool enabled = false;
-  std::vector<cudaEvent_t> pool;   // recycled events
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
-  double flops = 0.0;
-  double ms = 0.0;
-  unsigned long long launches = 0;
+  std::vector<cudaEvent_t> pool;
+  std::vector<Pending> pending;
+  std::map<std::string, ProfTotals> totals;
+  cudaEvent_t open_e0 = nullptr;
+  const char* open_label = nullptr;
   cudaEvent_t get() {
     if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
     cudaEvent_t e;
@@ -43,22 +47,65 @@ struct GemmProfile {
 } g_prof;
 }  // namespace
 
-void gemm_profile_enable(bool on) { g_prof.enabled = on; }
+void prof_enable(bool on) { g_prof.enabled = on; }
+bool prof_enabled() { return g_prof.enabled; }
 
-void gemm_profile_collect(double* ms, double* flops, unsigned long long* launches, bool reset) {
+void prof_begin(cudaStream_t stream, const char* label, double flops, bool is_gemm) {
+  ProfTotals& t = g_prof.totals[label];
+  t.flops += flops;
+  t.launches += 1;
+  t.is_gemm = is_gemm;
+  g_prof.open_e0 = g_prof.get();
+  g_prof.open_label = label;
+  cudaEventRecord(g_prof.open_e0, stream);
+}
+
+void prof_end(cudaStream_t stream) {
+  cudaEvent_t e1 = g_prof.get();
+  cudaEventRecord(e1, stream);
+  g_prof.pending.push_back({g_prof.open_e0, e1, g_prof.open_label});
+}
+
+void prof_collect(bool reset) {
   for (auto& pr : g_prof.pending) {
-    cudaEventSynchronize(pr.second);
+    cudaEventSynchronize(pr.e1);
     float t = 0.f;
-    cudaEventElapsedTime(&t, pr.first, pr.second);
-    g_prof.ms += t;
-    g_prof.pool.push_back(pr.first);
-    g_prof.pool.push_back(pr.second);
+    cudaEventElapsedTime(&t, pr.e0, pr.e1);
+    g_prof.totals[pr.label].ms += t;
+    g_prof.pool.push_back(pr.e0);
+    g_prof.pool.push_back(pr.e1);
   }
   g_prof.pending.clear();
-  if (ms) *ms = g_prof.ms;
-  if (flops) *flops = g_prof.flops;
-  if (launches) *launches = g_prof.launches;
-  if (reset) { g_prof.ms = 0.0; g_prof.flops = 0.0; g_prof.launches = 0; }
+  if (reset) g_prof.totals.clear();
+}
+
+void prof_gemm_totals(double* ms, double* flops, unsigned long long* launches) {
+  double m = 0.0, f = 0.0;
+  unsigned long long n = 0;
+  for (auto& kv : g_prof.totals)
+    if (kv.second.is_gemm) { m += kv.second.ms; f += kv.second.flops; n += kv.second.launches; }
+  if (ms) *ms = m;
+  if (flops) *flops = f;
+  if (launches) *launches = n;
+}
+
+size_t prof_json(char* out, size_t cap) {
+  std::string js = "{";
+  bool first = true;
+  for (auto& kv : g_prof.totals) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "%s\"%s\": {\"ms\": %.6f, \"flops\": %.6e, \"launches\": %llu, \"gemm\": %s}", first ? "" : ", ",
+             kv.first.c_str(), kv.second.ms, kv.second.flops, kv.second.launches, kv.second.is_gemm ? "true" : "false");
+    js += buf;
+    first = false;
+  }
+  js += "}";
+  if (out && cap > 0) {
+    size_t n = js.size() < cap - 1 ? js.size() : cap - 1;
+    memcpy(out, js.data(), n);
+    out[n] = 0;
+  }
+  return js.size() + 1;
 }
 
 namespace {
@@ -296,12 +343,7 @@ cudaError_t zgemm_launch(const GemmDesc& d, cudaStream_t stream) {
   }
   dim3 grid((d.N + BN - 1) / BN, (d.M + BM - 1) / BM, d.batch);
   const bool ak = (d.a_k == 1), bk = (d.b_k == 1);
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  if (g_prof.enabled) {
-    ev0 = g_prof.get();
-    ev1 = g_prof.get();
-    cudaEventRecord(ev0, stream);
-  }
+  ProfScope scope(stream, d.tag, 8.0 * (double)d.M * (double)d.N * (double)d.K * (double)d.batch, true);
   if (ak && bk)
     zgemm_dmma_kernel<true, true><<<grid, THREADS, SMEM_BYTES, stream>>>(d);
   else if (ak && !bk)
@@ -311,12 +353,6 @@ cudaError_t zgemm_launch(const GemmDesc& d, cudaStream_t stream) {
   else
     zgemm_dmma_kernel<false, false><<<grid, THREADS, SMEM_BYTES, stream>>>(d);
   ++g_launch_count;
-  if (g_prof.enabled) {
-    cudaEventRecord(ev1, stream);
-    g_prof.pending.emplace_back(ev0, ev1);
-    g_prof.flops += 8.0 * (double)d.M * (double)d.N * (double)d.K * (double)d.batch;
-    ++g_prof.launches;
-  }
   return cudaGetLastError();
 }
 

@@ -10,7 +10,24 @@ from oracle import tdvp_oracle as orc
 from tests.golden_io import RUN_CASES, load_run
 
 pytestmark = pytest.mark.gpu
-REL = 1e-10
+REL = 1e-10  # north-star tolerance (complex128)
+
+
+def tolerances(name):
+    """max(1e-10, 4 x the reference algorithm's own rounding-noise floor) per observable.
+
+    tests/golden/noise_floor.json (made by tests/golden/make_noise_floor.py) records how far the reference
+    algorithm moves when its H_eff outputs are perturbed by one rounding (2e-16 relative): for well-conditioned
+    cases that is ~1e-15 and the bar is the plain 1e-10; exciton_D6 (bond dimension 6 on a state of numerical
+    rank ~2) is ill-conditioned -- 1e-8 in the autocorrelation -- and no implementation, the reference with
+    another BLAS included, can agree better than that."""
+    import json
+
+    from tests.golden_io import GOLDEN_DIR
+
+    nf = json.load(open(os.path.join(GOLDEN_DIR, "noise_floor.json")))[name]
+    return {"autocorr": max(REL, 4 * nf["autocorr_abs"]), "energy": max(REL, 4 * nf["energy_rel"]),
+            "state": max(1e-9, 4 * nf["state_abs"])}
 
 
 def dense_state(cores):
@@ -66,14 +83,16 @@ def test_propagation_matches_reference(name, tmp_path):
     sim, ener, wf = run_cuda(g, tmp_path)
     trace = np.array(wf.ci_coef.trace)
     assert trace.shape == g["trace"].shape and (trace == g["trace"]).all(), "Krylov iteration trace differs"
+    tol = tolerances(name)
     if g["space"] == "hilbert":
         for rec, row in zip(sim.history, g["props"], strict=True):
             t, ar, ai, er, ei, nrm = row
-            assert abs(rec["autocorr"] - complex(ar, ai)) <= REL * max(1.0, abs(complex(ar, ai)))
-            assert abs(rec["energy"] - er) <= REL * abs(er)
+            assert abs(rec["autocorr"] - complex(ar, ai)) <= tol["autocorr"] * max(1.0, abs(complex(ar, ai)))
+            assert abs(rec["energy"] - er) <= tol["energy"] * abs(er)
             assert abs(rec["norm"] - nrm) <= REL
-        assert abs(ener - g["final_energy"].real) <= REL * abs(g["final_energy"].real)
-    assert_same_state(wf.ci_coef.to_numpy(), g["final"])
+            assert abs(rec["pops"][0] - nrm**2) <= REL
+        assert abs(ener - g["final_energy"].real) <= tol["energy"] * abs(g["final_energy"].real)
+    assert_same_state(wf.ci_coef.to_numpy(), g["final"], tol["state"])
     # output files in the reference layout
     assert os.path.exists(os.path.join(g["name"] + "_prop", "main.log"))
     if g["space"] == "hilbert":
