@@ -78,6 +78,7 @@ int tdvp_create(int device, void* cuda_stream, tdvp_handle_t* out) {
   if ((e = cudaMallocHost((void**)&h->h_scal, 4096 * sizeof(double))) != cudaSuccess) { delete h; return (int)e; }
   if ((e = cudaMalloc((void**)&h->d_partial, 1024 * 64 * sizeof(double))) != cudaSuccess) { delete h; return (int)e; }
   if ((e = cudaMalloc((void**)&h->d_counter, 16 * sizeof(unsigned int))) != cudaSuccess) { delete h; return (int)e; }
+  if ((e = cudaMalloc((void**)&h->d_splitk, tdvp::SPLITK_SCRATCH_ELEMS * sizeof(c128))) != cudaSuccess) { delete h; return (int)e; }
   cudaMemsetAsync(h->d_counter, 0, 16 * sizeof(unsigned int), h->stream);
   cudaMemsetAsync(h->d_scal, 0, 4096 * sizeof(double), h->stream);
   memset(h->h_scal, 0, 4096 * sizeof(double));
@@ -94,6 +95,7 @@ int tdvp_destroy(tdvp_handle_t h) {
   if (h->h_scal) cudaFreeHost(h->h_scal);
   if (h->d_partial) cudaFree(h->d_partial);
   if (h->d_counter) cudaFree(h->d_counter);
+  if (h->d_splitk) cudaFree(h->d_splitk);
   delete h;
   return 0;
 }
@@ -206,7 +208,7 @@ int tdvp_zgemm(tdvp_handle_t h, int transA, int transB, int M, int N, int K, dou
   GemmDesc g = gemm_rowmajor(M, N, K, (const c128*)A, lda, transA != 0, transA == 2, (const c128*)B, ldb, transB != 0,
                              (c128*)C, ldc, c128{alpha_re, alpha_im}, c128{beta_re, beta_im});
   g.b_conj = transB == 2 ? 1 : 0;
-  cudaError_t e = zgemm_launch(g, h->stream);
+  cudaError_t e = zgemm_auto(g, h->stream, h->d_splitk, tdvp::SPLITK_SCRATCH_ELEMS);
   if (e != cudaSuccess) return cuda_fail(h, e, "zgemm_launch", __FILE__, __LINE__);
   return 0;
 }

@@ -59,10 +59,20 @@ struct GemmDesc {
   c128 alpha = {1.0, 0.0};
   c128 beta = {0.0, 0.0};
   const char* tag = "gemm";   // profiling label (static string)
+  // split-K (set by gemm_auto): blockIdx.z = batch * splitk + split; split s covers k in [s*k_chunk, (s+1)*k_chunk)
+  // and writes its partial to C + s * c_split (then combined by the fixed-order reduction kernel).
+  int splitk = 1;
+  int k_chunk = 0;
+  long long c_split = 0;
 };
 
 // Launch the DMMA ZGEMM on `stream`.  Returns cudaGetLastError() of the launch.
 cudaError_t zgemm_launch(const GemmDesc& d, cudaStream_t stream);
+// GEMM with automatic split-K for shapes that would leave most of the 148 SMs idle (few output tiles, long K):
+// partial products go to `scratch` (scratch_elems complex128 available, may be null) and are combined in fixed
+// order by a second kernel, so results stay deterministic.
+cudaError_t zgemm_auto(const GemmDesc& d, cudaStream_t stream, c128* scratch, size_t scratch_elems);
+constexpr size_t SPLITK_SCRATCH_ELEMS = size_t(3) << 20;  // 48 MiB: >= 296 partial tiles of 128x64
 // Number of kernel launches issued through this library since load (bench.py's gpu_launches claim).
 extern unsigned long long g_launch_count;
 // Per-launch CUDA-event timing (off by default; used by bench.py for the roofline and the per-kernel breakdown).

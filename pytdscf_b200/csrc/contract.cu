@@ -116,7 +116,7 @@ int launch_check(Handle* h, const char* what) {
 }
 
 int gemm(Handle* h, const GemmDesc& g) {
-  cudaError_t e = zgemm_launch(g, h->stream);
+  cudaError_t e = zgemm_auto(g, h->stream, h->d_splitk, SPLITK_SCRATCH_ELEMS);
   if (e != cudaSuccess) return cuda_fail(h, e, "zgemm_launch", __FILE__, __LINE__);
   return 0;
 }

@@ -20,6 +20,7 @@ struct Handle {
   double* h_scal = nullptr;   // pinned, 4096 doubles
   double* d_partial = nullptr;  // reduction partials: 1024 blocks x 64 doubles
   unsigned int* d_counter = nullptr;  // "last block done" tickets
+  c128* d_splitk = nullptr;           // split-K partial products (SPLITK_SCRATCH_ELEMS)
   // statistics
   unsigned long long krylov_matvecs = 0;
   unsigned long long krylov_solves = 0;

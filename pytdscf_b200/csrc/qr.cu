@@ -242,6 +242,19 @@ __global__ void k_extract_r(const c128* A, int lda, int k, int n, c128* R, int l
   }
 }
 
+// W(jb x nc, ld = nc) = V^H C for a tall panel V (mp x jb, ld = ldv) and C (mp x nc, ld = ldc), issued as the
+// transposed product W^T = C^T conj(V) so that the long dimension nc maps to the 128-row tile direction and the
+// reduction over the mp rows is split across CTAs (split-K) instead of running on a handful of SMs.
+GemmDesc vhc_desc(int jb, int nc, int mp, const c128* V, long long ldv, const c128* C, long long ldc, c128* W, const char* tag) {
+  GemmDesc g;
+  g.M = nc; g.N = jb; g.K = mp;
+  g.A = C; g.a_m_inner = 1; g.a_m1 = 1; g.a_m0 = 0; g.a_k = ldc; g.a_conj = 0;
+  g.B = V; g.b_n_inner = 1; g.b_n1 = 1; g.b_n0 = 0; g.b_k = ldv; g.b_conj = 1;
+  g.C = W; g.c_m_inner = 1; g.c_m1 = 1; g.c_m0 = 0; g.c_n = nc;
+  g.tag = tag;
+  return g;
+}
+
 int lq(Handle* h, const char* what) {
   ++g_launch_count;
   cudaError_t e = cudaGetLastError();
@@ -250,7 +263,7 @@ int lq(Handle* h, const char* what) {
 }
 
 int gemmq(Handle* h, const GemmDesc& g) {
-  cudaError_t e = zgemm_launch(g, h->stream);
+  cudaError_t e = zgemm_auto(g, h->stream, h->d_splitk, SPLITK_SCRATCH_ELEMS);
   if (e != cudaSuccess) return cuda_fail(h, e, "zgemm_launch", __FILE__, __LINE__);
   return 0;
 }
@@ -311,7 +324,7 @@ int qr_factor(Handle* h, c128* A, int m, int n, int lda, c128* Q, int ldq) {
       c128* Vp = Vall + (long long)j0 * lda + j0;
       c128* C = A + (long long)j0 * lda + j0 + jb;
       c128* T = Tall + (size_t)pnl * NB * NB;
-      TDVP_TRY(gemmq(h, tagged(gemm_rowmajor(jb, nc, mp, Vp, lda, true, true, C, lda, false, W, nc, one, zero), "qr.VhC")));     // W = V^H C
+      TDVP_TRY(gemmq(h, vhc_desc(jb, nc, mp, Vp, lda, C, lda, W, "qr.VhC")));     // W = V^H C
       TDVP_TRY(gemmq(h, tagged(gemm_rowmajor(jb, nc, jb, T, NB, true, true, W, nc, false, W2, nc, one, zero), "qr.TW")));      // W2 = T^H W
       TDVP_TRY(gemmq(h, tagged(gemm_rowmajor(mp, nc, jb, Vp, lda, false, false, W2, nc, false, C, lda, mone, one), "qr.VW"))); // C -= V W2
     }
@@ -327,7 +340,7 @@ int qr_factor(Handle* h, c128* A, int m, int n, int lda, c128* Q, int ldq) {
     c128* Vp = Vall + (long long)j0 * lda + j0;
     c128* C = Q + (long long)j0 * ldq + j0;
     c128* T = Tall + (size_t)pnl * NB * NB;
-    TDVP_TRY(gemmq(h, tagged(gemm_rowmajor(jb, nc, mp, Vp, lda, true, true, C, ldq, false, W, nc, one, zero), "ungqr.VhC")));      // W = V^H C
+    TDVP_TRY(gemmq(h, vhc_desc(jb, nc, mp, Vp, lda, C, ldq, W, "ungqr.VhC")));      // W = V^H C
     TDVP_TRY(gemmq(h, tagged(gemm_rowmajor(jb, nc, jb, T, NB, false, false, W, nc, false, W2, nc, one, zero), "ungqr.TW")));     // W2 = T W
     TDVP_TRY(gemmq(h, tagged(gemm_rowmajor(mp, nc, jb, Vp, lda, false, false, W2, nc, false, C, ldq, mone, one), "ungqr.VW")));  // C -= V W2
   }

@@ -110,10 +110,14 @@ size_t prof_json(char* out, size_t cap) {
 
 namespace {
 
-constexpr int BM = 128, BN = 64, BK = 8, STAGES = 4, THREADS = 256;
+constexpr int BM = 128, BN = 64, THREADS = 256;
+constexpr int BK = 16, STAGES = 3;
 constexpr int A_STAGE = BM * BK;  // c128 elements per stage
 constexpr int B_STAGE = BN * BK;
-constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) * (int)sizeof(c128);  // 96 KiB
+constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) * (int)sizeof(c128);  // 144 KiB
+constexpr int A_ITERS = A_STAGE / THREADS;  // cp.async per thread per stage
+constexpr int B_ITERS = B_STAGE / THREADS;
+static_assert(THREADS % BK == 0 && THREADS % BM == 0 && THREADS % BN == 0, "tile / thread mapping");
 
 __device__ __forceinline__ void cp_async16(c128* smem, const c128* gmem, bool pred) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -140,6 +144,54 @@ __device__ __forceinline__ int tile_chunk(int r, int k) {  // r: m or n inside t
   return k * ROWS + (r ^ ((k & 3) << 1));
 }
 
+// Per-thread global->shared copy plan of one operand tile (ROWS x BK), fixed for the whole k loop.
+//   K-major (k contiguous in memory): thread owns k-chunk kc = tid % BK of rows tid / BK + (THREADS / BK) * i
+//   row-major in m/n (the other index contiguous): thread owns row tid % ROWS for k = tid / ROWS + (THREADS / ROWS) * i
+template <bool KMAJOR, int ROWS, int ITERS>
+struct LoadPlan {
+  long long off[KMAJOR ? ITERS : 1];
+  unsigned ok;  // bit i: row of iteration i is inside the matrix
+  __device__ __forceinline__ void init(int tid, int tile0, int extent, int inner, long long s1, long long s0) {
+    ok = 0;
+    if (KMAJOR) {
+#pragma unroll
+      for (int i = 0; i < ITERS; ++i) {
+        const int r = tid / BK + (THREADS / BK) * i;
+        const int m = tile0 + r;
+        const bool in = m < extent;
+        const int mm = in ? m : 0;
+        off[i] = (long long)(mm / inner) * s1 + (long long)(mm % inner) * s0;
+        ok |= (in ? 1u : 0u) << i;
+      }
+    } else {
+      const int m = tile0 + tid % ROWS;
+      const bool in = m < extent;
+      const int mm = in ? m : 0;
+      off[0] = (long long)(mm / inner) * s1 + (long long)(mm % inner) * s0;
+      ok = in ? 0xffffffffu : 0u;
+    }
+  }
+  __device__ __forceinline__ void issue(int tid, c128* smem, const c128* __restrict__ g, long long kstride, int k0, int k_end) const {
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i) {
+      int r, kl;
+      long long o;
+      if (KMAJOR) {
+        r = tid / BK + (THREADS / BK) * i;
+        kl = tid % BK;
+        o = off[i];
+      } else {
+        r = tid % ROWS;
+        kl = tid / ROWS + (THREADS / ROWS) * i;
+        o = off[0];
+      }
+      const int k = k0 + kl;
+      const bool p = ((ok >> i) & 1u) && (k < k_end);
+      cp_async16(smem + tile_chunk<KMAJOR, ROWS>(r, kl), p ? (g + o + (long long)k * kstride) : g, p);
+    }
+  }
+};
+
 template <bool A_KMAJOR, bool B_KMAJOR>
 __global__ void __launch_bounds__(THREADS, 1) zgemm_dmma_kernel(const GemmDesc d) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -151,91 +203,22 @@ __global__ void __launch_bounds__(THREADS, 1) zgemm_dmma_kernel(const GemmDesc d
   const int g = lane >> 2, q = lane & 3;
   const int wm = warp & 3, wn = warp >> 2;
   const int tile_m = blockIdx.y * BM, tile_n = blockIdx.x * BN;
-  const long long bz = blockIdx.z;
+  const long long bz = blockIdx.z / d.splitk;
+  const int split = blockIdx.z % d.splitk;
+  const int k_begin = split * d.k_chunk;                       // k_chunk is a multiple of BK (or covers all of K)
+  const int k_end = (d.splitk > 1 && k_begin + d.k_chunk < d.K) ? k_begin + d.k_chunk : d.K;
   const c128* __restrict__ Ag = d.A + bz * d.a_batch;
   const c128* __restrict__ Bg = d.B + bz * d.b_batch;
-  c128* __restrict__ Cg = d.C + bz * d.c_batch;
+  c128* __restrict__ Cg = d.C + bz * d.c_batch + (long long)split * d.c_split;
 
-  // ---- per-thread global->shared assignments (fixed for the whole k loop) ----
-  // A, K-major: 4 rows x 1 k-chunk ; A, M-major: 1 row x 4 k's
-  long long a_off[4];
-  bool a_ok[4];
-  int a_sm[4];
-  int a_kl[4];
-  if (A_KMAJOR) {
-    const int kc = tid & 7;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = (tid >> 3) + 32 * i;
-      const int m = tile_m + r;
-      a_ok[i] = m < d.M;
-      const int mm = a_ok[i] ? m : 0;
-      a_off[i] = (long long)(mm / d.a_m_inner) * d.a_m1 + (long long)(mm % d.a_m_inner) * d.a_m0;
-      a_sm[i] = tile_chunk<true, BM>(r, kc);
-      a_kl[i] = kc;
-    }
-  } else {
-    const int r = tid & 127;
-    const int m = tile_m + r;
-    const bool ok = m < d.M;
-    const int mm = ok ? m : 0;
-    const long long off = (long long)(mm / d.a_m_inner) * d.a_m1 + (long long)(mm % d.a_m_inner) * d.a_m0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int k = (tid >> 7) + 2 * i;
-      a_ok[i] = ok;
-      a_off[i] = off;
-      a_sm[i] = tile_chunk<false, BM>(r, k);
-      a_kl[i] = k;
-    }
-  }
-  long long b_off[2];
-  bool b_ok[2];
-  int b_sm[2];
-  int b_kl[2];
-  if (B_KMAJOR) {
-    const int kc = tid & 7;
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int r = (tid >> 3) + 32 * i;
-      const int n = tile_n + r;
-      b_ok[i] = n < d.N;
-      const int nn = b_ok[i] ? n : 0;
-      b_off[i] = (long long)(nn / d.b_n_inner) * d.b_n1 + (long long)(nn % d.b_n_inner) * d.b_n0;
-      b_sm[i] = tile_chunk<true, BN>(r, kc);
-      b_kl[i] = kc;
-    }
-  } else {
-    const int r = tid & 63;
-    const int n = tile_n + r;
-    const bool ok = n < d.N;
-    const int nn = ok ? n : 0;
-    const long long off = (long long)(nn / d.b_n_inner) * d.b_n1 + (long long)(nn % d.b_n_inner) * d.b_n0;
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int k = (tid >> 6) + 4 * i;
-      b_ok[i] = ok;
-      b_off[i] = off;
-      b_sm[i] = tile_chunk<false, BN>(r, k);
-      b_kl[i] = k;
-    }
-  }
+  LoadPlan<A_KMAJOR, BM, A_ITERS> pa;
+  LoadPlan<B_KMAJOR, BN, B_ITERS> pb;
+  pa.init(tid, tile_m, d.M, d.a_m_inner, d.a_m1, d.a_m0);
+  pb.init(tid, tile_n, d.N, d.b_n_inner, d.b_n1, d.b_n0);
 
   auto load_stage = [&](int stage, int k0) {
-    c128* as = As + stage * A_STAGE;
-    c128* bs = Bs + stage * B_STAGE;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int k = k0 + a_kl[i];
-      const bool p = a_ok[i] && (k < d.K);
-      cp_async16(as + a_sm[i], p ? (Ag + a_off[i] + (long long)k * d.a_k) : Ag, p);
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int k = k0 + b_kl[i];
-      const bool p = b_ok[i] && (k < d.K);
-      cp_async16(bs + b_sm[i], p ? (Bg + b_off[i] + (long long)k * d.b_k) : Bg, p);
-    }
+    pa.issue(tid, As + stage * A_STAGE, Ag, d.a_k, k0, k_end);
+    pb.issue(tid, Bs + stage * B_STAGE, Bg, d.b_k, k0, k_end);
   };
 
   double cre[4][4][2], cim[4][4][2];
@@ -247,10 +230,10 @@ __global__ void __launch_bounds__(THREADS, 1) zgemm_dmma_kernel(const GemmDesc d
       cim[i][j][0] = cim[i][j][1] = 0.0;
     }
 
-  const int KT = (d.K + BK - 1) / BK;
+  const int KT = (k_end - k_begin + BK - 1) / BK;
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < KT) load_stage(s, s * BK);
+    if (s < KT) load_stage(s, k_begin + s * BK);
     cp_async_commit();
   }
 
@@ -262,7 +245,7 @@ __global__ void __launch_bounds__(THREADS, 1) zgemm_dmma_kernel(const GemmDesc d
     __syncthreads();
     {
       const int nk = kt + STAGES - 1;
-      if (nk < KT) load_stage(nk % STAGES, nk * BK);
+      if (nk < KT) load_stage(nk % STAGES, k_begin + nk * BK);
       cp_async_commit();
     }
     const c128* as = As + (kt % STAGES) * A_STAGE;
@@ -341,7 +324,7 @@ cudaError_t zgemm_launch(const GemmDesc& d, cudaStream_t stream) {
     cudaFuncSetAttribute(zgemm_dmma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     configured = true;
   }
-  dim3 grid((d.N + BN - 1) / BN, (d.M + BM - 1) / BM, d.batch);
+  dim3 grid((d.N + BN - 1) / BN, (d.M + BM - 1) / BM, d.batch * d.splitk);
   const bool ak = (d.a_k == 1), bk = (d.b_k == 1);
   ProfScope scope(stream, d.tag, 8.0 * (double)d.M * (double)d.N * (double)d.K * (double)d.batch, true);
   if (ak && bk)
@@ -352,6 +335,61 @@ cudaError_t zgemm_launch(const GemmDesc& d, cudaStream_t stream) {
     zgemm_dmma_kernel<false, true><<<grid, THREADS, SMEM_BYTES, stream>>>(d);
   else
     zgemm_dmma_kernel<false, false><<<grid, THREADS, SMEM_BYTES, stream>>>(d);
+  ++g_launch_count;
+  return cudaGetLastError();
+}
+
+namespace {
+// C[m,n] = alpha * sum_s P[s][m][n] + beta * C[m,n]   (fixed summation order over s; C addressed like GemmDesc)
+__global__ void k_splitk_reduce(const c128* __restrict__ P, int S, int M, int N, long long stride, GemmDesc d) {
+  const long long tot = (long long)M * N;
+  const bool use_beta = d.beta.x != 0.0 || d.beta.y != 0.0;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(e / N), n = (int)(e % N);
+    double sx = 0.0, sy = 0.0;
+    for (int s = 0; s < S; ++s) {
+      const c128 v = P[(long long)s * stride + e];
+      sx += v.x;
+      sy += v.y;
+    }
+    c128* p = d.C + (long long)(m / d.c_m_inner) * d.c_m1 + (long long)(m % d.c_m_inner) * d.c_m0 + (long long)n * d.c_n;
+    c128 o = cmul(d.alpha, c128{sx, sy});
+    if (use_beta) o = cadd(o, cmul(d.beta, *p));
+    *p = o;
+  }
+}
+}  // namespace
+
+cudaError_t zgemm_auto(const GemmDesc& d, cudaStream_t stream, c128* scratch, size_t scratch_elems) {
+  if (d.M <= 0 || d.N <= 0 || d.batch <= 0) return cudaSuccess;
+  const long long tiles = (long long)((d.M + BM - 1) / BM) * ((d.N + BN - 1) / BN) * d.batch;
+  if (d.batch != 1 || tiles >= 120 || d.K < 256 || scratch == nullptr) return zgemm_launch(d, stream);
+  int S = (int)((296 + tiles - 1) / tiles);
+  const int max_s = d.K / 64;
+  if (S > max_s) S = max_s;
+  if (S < 2) return zgemm_launch(d, stream);
+  int chunk = (d.K + S - 1) / S;
+  chunk = (chunk + BK - 1) / BK * BK;
+  S = (d.K + chunk - 1) / chunk;
+  const size_t need = (size_t)S * d.M * d.N;
+  if (S < 2 || need > scratch_elems) return zgemm_launch(d, stream);
+  GemmDesc g = d;
+  g.C = scratch;
+  g.c_m_inner = 1; g.c_m1 = d.N; g.c_m0 = 0; g.c_n = 1; g.c_batch = 0;
+  g.alpha = {1.0, 0.0};
+  g.beta = {0.0, 0.0};
+  g.splitk = S;
+  g.k_chunk = chunk;
+  g.c_split = (long long)d.M * d.N;
+  cudaError_t e = zgemm_launch(g, stream);
+  if (e != cudaSuccess) return e;
+  const long long tot = (long long)d.M * d.N;
+  int blocks = (int)((tot + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  {
+    ProfScope scope(stream, "aux.k_splitk_reduce");
+    k_splitk_reduce<<<blocks, 256, 0, stream>>>(scratch, S, d.M, d.N, (long long)d.M * d.N, d);
+  }
   ++g_launch_count;
   return cudaGetLastError();
 }
