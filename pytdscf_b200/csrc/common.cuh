@@ -72,7 +72,7 @@ cudaError_t zgemm_launch(const GemmDesc& d, cudaStream_t stream);
 // partial products go to `scratch` (scratch_elems complex128 available, may be null) and are combined in fixed
 // order by a second kernel, so results stay deterministic.
 cudaError_t zgemm_auto(const GemmDesc& d, cudaStream_t stream, c128* scratch, size_t scratch_elems);
-constexpr size_t SPLITK_SCRATCH_ELEMS = size_t(3) << 20;  // 48 MiB: >= 296 partial tiles of 128x64
+constexpr size_t SPLITK_SCRATCH_ELEMS = size_t(18) << 20;  // 288 MiB of partial products
 // Number of kernel launches issued through this library since load (bench.py's gpu_launches claim).
 extern unsigned long long g_launch_count;
 // Per-launch CUDA-event timing (off by default; used by bench.py for the roofline and the per-kernel breakdown).

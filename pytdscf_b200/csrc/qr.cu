@@ -224,6 +224,179 @@ __global__ void __launch_bounds__(PT, 1) k_qr_panel(PanelArgs p) {
   for (int a = ty; a < NB; a += PTY) Tout[a * NB + tx] = T[a * NB + tx];
 }
 
+
+// ---- cluster variant: the whole panel is owned by ONE thread-block cluster (<= 16 CTAs), partial reductions are
+// exchanged through distributed shared memory and ordered by barrier.cluster (~0.2 us) instead of a grid-wide
+// cooperative sync (~3 us).  Same arithmetic and the same fixed CTA-order summation as k_qr_panel. ----
+constexpr int CT = 1024;          // threads per CTA, arranged (32, 32)
+constexpr int CTY = CT / 32;
+
+__global__ void __launch_bounds__(CT, 1) k_qr_panel_cluster(PanelArgs p) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  c128* S = reinterpret_cast<c128*>(smraw);                 // [rows_per_cta][NB]
+  __shared__ c128 red[CTY][NB + 1];
+  __shared__ c128 pbuf[2][NB];   // this CTA's partial g (double-buffered by column parity)
+  __shared__ c128 rbuf[2][NB];   // diagonal row broadcast (valid in the owner CTA)
+  __shared__ c128 gtot[NB], rowc[NB], wv[NB];
+  __shared__ double s_tau[2], s_scal[2], s_beta;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int G = gridDim.x, b = blockIdx.x;
+  const int jb = p.jb, j0 = p.j0;
+  const int r0 = j0 + b * p.rows_per_cta;
+  int nrow = p.m - r0;
+  if (nrow > p.rows_per_cta) nrow = p.rows_per_cta;
+  if (nrow < 0) nrow = 0;
+
+  for (int i = ty; i < nrow; i += CTY) {
+    if (tx < jb) S[i * NB + tx] = p.A[(long long)(r0 + i) * p.lda + j0 + tx];
+    else S[i * NB + tx] = {0.0, 0.0};
+  }
+  __syncthreads();
+
+  for (int c = 0; c < jb; ++c) {
+    const int grow = j0 + c;
+    const int buf = c & 1;
+    const int owner = (grow - j0) / p.rows_per_cta;
+    c128 acc = {0.0, 0.0};
+    if (tx >= c && tx < jb) {
+      for (int i = ty; i < nrow; i += CTY) {
+        if (r0 + i > grow) {
+          const c128 x = S[i * NB + c], y = S[i * NB + tx];
+          acc.x += x.x * y.x + x.y * y.y;
+          acc.y += x.x * y.y - x.y * y.x;
+        }
+      }
+    }
+    red[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0) {
+      c128 t = {0.0, 0.0};
+#pragma unroll
+      for (int q = 0; q < CTY; ++q) { t.x += red[q][tx].x; t.y += red[q][tx].y; }
+      pbuf[buf][tx] = t;
+      if (b == owner) rbuf[buf][tx] = S[(grow - r0) * NB + tx];
+    }
+    cluster.sync();
+    if (ty == 0) {
+      c128 t = {0.0, 0.0};
+      for (int q = 0; q < G; ++q) {
+        const c128* remote = cluster.map_shared_rank(&pbuf[buf][0], q);
+        const c128 v = remote[tx];
+        t.x += v.x;
+        t.y += v.y;
+      }
+      gtot[tx] = t;
+      const c128* rrow = cluster.map_shared_rank(&rbuf[buf][0], owner);
+      rowc[tx] = rrow[tx];
+    }
+    __syncthreads();
+    if (tx == 0 && ty == 0) {
+      const double xnorm = sqrt(fmax(gtot[c].x, 0.0));
+      const double alphr = rowc[c].x, alphi = rowc[c].y;
+      if (xnorm == 0.0 && alphi == 0.0) {
+        s_tau[0] = 0.0; s_tau[1] = 0.0; s_scal[0] = 1.0; s_scal[1] = 0.0; s_beta = alphr;
+      } else {
+        double beta = dlapy3(alphr, alphi, xnorm);
+        beta = (alphr >= 0.0) ? -beta : beta;
+        s_tau[0] = (beta - alphr) / beta;
+        s_tau[1] = -alphi / beta;
+        const double dr = alphr - beta, di = alphi;
+        const double den = dr * dr + di * di;
+        s_scal[0] = dr / den; s_scal[1] = -di / den;
+        s_beta = beta;
+      }
+      if (b == 0) { p.tau[2 * (j0 + c)] = s_tau[0]; p.tau[2 * (j0 + c) + 1] = s_tau[1]; }
+    }
+    __syncthreads();
+    const c128 tau = {s_tau[0], s_tau[1]};
+    const c128 sc = {s_scal[0], s_scal[1]};
+    const bool trivial = (tau.x == 0.0 && tau.y == 0.0);
+    if (ty == 0 && tx > c && tx < jb) {
+      const c128 cs = {sc.x, -sc.y};
+      wv[tx] = cadd(rowc[tx], cmul(cs, gtot[tx]));
+    }
+    __syncthreads();
+    if (!trivial) {
+      const c128 ctau = {tau.x, -tau.y};
+      for (int i = ty; i < nrow; i += CTY) {
+        const int gr = r0 + i;
+        if (gr < grow) continue;
+        c128 v;
+        if (gr == grow) v = {1.0, 0.0};
+        else v = cmul(S[i * NB + c], sc);
+        if (tx > c && tx < jb) {
+          const c128 f = cmul(ctau, cmul(v, wv[tx]));
+          S[i * NB + tx].x -= f.x;
+          S[i * NB + tx].y -= f.y;
+        }
+        __syncwarp();
+        if (tx == c) S[i * NB + c] = (gr == grow) ? c128{s_beta, 0.0} : v;
+      }
+    }
+    __syncthreads();
+  }
+
+  for (int i = ty; i < nrow; i += CTY) {
+    const int gr = r0 + i;
+    if (tx < jb) {
+      const c128 a = S[i * NB + tx];
+      p.A[(long long)gr * p.lda + j0 + tx] = a;
+      c128 v;
+      const int dcol = gr - j0;
+      if (tx < dcol) v = a;
+      else if (tx == dcol) v = {1.0, 0.0};
+      else v = {0.0, 0.0};
+      p.Vall[(long long)gr * p.lda + j0 + tx] = v;
+      S[i * NB + tx] = v;
+    }
+  }
+  __syncthreads();
+  // partial Gram Z[a, c] = sum_i conj(V[i,a]) V[i,c] (a < c), row a = ty, column c = tx; kept in global scratch
+  {
+    const int a = ty;
+    c128 z = {0.0, 0.0};
+    if (tx < jb && a < tx) {
+      for (int i = 0; i < nrow; ++i) {
+        const c128 x = S[i * NB + a], y = S[i * NB + tx];
+        z.x += x.x * y.x + x.y * y.y;
+        z.y += x.x * y.y - x.y * y.x;
+      }
+    }
+    p.zpart[((size_t)b * NB + a) * NB * 2 + 2 * tx] = z.x;
+    p.zpart[((size_t)b * NB + a) * NB * 2 + 2 * tx + 1] = z.y;
+  }
+  __threadfence();
+  cluster.sync();
+  if (b != 0) return;
+  c128* Z = S;
+  c128* T = S + NB * NB;
+  {
+    const int a = ty;
+    c128 z = {0.0, 0.0};
+    for (int q = 0; q < G; ++q) {
+      z.x += __ldcg(&p.zpart[((size_t)q * NB + a) * NB * 2 + 2 * tx]);
+      z.y += __ldcg(&p.zpart[((size_t)q * NB + a) * NB * 2 + 2 * tx + 1]);
+    }
+    Z[a * NB + tx] = z;
+    T[a * NB + tx] = {0.0, 0.0};
+  }
+  __syncthreads();
+  for (int c = 0; c < jb; ++c) {
+    const c128 tau = {__ldcg(&p.tau[2 * (j0 + c)]), __ldcg(&p.tau[2 * (j0 + c) + 1])};
+    if (ty == 0 && tx < c) {
+      c128 s = {0.0, 0.0};
+      for (int q = tx; q < c; ++q) s = cadd(s, cmul(T[tx * NB + q], Z[q * NB + c]));
+      const c128 r = cmul(tau, s);
+      T[tx * NB + c] = {-r.x, -r.y};
+    }
+    if (ty == 0 && tx == c) T[c * NB + c] = tau;
+    __syncthreads();
+  }
+  c128* Tout = p.Tall + (size_t)(j0 / NB) * NB * NB;
+  Tout[ty * NB + tx] = T[ty * NB + tx];
+}
+
 __global__ void k_set_identity(c128* Q, int m, int n, int ld) {
   const long long tot = (long long)m * n;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
@@ -281,8 +454,25 @@ int qr_factor(Handle* h, c128* A, int m, int n, int lda, c128* Q, int ldq) {
   if (m < n) { set_error(h, "qr_factor: needs m >= n"); return TDVP_ERR_SHAPE; }
   static bool configured = false;
   static int max_coop = 0;
+  static int max_cluster = 0;      // largest cluster size the device can co-schedule for the cluster panel kernel
+  constexpr int CL_ROWS = 384;     // slab rows per CTA in the cluster kernel (384*32*16 B = 192 KiB)
   if (!configured) {
     cudaFuncSetAttribute(k_qr_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, SLAB_ROWS * NB * (int)sizeof(c128));
+    cudaFuncSetAttribute(k_qr_panel_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, CL_ROWS * NB * (int)sizeof(c128));
+    cudaFuncSetAttribute(k_qr_panel_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    for (int cs : {16, 8, 4, 2, 1}) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(cs);
+      cfg.blockDim = dim3(32, CTY);
+      cfg.dynamicSmemBytes = CL_ROWS * NB * sizeof(c128);
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int nclusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&nclusters, k_qr_panel_cluster, &cfg) == cudaSuccess && nclusters >= 1) { max_cluster = cs; break; }
+    }
+    cudaGetLastError();
     int nsm = 0, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
@@ -305,19 +495,39 @@ int qr_factor(Handle* h, c128* A, int m, int n, int lda, c128* Q, int ldq) {
     const int j0 = pnl * NB;
     const int jb = (n - j0) < NB ? (n - j0) : NB;
     const int mp = m - j0;
-    int rpc = SLAB_ROWS;
-    int G = (mp + rpc - 1) / rpc;
-    if (G > max_coop) { set_error(h, "qr_factor: matrix too tall for the cooperative panel kernel"); return TDVP_ERR_UNSUPPORTED; }
-    if (G < 1) G = 1;
-    // spread rows evenly
-    rpc = (mp + G - 1) / G;
-    PanelArgs pa{A, lda, m, n, j0, jb, tau, Vall, Tall, gpart, zpart, rpc};
-    void* args[] = {&pa};
-    const size_t smem = sizeof(c128) * (size_t)(rpc > 2 * NB ? rpc : 2 * NB) * NB;
     cudaError_t e;
-    { ProfScope _ps(h->stream, "qr.k_qr_panel"); e = cudaLaunchCooperativeKernel((void*)k_qr_panel, dim3(G), dim3(32, PTY), args, smem, h->stream); }
-    ++g_launch_count;
-    if (e != cudaSuccess) return cuda_fail(h, e, "cudaLaunchCooperativeKernel(k_qr_panel)", __FILE__, __LINE__);
+    if (max_cluster >= 1 && mp <= max_cluster * CL_ROWS) {
+      // one cluster owns the panel: pick the smallest power-of-two cluster that keeps <= 128 rows per CTA if possible
+      int G = 1;
+      while (G < max_cluster && (mp + G - 1) / G > 128) G *= 2;
+      while ((mp + G - 1) / G > CL_ROWS) G *= 2;
+      const int rpc = (mp + G - 1) / G;
+      PanelArgs pa{A, lda, m, n, j0, jb, tau, Vall, Tall, gpart, zpart, rpc};
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(G);
+      cfg.blockDim = dim3(32, CTY);
+      cfg.dynamicSmemBytes = sizeof(c128) * (size_t)(rpc > 2 * NB ? rpc : 2 * NB) * NB;
+      cfg.stream = h->stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = G; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      { ProfScope _ps(h->stream, "qr.k_qr_panel_cluster"); e = cudaLaunchKernelEx(&cfg, k_qr_panel_cluster, pa); }
+      ++g_launch_count;
+      if (e != cudaSuccess) return cuda_fail(h, e, "cudaLaunchKernelEx(k_qr_panel_cluster)", __FILE__, __LINE__);
+    } else {
+      int rpc = SLAB_ROWS;
+      int G = (mp + rpc - 1) / rpc;
+      if (G > max_coop) { set_error(h, "qr_factor: matrix too tall for the cooperative panel kernel"); return TDVP_ERR_UNSUPPORTED; }
+      if (G < 1) G = 1;
+      rpc = (mp + G - 1) / G;  // spread rows evenly
+      PanelArgs pa{A, lda, m, n, j0, jb, tau, Vall, Tall, gpart, zpart, rpc};
+      void* args[] = {&pa};
+      const size_t smem = sizeof(c128) * (size_t)(rpc > 2 * NB ? rpc : 2 * NB) * NB;
+      { ProfScope _ps(h->stream, "qr.k_qr_panel"); e = cudaLaunchCooperativeKernel((void*)k_qr_panel, dim3(G), dim3(32, PTY), args, smem, h->stream); }
+      ++g_launch_count;
+      if (e != cudaSuccess) return cuda_fail(h, e, "cudaLaunchCooperativeKernel(k_qr_panel)", __FILE__, __LINE__);
+    }
     const int nc = n - j0 - jb;
     if (nc > 0) {
       // C <- (I - V T^H V^H) C,  C = A[j0:, j0+jb:]
