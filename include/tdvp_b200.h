@@ -102,6 +102,13 @@ int tdvp_krylov_expm(tdvp_handle_t h, int kind, double scale_re, double scale_im
                      const tdvp_keff_term* kterms, int nterms, int Dl, int d, int Dr,
                      tdvp_c128* psi_inout, int* niter);
 
+/* psi <- normalised lowest (root == 0) or highest (root != 0) eigenvector of H_eff in the Krylov space grown from
+ * psi by textbook Lanczos -- replaces matrix_diagonalize_lanczos (pytdscf/_integrator.py:74-138), the site solve of
+ * improved relaxation.  The small tridiagonal eigenproblem is solved on device (bisection + inverse iteration); the
+ * eigenvector sign is fixed to a positive overlap with the input (LAPACK's sign is unpinned in the reference). */
+int tdvp_lanczos_eigvec(tdvp_handle_t h, const tdvp_heff_term* hterms, int nterms, int Dl, int d, int Dr,
+                        tdvp_c128* psi_inout, int root, double thresh, int* niter);
+
 /* ---- gauge shift ------------------------------------------------------------------------------- */
 /* Householder QR with LAPACK zgeqrf/zungqr conventions -- replaces SiteCoef.gauge_trf
  * (pytdscf/_site_cls.py:138-292).  gauge A: psi(Dl,d,Dr) -> site(Dl,d,k), sigma(k,Dr);

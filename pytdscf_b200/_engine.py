@@ -198,6 +198,16 @@ class Engine:
         check(self.h, rc)
         return int(niter.value)
 
+    def lanczos_eigvec(self, psi: torch.Tensor, hterms, root: int = 0, thresh: float = 1e-9) -> int:
+        """psi <- normalised extremal eigenvector of H_eff (improved relaxation); returns the Lanczos dimension."""
+        _chk_tensor(psi, "psi")
+        Dl, d, Dr = psi.shape
+        niter = C.c_int(0)
+        arr = self.heff_terms(hterms)
+        check(self.h, self.lib.tdvp_lanczos_eigvec(self.h, arr, len(hterms), Dl, d, Dr, _ptr(psi), int(root),
+                                                   float(thresh), C.byref(niter)))
+        return int(niter.value)
+
     # -- gauge -------------------------------------------------------------------------
     def qr_shift(self, gauge: str, psi: torch.Tensor):
         """'A': psi -> (A(Dl,d,k), sigma(k,Dr));  'B': psi -> (B(k,d,Dr), sigma(Dl,k))."""

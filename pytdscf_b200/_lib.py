@@ -64,6 +64,8 @@ SIGNATURES = {
     "tdvp_krylov_expm": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
                                    C.POINTER(HeffTerm), C.POINTER(KeffTerm), C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_void_p, C.POINTER(C.c_int)]),
+    "tdvp_lanczos_eigvec": (C.c_int, [C.c_void_p, C.POINTER(HeffTerm), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                      C.c_int, C.c_double, C.POINTER(C.c_int)]),
     "tdvp_qr_shift": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tdvp_absorb": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tdvp_inner": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(c128)]),

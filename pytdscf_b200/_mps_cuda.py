@@ -239,11 +239,24 @@ class MPSCoefCuda:
         return min(size, min(max(0, self.niter_krylov.get(site, 0) - 2), 15))
 
     def _expm(self, cfg, sign: complex, dt: float, x: torch.Tensor, site: int, kind: int, **terms) -> torch.Tensor:
-        if cfg.relax:
-            raise NotImplementedError("relaxation (imaginary time / improved) is not implemented in backend='cuda' yet")
+        if cfg.relax == "improved":
+            # improved relaxation: eigenvector of H_eff per site, the bond (K) step is skipped (_mps_cls.py:1078-1084, 1159-1160)
+            if kind == 1:
+                return x
+            y = x.clone()
+            niter = self.eng.lanczos_eigvec(y, terms["hterms"], root=0, thresh=1.0e-09)
+            self.niter_krylov[site] = niter
+            if self.record_trace:
+                self.trace.append((kind, site, niter))
+            return y
         n_warm = self._n_warmup(x.numel(), site)
         y = x.clone()
-        niter = self.eng.krylov_expm(cfg.integrator, sign * (dt / 2), cfg.thresh_exp, n_warm, cfg.conserve_norm, y, **terms)
+        if cfg.relax:
+            # imaginary time: exp(-H dt/2) on sites, exp(+K dt/2) on bonds, always the Lanczos variant (_mps_cls.py:1086-1094)
+            scale = (sign * -1j).real * (dt / 2)
+            niter = self.eng.krylov_expm("lanczos", scale, cfg.thresh_exp, n_warm, cfg.conserve_norm, y, **terms)
+        else:
+            niter = self.eng.krylov_expm(cfg.integrator, sign * (dt / 2), cfg.thresh_exp, n_warm, cfg.conserve_norm, y, **terms)
         self.niter_krylov[site] = niter
         if self.record_trace:
             self.trace.append((kind, site, niter))

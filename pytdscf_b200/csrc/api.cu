@@ -8,6 +8,8 @@ namespace tdvp {
 int krylov_expm_exec(Handle* h, int kind, double scale_re, double scale_im, double thresh, int n_warmup,
                      int conserve_norm, const tdvp_heff_term* hterms, const tdvp_keff_term* kterms, int nterms,
                      int Dl, int d, int Dr, c128* psi, int* niter);
+int lanczos_eigvec_exec(Handle* h, const tdvp_heff_term* hterms, int nterms, int Dl, int d, int Dr, c128* psi, int root,
+                        double thresh, int* niter);
 int inner_exec(Handle* h, long long n, const c128* bra, const c128* ket, int conj, c128* host_out);
 int qr_shift_exec(Handle* h, int gauge, int Dl, int d, int Dr, const c128* psi, c128* site, c128* sigma);
 int absorb_exec(Handle* h, int gauge, int Dl, int d, int Dr, int k, const c128* sigma, const c128* site, c128* out);
@@ -166,6 +168,13 @@ int tdvp_krylov_expm(tdvp_handle_t h, int kind, double scale_re, double scale_im
   if (!psi_inout || nterms <= 0 || Dl <= 0 || Dr <= 0 || (hterms && d <= 0)) { set_error(h, "krylov_expm: bad argument"); return TDVP_ERR_ARG; }
   return krylov_expm_exec(h, kind, scale_re, scale_im, thresh, n_warmup, conserve_norm, hterms, kterms, nterms, Dl, d, Dr,
                           (c128*)psi_inout, niter);
+}
+
+int tdvp_lanczos_eigvec(tdvp_handle_t h, const tdvp_heff_term* hterms, int nterms, int Dl, int d, int Dr,
+                        tdvp_c128* psi_inout, int root, double thresh, int* niter) {
+  H_CHECK(h);
+  if (!hterms || !psi_inout || nterms <= 0 || Dl <= 0 || d <= 0 || Dr <= 0) { set_error(h, "lanczos_eigvec: bad argument"); return TDVP_ERR_ARG; }
+  return lanczos_eigvec_exec(h, hterms, nterms, Dl, d, Dr, (c128*)psi_inout, root, thresh, niter);
 }
 
 int tdvp_qr_shift(tdvp_handle_t h, int gauge, int Dl, int d, int Dr, const tdvp_c128* psi, tdvp_c128* site,

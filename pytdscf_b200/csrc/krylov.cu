@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_dot(const c128* __restrict__ x,
     v[0] += a.x * b.x - ay * b.y;
     v[1] += a.x * b.y + ay * b.x;
   }
-  if (reduce_all<2>(v, partial, counter, tot) && threadIdx.x == 0) { out2[0] = tot[0]; out2[1] = tot[1]; }
+  if (reduce_all<2>(v, partial, counter, tot) && threadIdx.x == 0) { out2[0] = tot[0]; out2[1] = (conj == 2) ? 0.0 : tot[1]; }
 }
 
 // |x| -> out[0]
@@ -356,6 +356,114 @@ __global__ void __launch_bounds__(512) k_krylov_small_expm(int mode, int k, cons
   }
 }
 
+// y = sum_{i<k} c[i] V_i for arbitrary k (coefficients read from global memory); err = |y - prev|, ynorm = |y|
+__global__ void __launch_bounds__(RED_THREADS) k_combine_big(const c128* __restrict__ V, long long ldv, int k,
+                                                              const double* __restrict__ coef, c128* __restrict__ y,
+                                                              const c128* __restrict__ prev, long long n, double* partial,
+                                                              unsigned int* counter, double* err_out, double* ynorm_out) {
+  __shared__ double tot[2];
+  double v[2] = {0.0, 0.0};
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    double sx = 0.0, sy = 0.0;
+    for (int i = 0; i < k; ++i) {
+      const c128 a = V[(long long)i * ldv + e];
+      const double cr = __ldg(&coef[2 * i]), ci = __ldg(&coef[2 * i + 1]);
+      sx += cr * a.x - ci * a.y;
+      sy += cr * a.y + ci * a.x;
+    }
+    y[e] = {sx, sy};
+    v[1] += sx * sx + sy * sy;
+    if (prev) {
+      const c128 p = prev[e];
+      const double dx = sx - p.x, dy = sy - p.y;
+      v[0] += dx * dx + dy * dy;
+    }
+  }
+  if (reduce_all<2>(v, partial, counter, tot) && threadIdx.x == 0) {
+    err_out[0] = sqrt(tot[0]);
+    ynorm_out[0] = sqrt(tot[1]);
+  }
+}
+
+// Eigenvector of the real symmetric tridiagonal matrix (diag a[0..k), off-diagonal b[0..k-1)) for its smallest
+// (root == 0) or largest (root != 0) eigenvalue: Sturm-sequence bisection + inverse iteration, one thread
+// (k is the Lanczos dimension).  Sign convention: positive component along the first Lanczos vector.
+// (The reference calls scipy.linalg.eigh_tridiagonal, whose eigenvector sign is LAPACK-internal and unpinned.)
+__global__ void k_tridiag_eigvec(int k, const double* __restrict__ a, const double* __restrict__ b, int root,
+                                 double* __restrict__ coef, double* __restrict__ work) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (k == 1) { coef[0] = 1.0; coef[1] = 0.0; return; }
+  double lo = a[0], hi = a[0], nrm = 0.0;
+  for (int i = 0; i < k; ++i) {
+    const double r = (i > 0 ? fabs(b[i - 1]) : 0.0) + (i < k - 1 ? fabs(b[i]) : 0.0);
+    lo = fmin(lo, a[i] - r);
+    hi = fmax(hi, a[i] + r);
+    nrm = fmax(nrm, fabs(a[i]) + r);
+  }
+  const int target = root == 0 ? 1 : k;  // find lambda with count(lambda) >= target, i.e. the target-th smallest
+  const double tiny = 2.3e-308 / 2.2e-16;
+  for (int it = 0; it < 200; ++it) {
+    const double mid = 0.5 * (lo + hi);
+    if (mid <= lo || mid >= hi) break;
+    int cnt = 0;
+    double q = a[0] - mid;
+    if (q < 0.0) ++cnt;
+    for (int i = 1; i < k; ++i) {
+      if (fabs(q) < tiny) q = (q < 0.0 ? -tiny : tiny);
+      q = a[i] - mid - b[i - 1] * b[i - 1] / q;
+      if (q < 0.0) ++cnt;
+    }
+    if (cnt >= target) hi = mid; else lo = mid;
+  }
+  const double lam = 0.5 * (lo + hi);
+  // inverse iteration on (T - lam I) with partial pivoting (tridiagonal LU, fill-in in du2)
+  double* dl = work;            // sub-diagonal multipliers   (k-1)
+  double* dd = work + k;        // diagonal                   (k)
+  double* du = work + 2 * k;    // first super-diagonal       (k-1)
+  double* du2 = work + 3 * k;   // second super-diagonal      (k-2)
+  double* x = work + 4 * k;     // solution                   (k)
+  int* piv = reinterpret_cast<int*>(work + 5 * k);
+  const double shift = lam + (root == 0 ? -1.0 : 1.0) * 4.0 * 2.2e-16 * fmax(nrm, 1e-300);
+  for (int i = 0; i < k; ++i) { dd[i] = a[i] - shift; x[i] = 1.0 / sqrt((double)k); }
+  for (int i = 0; i < k - 1; ++i) { dl[i] = b[i]; du[i] = b[i]; }
+  for (int i = 0; i < k - 2; ++i) du2[i] = 0.0;
+  for (int i = 0; i < k - 1; ++i) {
+    if (fabs(dd[i]) >= fabs(dl[i])) {
+      piv[i] = 0;
+      if (dd[i] == 0.0) dd[i] = 2.2e-16 * fmax(nrm, 1e-300);
+      const double f = dl[i] / dd[i];
+      dl[i] = f;
+      dd[i + 1] -= f * du[i];
+      if (i < k - 2) du2[i] = 0.0;
+    } else {
+      piv[i] = 1;
+      const double f = dd[i] / dl[i];
+      dd[i] = dl[i];
+      dl[i] = f;
+      const double t = du[i];
+      du[i] = dd[i + 1];
+      dd[i + 1] = t - f * du[i];
+      if (i < k - 2) { du2[i] = du[i + 1]; du[i + 1] = -f * du[i + 1]; }
+    }
+  }
+  if (dd[k - 1] == 0.0) dd[k - 1] = 2.2e-16 * fmax(nrm, 1e-300);
+  for (int iter = 0; iter < 4; ++iter) {
+    for (int i = 0; i < k - 1; ++i) {        // forward: apply L^-1 with the row interchanges
+      if (piv[i]) { const double t = x[i]; x[i] = x[i + 1]; x[i + 1] = t - dl[i] * x[i]; }
+      else x[i + 1] -= dl[i] * x[i];
+    }
+    x[k - 1] /= dd[k - 1];                   // backward: U x = y
+    if (k > 1) x[k - 2] = (x[k - 2] - du[k - 2] * x[k - 1]) / dd[k - 2];
+    for (int i = k - 3; i >= 0; --i) x[i] = (x[i] - du[i] * x[i + 1] - du2[i] * x[i + 2]) / dd[i];
+    double s = 0.0;
+    for (int i = 0; i < k; ++i) s += x[i] * x[i];
+    s = 1.0 / sqrt(s);
+    for (int i = 0; i < k; ++i) x[i] *= s;
+  }
+  const double sg = x[0] < 0.0 ? -1.0 : 1.0;
+  for (int i = 0; i < k; ++i) { coef[2 * i] = sg * x[i]; coef[2 * i + 1] = 0.0; }
+}
+
 __global__ void k_set_scalars(double* p, int n, double v) {
   for (int i = threadIdx.x; i < n; i += blockDim.x) p[i] = v;
 }
@@ -500,6 +608,77 @@ int krylov_expm_exec(Handle* h, int kind, double scale_re, double scale_im, doub
   }
   set_error(h, kind == TDVP_KRYLOV_ARNOLDI ? "Short Iterative Arnoldi is not converged in 20 basis"
                                            : "Short Iterative Lanczos is not converged. Try shorter time interval.");
+  return TDVP_ERR_NOT_CONVERGED;
+}
+
+// Lowest (root = 0) / highest eigenvector of the effective Hamiltonian by textbook Lanczos -- the site solve of
+// improved relaxation (pytdscf/_integrator.py:74-138, matrix_diagonalize_lanczos): alpha_i = Re<v_i|H v_i>, full
+// three-term recurrence, Ritz vector rebuilt every iteration, stop on |y_i - y_{i-1}| < thresh, beta < 1e-12 or
+// i == N.  The result is normalised (pytdscf/_mps_cls.py:1078-1084).
+int lanczos_eigvec_exec(Handle* h, const tdvp_heff_term* hterms, int nterms, int Dl, int d, int Dr, c128* psi, int root,
+                        double thresh, int* niter) {
+  const long long N = (long long)Dl * d * Dr;
+  if (N <= 0) { set_error(h, "lanczos_eigvec: empty vector"); return TDVP_ERR_SHAPE; }
+  long long kmax = N < 3000 ? N : 3000;
+  const long long mem_cap = (long long)((size_t(8) << 30) / (sizeof(c128) * (size_t)N));  // <= 8 GiB of Lanczos vectors
+  if (kmax > mem_cap) kmax = mem_cap < 4 ? 4 : mem_cap;
+  const size_t contr = heff_ws_elems(hterms, nterms, Dl, d, Dr);
+  const size_t need = sizeof(c128) * ((size_t)(kmax + 4) * N + contr) + sizeof(double) * (size_t)(10 * kmax + 64) + 256 * 16;
+  TDVP_TRY(ws_reserve(h, need));
+  c128* V = (c128*)ws_alloc(h, sizeof(c128) * (size_t)(kmax + 2) * N);
+  c128* ybuf[2] = {(c128*)ws_alloc(h, sizeof(c128) * N), (c128*)ws_alloc(h, sizeof(c128) * N)};
+  double* alpha = (double*)ws_alloc(h, sizeof(double) * (size_t)(kmax + 2));   // real diagonal
+  double* beta = (double*)ws_alloc(h, sizeof(double) * (size_t)(kmax + 2));    // beta[i] = |w_i|, off-diagonal i
+  double* coef = (double*)ws_alloc(h, sizeof(double) * 2 * (size_t)(kmax + 2));
+  double* work = (double*)ws_alloc(h, sizeof(double) * 6 * (size_t)(kmax + 2));
+  if (!V || !ybuf[0] || !ybuf[1] || !alpha || !beta || !coef || !work) { set_error(h, "lanczos_eigvec: workspace"); return TDVP_ERR_ARG; }
+  double* S = h->d_scal;
+  cudaStream_t st = h->stream;
+  const int nb = red_blocks(N);
+  TDVP_CUDA(h, cudaMemcpyAsync(V, psi, sizeof(c128) * N, cudaMemcpyDeviceToDevice, st));
+  ++h->krylov_solves;
+  int cur = 0;
+  bool have_prev = false;
+  for (long long i = 0; i <= kmax; ++i) {
+    c128* vi = V + (size_t)i * N;
+    c128* w = V + (size_t)(i + 1) * N;
+    ++h->krylov_matvecs;
+    TDVP_TRY(heff_apply_exec(h, hterms, nterms, Dl, d, Dr, vi, w));
+    { ProfScope _ps(st, "vec.k_dot"); k_dot<<<nb, RED_THREADS, 0, st>>>(vi, w, N, 2, h->d_partial, h->d_counter, S + S_TMP); }
+    TDVP_TRY(lc(h, "k_dot"));
+    TDVP_CUDA(h, cudaMemcpyAsync(alpha + i, S + S_TMP, sizeof(double), cudaMemcpyDeviceToDevice, st));
+    { ProfScope _ps(st, "vec.k_lanczos_update");
+      k_lanczos_update<<<nb, RED_THREADS, 0, st>>>(w, vi, i > 0 ? V + (size_t)(i - 1) * N : nullptr, N, S + S_TMP,
+                                                     i > 0 ? beta + (i - 1) : beta, h->d_partial, h->d_counter, beta + i, S + S_TMP + 4); }
+    TDVP_TRY(lc(h, "k_lanczos_update"));
+    { ProfScope _ps(st, "vec.k_scale_dev"); k_scale_dev<<<nb, RED_THREADS, 0, st>>>(w, w, N, beta + i, 0, 0.0); }
+    TDVP_TRY(lc(h, "k_scale_dev"));
+    const int k = (int)i + 1;
+    { ProfScope _ps(st, "vec.k_tridiag_eigvec"); k_tridiag_eigvec<<<1, 32, 0, st>>>(k, alpha, beta, root, coef, work); }
+    TDVP_TRY(lc(h, "k_tridiag_eigvec"));
+    c128* y = ybuf[cur];
+    { ProfScope _ps(st, "vec.k_combine_big");
+      k_combine_big<<<nb, RED_THREADS, 0, st>>>(V, N, k, coef, y, have_prev ? ybuf[cur ^ 1] : nullptr, N, h->d_partial,
+                                                  h->d_counter, S + S_ERR, S + S_YNORM); }
+    TDVP_TRY(lc(h, "k_combine_big"));
+    TDVP_CUDA(h, cudaMemcpyAsync(h->h_scal + S_BETA, beta + i, sizeof(double), cudaMemcpyDeviceToHost, st));
+    TDVP_CUDA(h, cudaMemcpyAsync(h->h_scal + S_ERR, S + S_ERR, sizeof(double), cudaMemcpyDeviceToHost, st));
+    TDVP_CUDA(h, cudaStreamSynchronize(st));
+    const double b = h->h_scal[S_BETA];
+    if (!(b == b)) { set_error(h, "lanczos_eigvec: NaN in the recurrence"); return TDVP_ERR_NOT_CONVERGED; }
+    bool done = b < EPS_K;
+    if (!done && i > 0) done = (h->h_scal[S_ERR] < thresh) || (i == N);
+    if (done || i == kmax) {
+      if (!done && kmax < N && kmax >= 3000) break;
+      { ProfScope _ps(st, "vec.k_scale_dev"); k_scale_dev<<<nb, RED_THREADS, 0, st>>>(y, psi, N, S + S_YNORM, 0, 0.0); }
+      TDVP_TRY(lc(h, "k_scale_dev"));
+      if (niter) *niter = (int)i + 1;
+      return 0;
+    }
+    have_prev = true;
+    cur ^= 1;
+  }
+  set_error(h, "Lanczos Diagonalization is not converged in 3000 basis");
   return TDVP_ERR_NOT_CONVERGED;
 }
 

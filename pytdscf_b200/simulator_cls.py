@@ -147,8 +147,19 @@ class Simulator:
             raise NotImplementedError("reduced densities are a 'next' row (SURVEY 8(f1)); not in backend='cuda' yet")
         if parallel_split_indices is not None:
             raise NotImplementedError("site-parallel propagation is driven by pytdscf_b200.parallel (torchrun), not by this argument")
-        stepsize_au = (Δt if Δt is not None else stepsize) / units.au_in_fs
-        cfg = RunConfig(jobname=self.jobname + "_prop", relax=False, maxstep=maxstep, thresh_exp=thresh_sil,
+        return self._run(Δt if Δt is not None else stepsize, maxstep, False, restart, savefile_ext, loadfile_ext,
+                         backup_interval, autocorr=autocorr, energy=energy, norm=norm, populations=populations,
+                         observables=observables, thresh_sil=thresh_sil, integrator=integrator,
+                         display_time_unit=display_time_unit, conserve_norm=conserve_norm, write_files=write_files,
+                         record_trace=record_trace, suffix="_prop", adaptive=adaptive,
+                         per_step=(autocorr_per_step, energy_per_step, norm_per_step, populations_per_step, observables_per_step))
+
+    def _run(self, stepsize_fs, maxstep, relax, restart, savefile_ext, loadfile_ext, backup_interval, *, autocorr, energy,
+             norm, populations, observables, thresh_sil, integrator, display_time_unit, conserve_norm, write_files,
+             record_trace, suffix, adaptive=False, per_step=(1, 1, 1, 1, 1)):
+        autocorr_per_step, energy_per_step, norm_per_step, populations_per_step, observables_per_step = per_step
+        stepsize_au = stepsize_fs / units.au_in_fs
+        cfg = RunConfig(jobname=self.jobname + suffix, relax=relax, maxstep=maxstep, thresh_exp=thresh_sil,
                         verbose=self.verbose, space=self.model.space, integrator=integrator, conserve_norm=conserve_norm,
                         display_time_unit=display_time_unit, adaptive=adaptive)
         self.cfg = cfg
@@ -189,8 +200,17 @@ class Simulator:
                 f.close()
         return (last_energy, wf)
 
-    def relax(self, *args, **kwargs):
-        raise NotImplementedError("relaxation is not implemented in backend='cuda' yet (SURVEY 3.5)")
+    def relax(self, stepsize: float = 0.1, maxstep: int = 20, improved: bool = True, restart: bool = False,
+              savefile_ext: str = "_gs", loadfile_ext: str = "", backup_interval: int = 10, norm: bool = True,
+              populations: bool = True, observables: bool = False, integrator: str = "lanczos",
+              display_time_unit: str = "fs", write_files: bool = True, record_trace: bool = False):
+        """Ground-state relaxation (reference ``simulator_cls.py:95-158``): improved relaxation (per-site Lanczos
+        eigen-solve, default) or imaginary-time propagation.  Returns ``(energy, wf)``."""
+        return self._run(stepsize, maxstep, "improved" if improved else True, restart, savefile_ext, loadfile_ext,
+                         backup_interval, autocorr=False, energy=True, norm=norm, populations=populations,
+                         observables=observables, thresh_sil=1.0e-09, integrator=integrator,
+                         display_time_unit=display_time_unit, conserve_norm=True, write_files=write_files,
+                         record_trace=record_trace, suffix="_relax")
 
     def operate(self, *args, **kwargs):
         raise NotImplementedError("operator application is outside the TDVP hot-path scope")

@@ -94,6 +94,17 @@ def _wrap_solver(name):
 _wrap_solver("short_iterative_lanczos")
 _wrap_solver("short_iterative_arnoldi")
 
+_orig_diag = _integrator.matrix_diagonalize_lanczos
+
+
+def _diag_and_record(multiplyOp, psi_states, root=0, thresh=1.0e-09):
+    out = _orig_diag(multiplyOp, psi_states, root, thresh)
+    RECORD["trace"].append((0, int(_Debug.site_now), int(_Debug.niter_krylov[_Debug.site_now])))
+    return out
+
+
+_integrator.matrix_diagonalize_lanczos = _diag_and_record
+
 
 def _reset_reference_state():
     RECORD["props"].clear()
@@ -103,7 +114,7 @@ def _reset_reference_state():
 
 
 def run_reference(name, basis, operators, *, bond_dim, hartree, dt_fs, nstep, space="hilbert",
-                  integrator="lanczos", conserve_norm=True, vibstate=None, thresh_sil=1e-9):
+                  integrator="lanczos", conserve_norm=True, vibstate=None, thresh_sil=1e-9, relax=None):
     """Run Simulator.propagate and dump inputs + outputs to tests/golden/<name>.npz."""
     _reset_reference_state()
     model = Model(basis, operators, bond_dim=bond_dim, space=space)
@@ -123,10 +134,17 @@ def run_reference(name, basis, operators, *, bond_dim, hartree, dt_fs, nstep, sp
 
             init = MPSCoefMPO.alloc_random(model)
             init_cores = [np.array(s.data) for s in init.superblock_states[0]]
-            ener, wf = sim.propagate(stepsize=dt_fs, maxstep=nstep, thresh_sil=thresh_sil,
-                                     integrator=integrator, conserve_norm=conserve_norm,
-                                     energy=(space == "hilbert"), autocorr=(space == "hilbert"),
-                                     norm=(space == "hilbert"), populations=False)
+            if relax is None:
+                ener, wf = sim.propagate(stepsize=dt_fs, maxstep=nstep, thresh_sil=thresh_sil,
+                                         integrator=integrator, conserve_norm=conserve_norm,
+                                         energy=(space == "hilbert"), autocorr=(space == "hilbert"),
+                                         norm=(space == "hilbert"), populations=False)
+            else:
+                import contextlib
+                import io
+
+                with contextlib.redirect_stdout(io.StringIO()):  # the reference prints a debug line per site
+                    ener, wf = sim.relax(stepsize=dt_fs, maxstep=nstep, improved=(relax == "improved"), populations=False)
         finally:
             os.chdir(cwd)
     ham = model.hamiltonian
@@ -139,6 +157,7 @@ def run_reference(name, basis, operators, *, bond_dim, hartree, dt_fs, nstep, sp
         "space": np.array(space),
         "integrator": np.array(integrator),
         "conserve_norm": np.array(conserve_norm),
+        "relax": np.array("" if relax is None else relax),
         "thresh_sil": np.array(thresh_sil),
         "coupleJ": np.array(complex(ham.coupleJ[0][0])),
         "nkeys": np.array(len(mpo.operators)),
@@ -438,6 +457,10 @@ def main():
     run_reference("henon_heiles_f6", prims, ops, bond_dim=8, hartree=None, vibstate=vib, dt_fs=0.05, nstep=4)
     prims, ops = h2co_model()
     run_reference("h2co_D16", prims, ops, bond_dim=16, hartree=None, dt_fs=0.1, nstep=4)
+    prims, ops, vib = henon_heiles_model(2000, 1.0e-3, 4, 6)
+    run_reference("relax_improved_hh4", prims, ops, bond_dim=6, hartree=None, vibstate=vib, dt_fs=0.1, nstep=4, relax="improved")
+    prims, ops, vib = henon_heiles_model(2000, 1.0e-3, 4, 6)
+    run_reference("relax_imag_hh4", prims, ops, bond_dim=6, hartree=None, vibstate=vib, dt_fs=0.5, nstep=4, relax="imag")
     basis, ops, hartree = liouville_model()
     run_reference("liouville_spin3", basis, ops, bond_dim=8, hartree=hartree, dt_fs=2.0, nstep=5,
                   space="liouville", integrator="arnoldi")

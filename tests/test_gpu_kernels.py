@@ -290,3 +290,23 @@ def test_argument_errors_do_not_crash(eng, K):
     L = eng.to_device(K["L"])  # w = 3 with an identity core -> unsupported, as in the reference (gap cores crash there)
     with pytest.raises(TdvpError):
         eng.heff_apply([(L, None, None, 1.0)], eng.to_device(K["psi"]))
+
+
+def test_lanczos_eigvec(eng):
+    """Ground vector of a dense Hermitian operator through the H_eff interface vs the oracle's textbook Lanczos."""
+    rng = np.random.default_rng(17)
+    n = 60
+    H = crand(rng, n, n)
+    H = (H + H.conj().T) / 2 + np.diag(np.linspace(-3, 3, n))
+    x = crand(rng, n)
+    x /= np.linalg.norm(x)
+    ref, nref = orc.lanczos_ground_state(lambda v: H @ v, x)
+    ref = ref / np.linalg.norm(ref)
+    psi = eng.to_device(x.reshape(n, 1, 1))
+    niter = eng.lanczos_eigvec(psi, [(eng.to_device(H.reshape(n, 1, n)), None, None, 1.0)])
+    got = psi.cpu().numpy().reshape(-1)
+    assert abs(niter - nref) <= 1
+    assert abs(abs(np.vdot(got, ref)) - 1) < 1e-9
+    assert abs(np.linalg.norm(got) - 1) < 1e-13
+    assert np.linalg.norm(H @ got - np.vdot(got, H @ got) * got) < 1e-7
+    assert abs(np.vdot(got, H @ got).real - np.linalg.eigvalsh(H)[0]) < 1e-9
