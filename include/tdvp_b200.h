@@ -120,6 +120,18 @@ int tdvp_qr_shift(tdvp_handle_t h, int gauge, int Dl, int d, int Dr, const tdvp_
 int tdvp_absorb(tdvp_handle_t h, int gauge, int Dl, int d, int Dr, int k, const tdvp_c128* sigma,
                 const tdvp_c128* site, tdvp_c128* out);
 
+/* ---- bond-matrix SVD (parallel / adaptive modes) --------------------------------------------------- */
+/* SVD of the square bond matrix sigma(n,n) with the reference's truncation rule -- replaces truncate_sigvec
+ * (pytdscf/_site_cls.py:586-690): keep the smallest idx with cumsum(s)[idx-1] / sum(s) >= 1 - p (singular VALUES,
+ * not squares), optional flooring of small values (regularize: s + 1e-4 exp(-s/1e-4)), renormalised.
+ * Outputs: U(n,n) and Vh(n,n) complete unitaries (leading *rank columns / rows are the kept ones), S = diag(s/|s|)
+ * as a (k,k) matrix with k = n (keepdim, zero-padded) or k = *rank.  One-sided Jacobi on device; the truncation
+ * decision reads the singular values back to the host. */
+int tdvp_svd_truncate(tdvp_handle_t h, int m, int n, const tdvp_c128* sigma, double p, int keepdim, int regularize,
+                      tdvp_c128* U, tdvp_c128* S, tdvp_c128* Vh, int* rank);
+/* out(n,m) = pinv(X(m,n), rcond) -- replaces np.linalg.pinv in multiply_sigvec_pinv (pytdscf/_site_cls.py:734). */
+int tdvp_pinv(tdvp_handle_t h, int m, int n, const tdvp_c128* X, double rcond, tdvp_c128* out);
+
 /* ---- observables on device --------------------------------------------------------------------- */
 /* <bra|ket> = sum conj(bra_i) ket_i (conj != 0) or sum bra_i ket_i  -- np.inner of
  * pytdscf/_integrator.py:65-71.  Result is written to host memory (synchronises the stream). */

@@ -242,6 +242,27 @@ class Engine:
         check(self.h, self.lib.tdvp_absorb(self.h, g, Dl, d, Dr, k, _ptr(sigma), _ptr(site), _ptr(out)))
         return out
 
+    # -- bond SVD ------------------------------------------------------------------------
+    def svd_truncate(self, sigma: torch.Tensor, p: float, keepdim: bool = False, regularize: bool = False):
+        """(U, S, Vh, rank) of ``truncate_sigvec(None, sigma, None, p, regularize, keepdim)``."""
+        _chk_tensor(sigma, "sigma")
+        n = int(sigma.shape[0])
+        U, Vh, S = self.empty(n, n), self.empty(n, n), self.empty(n, n)
+        rank = C.c_int(0)
+        check(self.h, self.lib.tdvp_svd_truncate(self.h, n, int(sigma.shape[1]), _ptr(sigma), float(p), int(keepdim),
+                                                 int(regularize), _ptr(U), _ptr(S), _ptr(Vh), C.byref(rank)))
+        r = int(rank.value)
+        if keepdim:
+            return U, S, Vh, r
+        return U[:, :r].contiguous(), S.reshape(-1)[: r * r].reshape(r, r), Vh[:r, :].contiguous(), r
+
+    def pinv(self, X: torch.Tensor, rcond: float = 1e-13) -> torch.Tensor:
+        _chk_tensor(X, "X")
+        m, n = X.shape
+        out = self.empty(n, m)
+        check(self.h, self.lib.tdvp_pinv(self.h, m, n, _ptr(X), float(rcond), _ptr(out)))
+        return out
+
     # -- observables -------------------------------------------------------------------
     def inner(self, bra: torch.Tensor, ket: torch.Tensor, conj: bool = True) -> complex:
         _chk_tensor(bra, "bra")

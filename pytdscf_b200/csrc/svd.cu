@@ -1,0 +1,348 @@
+// Bond-matrix SVD, truncation and pseudo-inverse on the device.
+//
+// Replaces (reference file:line):
+//   svd_exec + tdvp_svd_truncate   scipy.linalg.svd + cumulative-weight truncation in truncate_sigvec
+//                                  (pytdscf/_site_cls.py:586-690)
+//   tdvp_pinv                      np.linalg.pinv(X, rcond) in multiply_sigvec_pinv (pytdscf/_site_cls.py:709-754)
+//
+// Algorithm: one-sided (Hestenes) Jacobi on the columns of sigma, complex version: for a column pair (p, q) with
+// gamma = g_p^H g_q = |gamma| e^{i phi} the pair (g_p, g_q e^{-i phi}) is rotated by the real Jacobi rotation that
+// zeroes their inner product; V accumulates the same unitary, so sigma V = G at all times.  Pairs of one round of
+// the round-robin tournament are independent and are spread over the CTAs of a cooperative grid (one grid sync per
+// round).  One-sided Jacobi orthogonalises tiny columns to THEIR OWN scale (high relative accuracy), so U stays
+// unitary down to the smallest non-zero singular value; exactly-zero columns are completed by a Householder QR of
+// the padded matrix (the same LAPACK-style null-space completion the gauge shift uses).
+#include <cooperative_groups.h>
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "contract.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace tdvp {
+
+int qr_factor(Handle* h, c128* A, int m, int n, int lda, c128* Q, int ldq);
+size_t qr_ws_elems(int m, int n);
+
+namespace {
+
+constexpr int JT = 256;
+
+__device__ __forceinline__ void block_sum3(double& a, double& b, double& c, double& d_, double* sm) {
+  // sums 4 doubles over the block; results broadcast to all threads
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  double v[4] = {a, b, c, d_};
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+  __syncthreads();
+  if (lane == 0) { sm[warp * 4 + 0] = v[0]; sm[warp * 4 + 1] = v[1]; sm[warp * 4 + 2] = v[2]; sm[warp * 4 + 3] = v[3]; }
+  __syncthreads();
+  double t[4] = {0, 0, 0, 0};
+  for (int w = 0; w < nw; ++w) { t[0] += sm[w * 4]; t[1] += sm[w * 4 + 1]; t[2] += sm[w * 4 + 2]; t[3] += sm[w * 4 + 3]; }
+  a = t[0]; b = t[1]; c = t[2]; d_ = t[3];
+}
+
+// Gt: n x m (row j = column j of sigma), Vt: n x n (row j = column j of V).  n may be odd (a bye is inserted).
+__global__ void __launch_bounds__(JT) k_jacobi_svd(c128* __restrict__ Gt, c128* __restrict__ Vt, int n, int m, int max_sweeps,
+                                                    double tol, int* __restrict__ flags /* [0]: rotations in this sweep */) {
+  __shared__ double sm[4 * (JT / 32)];
+  cg::grid_group grid = cg::this_grid();
+  const int ne = (n + 1) & ~1;           // players (even)
+  const int npairs = ne / 2;
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) flags[(sweep + 1) % 3] = 0;   // reset the counter of the NEXT sweep (3 slots: no reader of slot sweep-1 is disturbed)
+    for (int r = 0; r < ne - 1; ++r) {
+      for (int t = blockIdx.x; t < npairs; t += gridDim.x) {
+        int p, q;
+        if (t == 0) { p = ne - 1; q = r; }
+        else { p = (r + t) % (ne - 1); q = (r - t + (ne - 1)) % (ne - 1); }
+        if (p >= n || q >= n) continue;   // bye
+        if (p > q) { const int x = p; p = q; q = x; }
+        c128* gp = Gt + (size_t)p * m;
+        c128* gq = Gt + (size_t)q * m;
+        double al = 0.0, be = 0.0, gr = 0.0, gi = 0.0;
+        for (int i = threadIdx.x; i < m; i += blockDim.x) {
+          const c128 x = gp[i], y = gq[i];
+          al += x.x * x.x + x.y * x.y;
+          be += y.x * y.x + y.y * y.y;
+          gr += x.x * y.x + x.y * y.y;   // conj(x) * y
+          gi += x.x * y.y - x.y * y.x;
+        }
+        block_sum3(al, be, gr, gi, sm);
+        const double ga = hypot(gr, gi);
+        if (ga > tol * sqrt(al) * sqrt(be) && ga > 0.0) {
+          if (threadIdx.x == 0) atomicAdd(&flags[sweep % 3], 1);
+          const double pr = gr / ga, pi = gi / ga;          // e^{i phi}
+          const double zeta = (be - al) / (2.0 * ga);
+          const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          const double c = 1.0 / sqrt(1.0 + tt * tt), s = c * tt;
+          for (int i = threadIdx.x; i < m; i += blockDim.x) {
+            const c128 x = gp[i], y = gq[i];
+            const c128 yt = {y.x * pr + y.y * pi, y.y * pr - y.x * pi};   // y * e^{-i phi}
+            gp[i] = {c * x.x - s * yt.x, c * x.y - s * yt.y};
+            gq[i] = {s * x.x + c * yt.x, s * x.y + c * yt.y};
+          }
+          c128* vp = Vt + (size_t)p * n;
+          c128* vq = Vt + (size_t)q * n;
+          for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const c128 x = vp[i], y = vq[i];
+            const c128 yt = {y.x * pr + y.y * pi, y.y * pr - y.x * pi};
+            vp[i] = {c * x.x - s * yt.x, c * x.y - s * yt.y};
+            vq[i] = {s * x.x + c * yt.x, s * x.y + c * yt.y};
+          }
+        }
+        __syncthreads();
+      }
+      __threadfence();
+      grid.sync();
+    }
+    const int nrot = *((volatile int*)&flags[sweep % 3]);
+    if (nrot == 0) break;
+  }
+}
+
+// norms[j] = |Gt[j, :]|
+__global__ void k_row_norms(const c128* __restrict__ Gt, int n, int m, double* __restrict__ norms) {
+  __shared__ double sm[4 * (JT / 32)];
+  for (int j = blockIdx.x; j < n; j += gridDim.x) {
+    double a = 0.0, b = 0.0, c = 0.0, d = 0.0;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+      const c128 x = Gt[(size_t)j * m + i];
+      a += x.x * x.x + x.y * x.y;
+    }
+    block_sum3(a, b, c, d, sm);
+    if (threadIdx.x == 0) norms[j] = sqrt(a);
+    __syncthreads();
+  }
+}
+
+// U[i, jj] = Gt[perm[jj], i] / s[jj] (zero column when s == 0); Vh[jj, i] = conj(Vt[perm[jj], i])
+__global__ void k_assemble_uv(const c128* __restrict__ Gt, const c128* __restrict__ Vt, const int* __restrict__ perm,
+                              const double* __restrict__ s, int n, int m, c128* __restrict__ U, int ldu,
+                              c128* __restrict__ Vh, int ldv) {
+  const long long totU = (long long)m * n, totV = (long long)n * n;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < totU + totV; e += (long long)gridDim.x * blockDim.x) {
+    if (e < totU) {
+      const int i = (int)(e / n), jj = (int)(e % n);
+      const double sv = s[jj];
+      c128 g = Gt[(size_t)perm[jj] * m + i];
+      if (sv > 0.0) { g.x /= sv; g.y /= sv; } else { g.x = 0.0; g.y = 0.0; }
+      U[(size_t)i * ldu + jj] = g;
+    } else {
+      const long long f = e - totU;
+      const int jj = (int)(f / n), i = (int)(f % n);
+      const c128 v = Vt[(size_t)perm[jj] * n + i];
+      Vh[(size_t)jj * ldv + i] = {v.x, -v.y};
+    }
+  }
+}
+
+// copy columns [c0, c1) of src (ld lds) into the same columns of dst (ld ldd), m rows
+__global__ void k_copy_cols(const c128* __restrict__ src, int lds, c128* __restrict__ dst, int ldd, int m, int c0, int c1) {
+  const int w = c1 - c0;
+  const long long tot = (long long)m * w;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(e / w), j = c0 + (int)(e % w);
+    dst[(size_t)i * ldd + j] = src[(size_t)i * lds + j];
+  }
+}
+
+// rows[j, :] *= f[j]
+__global__ void k_scale_rows(c128* __restrict__ A, int rows, int cols, int ld, const double* __restrict__ f) {
+  const long long tot = (long long)rows * cols;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(e / cols), j = (int)(e % cols);
+    c128& v = A[(size_t)i * ld + j];
+    v.x *= f[i];
+    v.y *= f[i];
+  }
+}
+
+__global__ void k_diag_matrix(c128* __restrict__ S, int k, const double* __restrict__ vals) {
+  const long long tot = (long long)k * k;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(e / k), j = (int)(e % k);
+    S[e] = {i == j ? vals[i] : 0.0, 0.0};
+  }
+}
+
+int ls(Handle* h, const char* what) {
+  ++g_launch_count;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(h, e, what, __FILE__, __LINE__);
+  return 0;
+}
+
+// Orthonormal completion of the last (n - r) columns of the m x n matrix U whose first r columns are orthonormal:
+// Householder QR of [U_r | 0] gives Q whose trailing columns span the orthogonal complement.
+int complete_columns(Handle* h, c128* U, int m, int n, int ldu, int r) {
+  if (r >= n) return 0;
+  c128* W = (c128*)ws_alloc(h, sizeof(c128) * (size_t)m * n);
+  c128* Q = (c128*)ws_alloc(h, sizeof(c128) * (size_t)m * n);
+  if (!W || !Q) { set_error(h, "svd: workspace (completion)"); return TDVP_ERR_ARG; }
+  TDVP_CUDA(h, cudaMemsetAsync(W, 0, sizeof(c128) * (size_t)m * n, h->stream));
+  if (r > 0) {
+    k_copy_cols<<<148, 256, 0, h->stream>>>(U, ldu, W, n, m, 0, r);
+    TDVP_TRY(ls(h, "k_copy_cols"));
+  }
+  TDVP_TRY(qr_factor(h, W, m, n, n, Q, n));
+  k_copy_cols<<<148, 256, 0, h->stream>>>(Q, n, U, ldu, m, r, n);
+  return ls(h, "k_copy_cols");
+}
+
+}  // namespace
+
+// Thin SVD sigma(m x n, row-major, m >= n) = U(m x n) diag(s) Vh(n x n); s descending, copied to host_s.
+int svd_exec(Handle* h, int m, int n, const c128* sigma, c128* U, c128* Vh, double* host_s) {
+  if (m < n) { set_error(h, "svd: needs m >= n"); return TDVP_ERR_SHAPE; }
+  const size_t need = sizeof(c128) * ((size_t)n * m + (size_t)n * n + 2 * (size_t)m * n + qr_ws_elems(m, n)) +
+                      sizeof(double) * 4 * (size_t)n + 4096;
+  TDVP_TRY(ws_reserve(h, need));
+  c128* Gt = (c128*)ws_alloc(h, sizeof(c128) * (size_t)n * m);
+  c128* Vt = (c128*)ws_alloc(h, sizeof(c128) * (size_t)n * n);
+  double* norms = (double*)ws_alloc(h, sizeof(double) * n);
+  double* svals = (double*)ws_alloc(h, sizeof(double) * n);
+  int* perm = (int*)ws_alloc(h, sizeof(int) * n);
+  int* flags = (int*)ws_alloc(h, sizeof(int) * 4);
+  if (!Gt || !Vt || !norms || !svals || !perm || !flags) { set_error(h, "svd: workspace"); return TDVP_ERR_ARG; }
+  cudaStream_t st = h->stream;
+  TDVP_TRY(permute_site(h, sigma, Gt, m, 1, n));   // Gt[j, i] = sigma[i, j]
+  TDVP_CUDA(h, cudaMemsetAsync(Vt, 0, sizeof(c128) * (size_t)n * n, st));
+  {
+    std::vector<double> one(1, 1.0);
+    // identity: strided 2D copy of a device scalar would need a kernel; reuse k_diag_matrix with ones
+    double* ones = (double*)ws_alloc(h, sizeof(double) * n);
+    if (!ones) { set_error(h, "svd: workspace"); return TDVP_ERR_ARG; }
+    std::vector<double> hv(n, 1.0);
+    TDVP_CUDA(h, cudaMemcpyAsync(ones, hv.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    TDVP_CUDA(h, cudaStreamSynchronize(st));
+    k_diag_matrix<<<148, 256, 0, st>>>(Vt, n, ones);
+    TDVP_TRY(ls(h, "k_diag_matrix"));
+  }
+  TDVP_CUDA(h, cudaMemsetAsync(flags, 0, sizeof(int) * 4, st));
+  {
+    static int max_blocks = 0;
+    if (max_blocks == 0) {
+      int nsm = 0, dev = 0, per = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_jacobi_svd, JT, 0);
+      max_blocks = nsm * (per > 4 ? 4 : (per < 1 ? 1 : per));
+    }
+    int grid = (n + 1) / 2;
+    if (grid > max_blocks) grid = max_blocks;
+    if (grid < 1) grid = 1;
+    int max_sweeps = 40;
+    double tol = 1.0e-15;
+    void* args[] = {&Gt, &Vt, &n, &m, &max_sweeps, &tol, &flags};
+    cudaError_t e;
+    { ProfScope _ps(st, "svd.k_jacobi_svd"); e = cudaLaunchCooperativeKernel((void*)k_jacobi_svd, dim3(grid), dim3(JT), args, 0, st); }
+    ++g_launch_count;
+    if (e != cudaSuccess) return cuda_fail(h, e, "cudaLaunchCooperativeKernel(k_jacobi_svd)", __FILE__, __LINE__);
+  }
+  k_row_norms<<<148, JT, 0, st>>>(Gt, n, m, norms);
+  TDVP_TRY(ls(h, "k_row_norms"));
+  std::vector<double> hn(n);
+  TDVP_CUDA(h, cudaMemcpyAsync(hn.data(), norms, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  TDVP_CUDA(h, cudaStreamSynchronize(st));
+  // ordering of the (already computed) singular values is index bookkeeping: descending, stable
+  std::vector<int> hp(n);
+  for (int i = 0; i < n; ++i) hp[i] = i;
+  std::stable_sort(hp.begin(), hp.end(), [&](int a, int b) { return hn[a] > hn[b]; });
+  std::vector<double> hs(n);
+  int r = 0;
+  for (int i = 0; i < n; ++i) { hs[i] = hn[hp[i]]; if (hs[i] > 0.0) r = i + 1; }
+  TDVP_CUDA(h, cudaMemcpyAsync(perm, hp.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
+  TDVP_CUDA(h, cudaMemcpyAsync(svals, hs.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  k_assemble_uv<<<148 * 2, 256, 0, st>>>(Gt, Vt, perm, svals, n, m, U, n, Vh, n);
+  TDVP_TRY(ls(h, "k_assemble_uv"));
+  TDVP_CUDA(h, cudaStreamSynchronize(st));   // hp / hs are host temporaries
+  if (r < n) TDVP_TRY(complete_columns(h, U, m, n, n, r));
+  for (int i = 0; i < n; ++i) host_s[i] = hs[i];
+  return 0;
+}
+
+}  // namespace tdvp
+
+using namespace tdvp;
+
+extern "C" {
+
+int tdvp_svd_truncate(tdvp_handle_t hh, int m, int n, const tdvp_c128* sigma, double p, int keepdim, int regularize,
+                      tdvp_c128* U, tdvp_c128* S, tdvp_c128* Vh, int* rank) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return TDVP_ERR_ARG;
+  h->err.clear();
+  if (!sigma || !U || !S || !Vh || !rank || m <= 0 || n <= 0 || m != n) {
+    set_error(h, "svd_truncate: bad argument (the bond matrix must be square)");
+    return TDVP_ERR_ARG;
+  }
+  std::vector<double> s(n);
+  TDVP_TRY(svd_exec(h, m, n, (const c128*)sigma, (c128*)U, (c128*)Vh, s.data()));
+  // cumulative singular-VALUE weight (not squared), first index with contribution >= 1 - p  (_site_cls.py:629-634)
+  std::vector<double> cs(n);
+  double acc = 0.0;
+  for (int i = 0; i < n; ++i) { acc += s[i]; cs[i] = acc; }
+  int idx = n;
+  for (int i = 0; i < n; ++i) if (cs[i] / cs[n - 1] >= 1.0 - p) { idx = i + 1; break; }
+  std::vector<double> thin(s.begin(), s.begin() + idx);
+  const double sqrt_epsrho = 1.0e-4;   // SQRT_EPSRHO, _site_cls.py:22
+  if (regularize && !(m == 1 && n == 1))
+    for (double& v : thin) if (!(v > sqrt_epsrho)) v = v + sqrt_epsrho * std::exp(-v / sqrt_epsrho);
+  double nrm = 0.0;
+  for (double v : thin) nrm += v * v;
+  nrm = std::sqrt(nrm);
+  const int k = keepdim ? n : idx;
+  std::vector<double> diag(k, 0.0);
+  for (int i = 0; i < idx; ++i) diag[i] = thin[i] / nrm;
+  double* dvals = (double*)ws_alloc(h, sizeof(double) * k);
+  if (!dvals) { set_error(h, "svd_truncate: workspace"); return TDVP_ERR_ARG; }
+  TDVP_CUDA(h, cudaMemcpyAsync(dvals, diag.data(), sizeof(double) * k, cudaMemcpyHostToDevice, h->stream));
+  k_diag_matrix<<<148, 256, 0, h->stream>>>((c128*)S, k, dvals);
+  ++g_launch_count;
+  TDVP_CUDA(h, cudaStreamSynchronize(h->stream));
+  // without keepdim the caller uses the leading idx columns of U (ld n) and rows of Vh
+  *rank = idx;
+  return 0;
+}
+
+int tdvp_pinv(tdvp_handle_t hh, int m, int n, const tdvp_c128* X, double rcond, tdvp_c128* out) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return TDVP_ERR_ARG;
+  h->err.clear();
+  if (!X || !out || m <= 0 || n <= 0 || m != n) { set_error(h, "pinv: bad argument (square matrices only)"); return TDVP_ERR_ARG; }
+  c128 *U = nullptr, *Vh = nullptr;
+  TDVP_CUDA(h, cudaMalloc((void**)&U, sizeof(c128) * (size_t)m * n));
+  TDVP_CUDA(h, cudaMalloc((void**)&Vh, sizeof(c128) * (size_t)n * n));
+  std::vector<double> s(n);
+  int rc = svd_exec(h, m, n, (const c128*)X, U, Vh, s.data());
+  if (rc == 0) {
+    std::vector<double> inv(n);
+    const double cut = rcond * s[0];
+    for (int i = 0; i < n; ++i) inv[i] = (s[i] > cut) ? 1.0 / s[i] : 0.0;
+    double* dinv = (double*)ws_alloc(h, sizeof(double) * n);
+    if (!dinv) { set_error(h, "pinv: workspace"); rc = TDVP_ERR_ARG; }
+    if (rc == 0) {
+      cudaMemcpyAsync(dinv, inv.data(), sizeof(double) * n, cudaMemcpyHostToDevice, h->stream);
+      k_scale_rows<<<148, 256, 0, h->stream>>>(Vh, n, n, n, dinv);
+      ++g_launch_count;
+      // out(n x m) = Vh^H (n x k) . U^H (k x m)
+      GemmDesc g = gemm_rowmajor(n, m, n, Vh, n, true, true, U, n, true, (c128*)out, m);
+      g.b_conj = 1;
+      g.tag = "pinv";
+      cudaError_t e = zgemm_auto(g, h->stream, h->d_splitk, SPLITK_SCRATCH_ELEMS);
+      if (e != cudaSuccess) rc = cuda_fail(h, e, "zgemm(pinv)", __FILE__, __LINE__);
+      cudaStreamSynchronize(h->stream);
+    }
+  }
+  cudaFree(U);
+  cudaFree(Vh);
+  return rc;
+}
+
+}  // extern "C"

@@ -110,14 +110,20 @@ size_t prof_json(char* out, size_t cap) {
 
 namespace {
 
-constexpr int BM = 128, BN = 64, THREADS = 256;
-constexpr int BK = 16, STAGES = 3;
-constexpr int A_STAGE = BM * BK;  // c128 elements per stage
-constexpr int B_STAGE = BN * BK;
-constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) * (int)sizeof(c128);  // 144 KiB
-constexpr int A_ITERS = A_STAGE / THREADS;  // cp.async per thread per stage
-constexpr int B_ITERS = B_STAGE / THREADS;
-static_assert(THREADS % BK == 0 && THREADS % BM == 0 && THREADS % BN == 0, "tile / thread mapping");
+// Tile configurations.  The warp tile is always 32x32 complex (64 independent DMMA accumulations per k4-step).
+//   Big:   4x2 warps -> CTA tile 128x64, BK = 16, 3 stages (144 KiB), 1 CTA/SM      (bulk of the D >= 256 work)
+//   Small: 2x1 warps -> CTA tile  64x32, BK = 8,  4 stages ( 48 KiB), 4 CTAs/SM     (D <= 128: more CTAs, same 8 warps/SM)
+template <int WMW_, int WNW_, int BK_, int STAGES_>
+struct Cfg {
+  static constexpr int WMW = WMW_, WNW = WNW_, BK = BK_, STAGES = STAGES_;
+  static constexpr int BM = 32 * WMW, BN = 32 * WNW, THREADS = 32 * WMW * WNW;
+  static constexpr int A_STAGE = BM * BK, B_STAGE = BN * BK;
+  static constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) * (int)sizeof(c128);
+  static constexpr int A_ITERS = A_STAGE / THREADS, B_ITERS = B_STAGE / THREADS;
+  static_assert(THREADS % BK == 0 && THREADS % BM == 0 && THREADS % BN == 0, "tile / thread mapping");
+};
+using BigCfg = Cfg<4, 2, 16, 3>;
+using SmallCfg = Cfg<2, 1, 8, 4>;
 
 __device__ __forceinline__ void cp_async16(c128* smem, const c128* gmem, bool pred) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -142,7 +148,7 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 
 // SMEM chunk (16 B) index of tile element; the XOR keeps the 8 lanes of every LDS.128 phase on
 // distinct 16-byte bank groups (see DESIGN.md for the bank arithmetic).
-template <bool KMAJOR, int ROWS>
+template <bool KMAJOR, int ROWS, int BK>
 __device__ __forceinline__ int tile_chunk(int r, int k) {  // r: m or n inside the tile, k in [0, BK)
   if (KMAJOR) return r * BK + (k ^ ((r & 1) << 2));
   return k * ROWS + (r ^ ((k & 3) << 1));
@@ -151,7 +157,7 @@ __device__ __forceinline__ int tile_chunk(int r, int k) {  // r: m or n inside t
 // Per-thread global->shared copy plan of one operand tile (ROWS x BK), fixed for the whole k loop.
 //   K-major (k contiguous in memory): thread owns k-chunk kc = tid % BK of rows tid / BK + (THREADS / BK) * i
 //   row-major in m/n (the other index contiguous): thread owns row tid % ROWS for k = tid / ROWS + (THREADS / ROWS) * i
-template <bool KMAJOR, int ROWS, int ITERS>
+template <bool KMAJOR, int ROWS, int ITERS, int BK, int THREADS>
 struct LoadPlan {
   long long off[KMAJOR ? ITERS : 1];
   unsigned ok;  // bit i: row of iteration i is inside the matrix
@@ -191,13 +197,14 @@ struct LoadPlan {
       }
       const int k = k0 + kl;
       const bool p = ((ok >> i) & 1u) && (k < k_end);
-      cp_async16(smem + tile_chunk<KMAJOR, ROWS>(r, kl), p ? (g + o + (long long)k * kstride) : g, p);
+      cp_async16(smem + tile_chunk<KMAJOR, ROWS, BK>(r, kl), p ? (g + o + (long long)k * kstride) : g, p);
     }
   }
 };
 
-template <bool A_KMAJOR, bool B_KMAJOR>
-__global__ void __launch_bounds__(THREADS, 1) zgemm_dmma_kernel(const GemmDesc d) {
+template <typename C, bool A_KMAJOR, bool B_KMAJOR>
+__global__ void __launch_bounds__(C::THREADS, C::THREADS == 256 ? 1 : 4) zgemm_dmma_kernel(const GemmDesc d) {
+  constexpr int BM = C::BM, BN = C::BN, BK = C::BK, STAGES = C::STAGES, A_STAGE = C::A_STAGE, B_STAGE = C::B_STAGE;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   c128* As = reinterpret_cast<c128*>(smem_raw);
   c128* Bs = As + STAGES * A_STAGE;
@@ -205,7 +212,7 @@ __global__ void __launch_bounds__(THREADS, 1) zgemm_dmma_kernel(const GemmDesc d
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, q = lane & 3;
-  const int wm = warp & 3, wn = warp >> 2;
+  const int wm = warp % C::WMW, wn = warp / C::WMW;
   const int tile_m = blockIdx.y * BM, tile_n = blockIdx.x * BN;
   const long long bz = blockIdx.z / d.splitk;
   const int split = blockIdx.z % d.splitk;
@@ -215,8 +222,8 @@ __global__ void __launch_bounds__(THREADS, 1) zgemm_dmma_kernel(const GemmDesc d
   const c128* __restrict__ Bg = d.B + bz * d.b_batch;
   c128* __restrict__ Cg = d.C + bz * d.c_batch + (long long)split * d.c_split;
 
-  LoadPlan<A_KMAJOR, BM, A_ITERS> pa;
-  LoadPlan<B_KMAJOR, BN, B_ITERS> pb;
+  LoadPlan<A_KMAJOR, BM, C::A_ITERS, BK, C::THREADS> pa;
+  LoadPlan<B_KMAJOR, BN, C::B_ITERS, BK, C::THREADS> pb;
   pa.init(tid, tile_m, d.M, d.a_m_inner, d.a_m1, d.a_m0);
   pb.init(tid, tile_n, d.N, d.b_n_inner, d.b_n1, d.b_n0);
 
@@ -262,7 +269,7 @@ __global__ void __launch_bounds__(THREADS, 1) zgemm_dmma_kernel(const GemmDesc d
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int r = wm * 32 + 8 * i + g;
-        const c128 v = as[tile_chunk<A_KMAJOR, BM>(r, kk)];
+        const c128 v = as[tile_chunk<A_KMAJOR, BM, BK>(r, kk)];
         are[i] = v.x;
         aim[i] = flip_sign(v.y, sa);
         naim[i] = flip_sign(v.y, sa ^ 0x80000000u);
@@ -270,7 +277,7 @@ __global__ void __launch_bounds__(THREADS, 1) zgemm_dmma_kernel(const GemmDesc d
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int r = wn * 32 + 8 * j + g;
-        const c128 v = bs[tile_chunk<B_KMAJOR, BN>(r, kk)];
+        const c128 v = bs[tile_chunk<B_KMAJOR, BN, BK>(r, kk)];
         bre[j] = v.x;
         bim[j] = flip_sign(v.y, sb);
       }
@@ -317,31 +324,43 @@ __global__ void __launch_bounds__(THREADS, 1) zgemm_dmma_kernel(const GemmDesc d
   }
 }
 
+template <typename C>
+cudaError_t launch_cfg(const GemmDesc& d, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(zgemm_dmma_kernel<C, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaFuncSetAttribute(zgemm_dmma_kernel<C, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaFuncSetAttribute(zgemm_dmma_kernel<C, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaFuncSetAttribute(zgemm_dmma_kernel<C, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    configured = true;
+  }
+  dim3 grid((d.N + C::BN - 1) / C::BN, (d.M + C::BM - 1) / C::BM, d.batch * d.splitk);
+  const bool ak = (d.a_k == 1), bk = (d.b_k == 1);
+  ProfScope scope(stream, d.tag, 8.0 * (double)d.M * (double)d.N * (double)d.K * (double)d.batch, true);
+  if (ak && bk)
+    zgemm_dmma_kernel<C, true, true><<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(d);
+  else if (ak && !bk)
+    zgemm_dmma_kernel<C, true, false><<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(d);
+  else if (!ak && bk)
+    zgemm_dmma_kernel<C, false, true><<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(d);
+  else
+    zgemm_dmma_kernel<C, false, false><<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(d);
+  ++g_launch_count;
+  return cudaGetLastError();
+}
+
+inline long long tiles_of(const GemmDesc& d, int bm, int bn) {
+  return (long long)((d.M + bm - 1) / bm) * ((d.N + bn - 1) / bn) * d.batch;
+}
+
+// The small tile is used when the big one would occupy fewer than half of the SMs.
+inline bool use_small(const GemmDesc& d) { return tiles_of(d, BigCfg::BM, BigCfg::BN) < 74; }
+
 }  // namespace
 
 cudaError_t zgemm_launch(const GemmDesc& d, cudaStream_t stream) {
   if (d.M <= 0 || d.N <= 0 || d.batch <= 0) return cudaSuccess;
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(zgemm_dmma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    cudaFuncSetAttribute(zgemm_dmma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    cudaFuncSetAttribute(zgemm_dmma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    cudaFuncSetAttribute(zgemm_dmma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    configured = true;
-  }
-  dim3 grid((d.N + BN - 1) / BN, (d.M + BM - 1) / BM, d.batch * d.splitk);
-  const bool ak = (d.a_k == 1), bk = (d.b_k == 1);
-  ProfScope scope(stream, d.tag, 8.0 * (double)d.M * (double)d.N * (double)d.K * (double)d.batch, true);
-  if (ak && bk)
-    zgemm_dmma_kernel<true, true><<<grid, THREADS, SMEM_BYTES, stream>>>(d);
-  else if (ak && !bk)
-    zgemm_dmma_kernel<true, false><<<grid, THREADS, SMEM_BYTES, stream>>>(d);
-  else if (!ak && bk)
-    zgemm_dmma_kernel<false, true><<<grid, THREADS, SMEM_BYTES, stream>>>(d);
-  else
-    zgemm_dmma_kernel<false, false><<<grid, THREADS, SMEM_BYTES, stream>>>(d);
-  ++g_launch_count;
-  return cudaGetLastError();
+  return use_small(d) ? launch_cfg<SmallCfg>(d, stream) : launch_cfg<BigCfg>(d, stream);
 }
 
 namespace {
@@ -367,30 +386,41 @@ __global__ void k_splitk_reduce(const c128* __restrict__ P, int S, int M, int N,
 
 cudaError_t zgemm_auto(const GemmDesc& d, cudaStream_t stream, c128* scratch, size_t scratch_elems) {
   if (d.M <= 0 || d.N <= 0 || d.batch <= 0) return cudaSuccess;
-  const long long tiles = (long long)((d.M + BM - 1) / BM) * ((d.N + BN - 1) / BN) * d.batch;
-  if (d.batch != 1 || d.K < 256 || scratch == nullptr || tiles >= 8 * 148) return zgemm_launch(d, stream);
+  const bool small = use_small(d);
+  const int bm = small ? SmallCfg::BM : BigCfg::BM, bn = small ? SmallCfg::BN : BigCfg::BN;
+  const int bk = small ? SmallCfg::BK : BigCfg::BK;
+  const long long tiles = tiles_of(d, bm, bn);
+  const int min_chunk = small ? 64 : 128;
+  if (d.batch != 1 || d.K < 2 * min_chunk || scratch == nullptr || tiles >= 8 * 148) return zgemm_launch(d, stream);
   // Wave-aware split-K: model t(S) = waves(S) * (K/S + K0) * t_k + reduction traffic and pick the best S.
-  // A tile of 128x64 costs ~0.30 us per k on one SM (87 % of the 37 TFLOP/s DMMA peak); K0 ~ prologue + epilogue.
-  const double t_k = 0.30e-6, K0 = 32.0, bw = 5.0e12;
-  const int nsm = 148;
+  // One SM sustains ~220 GFLOP/s of DMMA work: a 128x64 tile costs ~0.30 us per k; a 64x32 tile ~0.075 us per k when it
+  // has an SM to itself and 4 of them share an SM at the same aggregate rate (slots = 4 x 148, t_k x 4); K0 ~ prologue
+  // + epilogue in units of k.
+  const double t_k = small ? 0.30e-6 : 0.30e-6, K0 = small ? 24.0 : 32.0, bw = 5.0e12;
+  const int slots = small ? 4 * 148 : 148;
   int best_s = 1;
   double best_t = 1e30;
-  const int max_s = d.K / 128 < 16 ? d.K / 128 : 16;
+  const int max_s = d.K / min_chunk < 16 ? d.K / min_chunk : 16;
   for (int S = 1; S <= max_s; ++S) {
     int chunk = (d.K + S - 1) / S;
-    chunk = (chunk + BK - 1) / BK * BK;
+    chunk = (chunk + bk - 1) / bk * bk;
     const int s_eff = (d.K + chunk - 1) / chunk;
     if (s_eff != S) continue;
     if (S > 1 && (size_t)S * d.M * d.N > scratch_elems) break;
-    const double waves = (double)((tiles * S + nsm - 1) / nsm);
-    double t = waves * (chunk + K0) * t_k;
+    const long long units = tiles * S;
+    // fewer units than SMs: every CTA has its SM to itself (a lone small CTA runs 4x faster per k than when 4 share)
+    double per_k = t_k;
+    if (small && units <= 148) per_k = 0.075e-6;
+    else if (small && units < slots) per_k = 0.075e-6 * (double)((units + 147) / 148);
+    const double waves = (double)((units + slots - 1) / slots);
+    double t = waves * (chunk + K0) * per_k;
     if (S > 1) t += (double)(S + 2) * d.M * d.N * 16.0 / bw + 4.0e-6;
     if (t < best_t * 0.97) { best_t = t; best_s = S; }   // prefer fewer splits unless >= 3 % better
   }
   int S = best_s;
   if (S < 2) return zgemm_launch(d, stream);
   int chunk = (d.K + S - 1) / S;
-  chunk = (chunk + BK - 1) / BK * BK;
+  chunk = (chunk + bk - 1) / bk * bk;
   GemmDesc g = d;
   g.C = scratch;
   g.c_m_inner = 1; g.c_m1 = d.N; g.c_m0 = 0; g.c_n = 1; g.c_batch = 0;

@@ -38,7 +38,8 @@ def core_of(data, left=False, right=False):
 
 
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("M,N,K_", [(1, 1, 1), (7, 5, 3), (128, 64, 8), (129, 65, 9), (200, 150, 77), (512, 384, 256), (33, 700, 130)])
+@pytest.mark.parametrize("M,N,K_", [(1, 1, 1), (7, 5, 3), (128, 64, 8), (129, 65, 9), (200, 150, 77), (512, 384, 256), (33, 700, 130),
+                                    (1100, 1030, 300), (2048, 640, 72), (96, 80, 2100)])
 @pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (2, 0), (1, 0), (2, 1), (0, 2)])
 def test_zgemm(eng, M, N, K_, ta, tb):
     rng = np.random.default_rng(M * 1000 + N * 10 + K_ + ta * 7 + tb)
@@ -310,3 +311,43 @@ def test_lanczos_eigvec(eng):
     assert abs(np.linalg.norm(got) - 1) < 1e-13
     assert np.linalg.norm(H @ got - np.vdot(got, H @ got) * got) < 1e-7
     assert abs(np.vdot(got, H @ got).real - np.linalg.eigvalsh(H)[0]) < 1e-9
+
+
+@pytest.mark.parametrize("tag,kw", [("a", dict(p=1e-7)), ("b", dict(p=1e-3, keepdim=True)),
+                                    ("c", dict(p=1e-5, regularize=True, keepdim=True))])
+def test_svd_truncate_golden(eng, K, tag, kw):
+    """Against the reference's truncate_sigvec on a graded 6x6 matrix (singular values 1 .. 1e-9)."""
+    U, S, Vh, rank = eng.svd_truncate(eng.to_device(K["t_sig"]), **kw)
+    U, S, Vh = U.cpu().numpy(), S.cpu().numpy(), Vh.cpu().numpy()
+    assert U.shape == K[f"t_{tag}_U"].shape and S.shape == K[f"t_{tag}_S"].shape
+    np.testing.assert_allclose(S, K[f"t_{tag}_S"], atol=1e-13)
+    np.testing.assert_allclose(U @ S @ Vh, K[f"t_{tag}_U"] @ K[f"t_{tag}_S"] @ K[f"t_{tag}_Vh"], atol=1e-12)
+    np.testing.assert_allclose(U.conj().T @ U, np.eye(U.shape[1]), atol=1e-13)
+    np.testing.assert_allclose(Vh @ Vh.conj().T, np.eye(Vh.shape[0]), atol=1e-13)
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 64, 257])
+def test_svd_random_and_rank_deficient(eng, n):
+    rng = np.random.default_rng(n)
+    X = crand(rng, n, n)
+    if n > 4:
+        X[:, n // 2:] = 0.0  # exact zero columns -> Householder completion path
+    U, S, Vh, rank = eng.svd_truncate(eng.to_device(X), p=0.0, keepdim=True)
+    U, S, Vh = U.cpu().numpy(), S.cpu().numpy(), Vh.cpu().numpy()
+    s_ref = np.linalg.svd(X, compute_uv=False)
+    nz = s_ref[s_ref > 1e-12 * s_ref[0]]
+    np.testing.assert_allclose(np.diag(S).real[: len(nz)] * np.linalg.norm(nz), nz, rtol=1e-12)
+    np.testing.assert_allclose(U.conj().T @ U, np.eye(n), atol=1e-12)
+    np.testing.assert_allclose(Vh @ Vh.conj().T, np.eye(n), atol=1e-12)
+    np.testing.assert_allclose(U @ (S * np.linalg.norm(nz)) @ Vh, X, atol=1e-12 * max(1.0, s_ref[0]))
+
+
+def test_pinv(eng, K):
+    X = K["t_sig"]
+    np.testing.assert_allclose(eng.pinv(eng.to_device(X), 1e-13).cpu().numpy(), np.linalg.pinv(X, rcond=1e-13), rtol=0,
+                               atol=1e-6 * np.abs(np.linalg.pinv(X, rcond=1e-13)).max())
+    rng = np.random.default_rng(2)
+    Y = crand(rng, 40, 40)
+    Y[:, 30:] = 0
+    ref = np.linalg.pinv(Y, rcond=1e-13)
+    np.testing.assert_allclose(eng.pinv(eng.to_device(Y), 1e-13).cpu().numpy(), ref, atol=1e-11 * np.abs(ref).max())
