@@ -279,17 +279,13 @@ def default_stats(wl) -> dict:
 def run_cuda(args):
     import torch
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py --impl cuda needs a CUDA device (no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
+    from pytdscf_b200 import parallel
 
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    info = parallel.init_from_env("nccl")
+    rank, world, local_rank, dist = info.rank, info.world, info.local_rank, info.dist
 
     from pytdscf_b200._const_cls import RunConfig
     from pytdscf_b200._engine import Engine

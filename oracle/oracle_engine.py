@@ -1,0 +1,116 @@
+"""CPU stand-in for ``pytdscf_b200._engine.Engine`` built on the oracle's NumPy kernels -- TEST INFRASTRUCTURE.
+
+It exists so that the host-side logic of the product (``pytdscf_b200/_mps_cuda.py``: environment bookkeeping,
+sweep order, Krylov warm-up history, Simulator loop, multi-process plumbing) can be exercised by ``-m "not gpu"``
+tests and by world_size-2 ``gloo`` tests in a container without a GPU.  It is never imported by the package:
+``Simulator`` always constructs the CUDA ``Engine`` and raises without a GPU.  Tensors are torch CPU complex128
+tensors (zero-copy NumPy views)."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from oracle import tdvp_oracle as orc
+from pytdscf_b200._engine import DeviceCore
+
+
+def _np(t):
+    return None if t is None else t.numpy()
+
+
+def _core(core: DeviceCore | None):
+    if core is None or core.data is None:
+        return None
+    return orc.SiteCore((), 0, core.data.numpy(), False, False)
+
+
+class OracleEngine:
+    def __init__(self):
+        self.torch_device = torch.device("cpu")
+        self._stats = {"solves": 0, "matvecs": 0, "flops": 0.0, "launches": 0}
+
+    def close(self):
+        pass
+
+    def to_device(self, a) -> torch.Tensor:
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.complex128).copy())
+
+    def upload_core(self, data) -> DeviceCore:
+        if data is None:
+            return DeviceCore(None)
+        return DeviceCore(self.to_device(data), None)
+
+    def empty(self, *shape) -> torch.Tensor:
+        return torch.empty(shape, dtype=torch.complex128)
+
+    def _wrap(self, a: np.ndarray) -> torch.Tensor:
+        return torch.from_numpy(np.ascontiguousarray(a))
+
+    def heff_apply(self, terms, psi):
+        d = {i: (_np(L), _core(c), _np(R)) for i, (L, c, R, coef) in enumerate(terms)}
+        out = None
+        for i, (L, c, R, coef) in enumerate(terms):
+            add = orc.heff_term(*d[i], psi.numpy()) * complex(coef) if complex(coef) != 1.0 else orc.heff_term(*d[i], psi.numpy())
+            out = add.copy() if out is None else out + add
+        return self._wrap(out)
+
+    def keff_apply(self, terms, sigma):
+        out = None
+        for (L, R, coef) in terms:
+            add = orc.keff_term(_np(L), _np(R), sigma.numpy())
+            if complex(coef) != 1.0:
+                add = add * complex(coef)
+            out = add.copy() if out is None else out + add
+        return self._wrap(out)
+
+    def env_update(self, gauge, bra, ket, E, core, out=None, accumulate=False):
+        res = orc.env_update_term(gauge, bra.numpy(), ket.numpy(), _np(E), _core(core))
+        if out is not None and accumulate:
+            out += self._wrap(res)
+            return out
+        return self._wrap(res)
+
+    def krylov_expm(self, kind, scale, thresh, n_warmup, conserve_norm, psi, *, hterms=None, kterms=None):
+        last = n_warmup + 2 if n_warmup > 0 else 0
+        if hterms is not None:
+            mv = lambda x: self.heff_apply(hterms, self._wrap(x)).numpy()  # noqa: E731
+        else:
+            mv = lambda x: self.keff_apply(kterms, self._wrap(x)).numpy()  # noqa: E731
+        solver = orc.sia_reference if kind == "arnoldi" else orc.sil_reference
+        y, n = solver(complex(scale), mv, psi.numpy().copy(), thresh, last_niter=last, conserve_norm=conserve_norm)
+        psi.copy_(self._wrap(y))
+        self._stats["solves"] += 1
+        self._stats["matvecs"] += n
+        return n
+
+    def lanczos_eigvec(self, psi, hterms, root=0, thresh=1e-9):
+        mv = lambda x: self.heff_apply(hterms, self._wrap(x)).numpy()  # noqa: E731
+        y, n = orc.lanczos_ground_state(mv, psi.numpy().copy(), root, thresh)
+        psi.copy_(self._wrap(y / np.linalg.norm(y)))
+        return n
+
+    def qr_shift(self, gauge, psi):
+        if gauge == "A":
+            A, s = orc.shift_qr(psi.numpy())
+            return self._wrap(A), self._wrap(s)
+        s, B = orc.shift_lq(psi.numpy())
+        return self._wrap(B), self._wrap(s)
+
+    def absorb(self, gauge, sigma, site):
+        if gauge == "A":
+            return self._wrap(np.tensordot(sigma.numpy(), site.numpy(), axes=(1, 0)))
+        return self._wrap(np.tensordot(site.numpy(), sigma.numpy(), axes=(2, 0)))
+
+    def inner(self, bra, ket, conj=True):
+        a = bra.numpy().ravel()
+        return complex(np.inner(np.conj(a) if conj else a, ket.numpy().ravel()))
+
+    def overlap_site(self, bra, ket, block, conj_bra):
+        b = np.conj(bra.numpy()) if conj_bra else bra.numpy()
+        return self._wrap(np.einsum("abc,abk->ck", b, np.einsum("ibk,ai->abk", ket.numpy(), block.numpy())))
+
+    def stats(self):
+        return dict(self._stats)
+
+    def reset_stats(self):
+        self._stats = {"solves": 0, "matvecs": 0, "flops": 0.0, "launches": 0}

@@ -1,0 +1,135 @@
+"""CPU tests of the PRODUCT's host logic (pytdscf_b200/_mps_cuda.py, Simulator loop, multi-process plumbing) with the
+oracle's NumPy kernels injected in place of the CUDA engine (oracle/oracle_engine.py, test infrastructure only)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.oracle_engine import OracleEngine
+from tests.golden_io import RUN_CASES, load_run
+
+
+def _build_model(g):
+    import pytdscf_b200 as tb
+
+    basis = [tb.Exciton(nstate=d) for d in g["dims"]]
+    pot = {key: tb.TensorOperator(mpo=[np.asarray(c) for c in cores]) for key, cores in g["operators"].items()}
+    ham = tb.TensorHamiltonian(ndof=len(basis), potential=[[pot]], backend="cuda")
+    return tb.Model(basis, {"hamiltonian": ham}, bond_dim=g["bond_dim"], space=g["space"])
+
+
+def _run(g, tmp_path, relax=None):
+    import pytdscf_b200 as tb
+
+    model = _build_model(g)
+    os.chdir(tmp_path)
+    sim = tb.Simulator(g["name"] + "_cpu", model, backend="cuda")
+    sim.eng = OracleEngine()  # inject: Simulator would otherwise insist on a CUDA device
+    sim.set_initial_mps(g["init"])
+    hil = g["space"] == "hilbert"
+    if relax is None:
+        ener, wf = sim.propagate(stepsize=g["dt_au"] * tb.units.au_in_fs, maxstep=g["nstep"], thresh_sil=g["thresh_sil"],
+                                 integrator=g["integrator"], conserve_norm=g["conserve_norm"], energy=hil, autocorr=hil,
+                                 norm=hil, populations=hil, record_trace=True)
+    else:
+        ener, wf = sim.relax(stepsize=g["dt_au"] * tb.units.au_in_fs, maxstep=g["nstep"], improved=(relax == "improved"),
+                             record_trace=True)
+    return sim, ener, wf
+
+
+@pytest.mark.parametrize("name", RUN_CASES)
+def test_host_sweep_logic_reproduces_reference(name, tmp_path):
+    """Same kernels as the oracle => the product's bookkeeping must reproduce the reference run exactly."""
+    g = load_run(name)
+    sim, ener, wf = _run(g, tmp_path)
+    assert (np.array(wf.ci_coef.trace) == g["trace"]).all()
+    if g["space"] == "hilbert":
+        for rec, row in zip(sim.history, g["props"], strict=True):
+            assert abs(rec["autocorr"] - complex(row[1], row[2])) < 1e-13
+            assert abs(rec["energy"] - row[3]) < 1e-13 * max(1.0, abs(row[3]))
+            assert abs(rec["norm"] - row[5]) < 1e-13
+    for c, r in zip(wf.ci_coef.to_numpy(), g["final"], strict=True):
+        np.testing.assert_allclose(c, r, rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("name,mode", [("relax_improved_hh4", "improved"), ("relax_imag_hh4", "imag")])
+def test_host_relaxation_logic(name, mode, tmp_path):
+    g = load_run(name)
+    sim, ener, wf = _run(g, tmp_path, relax=mode)
+    assert (np.array(wf.ci_coef.trace) == g["trace"]).all()
+    for rec, row in zip(sim.history, g["props"], strict=True):
+        assert abs(rec["energy"] - row[3]) < 1e-12 * abs(row[3])
+    assert abs(ener - g["final_energy"].real) < 1e-12 * abs(g["final_energy"].real)
+
+
+def test_device_alloc_random_logic_on_cpu():
+    from pytdscf_b200._mps_cuda import MPSCoefCuda
+
+    g = load_run("exciton_D6")
+    model = _build_model(g)
+    model.init_HartreeProduct = [[h for h in g["hartree"]]]
+    mps = MPSCoefCuda.alloc_random(OracleEngine(), model)
+    for c, r in zip(mps.to_numpy(), g["init"], strict=True):
+        np.testing.assert_allclose(c, r, rtol=0, atol=1e-15)
+    assert mps.bonddim() == [s.shape[2] for s in g["init"][:-1]]
+
+
+def test_checkpoint_roundtrip(tmp_path):
+    g = load_run("henon_heiles_f2")
+    sim, ener, wf = _run(g, tmp_path)
+    path = sim.save_wavefunction(wf, "_ck")
+    assert os.path.exists(path)
+    wf2 = sim.load_wavefunction("_ck")
+    for a, b in zip(wf.ci_coef.to_numpy(), wf2.ci_coef.to_numpy(), strict=True):
+        assert (a == b).all()
+    assert [s.gauge for s in wf2.ci_coef.sites] == [s.gauge for s in wf.ci_coef.sites]
+
+
+def _replica_worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import time
+
+    from pytdscf_b200 import parallel
+    from pytdscf_b200._const_cls import RunConfig
+    from pytdscf_b200._mps_cuda import DeviceMPO, MPSCoefCuda
+
+    info = parallel.init_from_env("gloo")
+    g = load_run("henon_heiles_f2")
+    eng = OracleEngine()
+    model = _build_model(g)
+    H = DeviceMPO(eng, model.hamiltonian)
+    mps = MPSCoefCuda(eng, [eng.to_device(c) for c in g["init"]])
+    cfg = RunConfig()
+    parallel.barrier(info)
+    t0 = time.perf_counter()
+    for _ in range(g["nstep"]):
+        mps.propagate(g["dt_au"], H, cfg)
+    sec = time.perf_counter() - t0 + 0.01 * rank  # make the ranks' clocks differ
+    slowest = parallel.max_over_ranks(info, sec)
+    total = parallel.aggregate_throughput(info, 2 * g["nstep"], sec)
+    e = mps.expectation(H).real
+    q.put((rank, sec, slowest, total, e))
+    parallel.finalize(info)
+
+
+def test_replicas_world_size_2_gloo():
+    """N > 1 path of round 1: independent replicas, control-plane reductions only (MAX of times, SUM of work)."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_replica_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = load_run("henon_heiles_f2")
+    secs = [r[1] for r in res]
+    for rank, sec, slowest, total, e in res:
+        assert slowest == pytest.approx(max(secs))
+        assert total == pytest.approx(2 * (2 * g["nstep"]) / max(secs))
+        assert abs(e - g["final_energy"].real) < 1e-9  # energy is conserved; every replica ran the same physics
