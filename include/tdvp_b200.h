@@ -129,6 +129,10 @@ int tdvp_absorb(tdvp_handle_t h, int gauge, int Dl, int d, int Dr, int k, const 
  * decision reads the singular values back to the host. */
 int tdvp_svd_truncate(tdvp_handle_t h, int m, int n, const tdvp_c128* sigma, double p, int keepdim, int regularize,
                       tdvp_c128* U, tdvp_c128* S, tdvp_c128* Vh, int* rank);
+/* Thin SVD A(m,n) = U(m,n) diag(s) Vh(n,n), m >= n, s descending and written to HOST memory -- replaces
+ * np.linalg.svd / scipy.linalg.svd in CC2ALambdaB (pytdscf/_mps_cls.py:3601-3630) and in the regularised gauge_trf
+ * (pytdscf/_site_cls.py:207-252). */
+int tdvp_svd(tdvp_handle_t h, int m, int n, const tdvp_c128* A, tdvp_c128* U, double* s_host, tdvp_c128* Vh);
 /* out(n,m) = pinv(X(m,n), rcond) -- replaces np.linalg.pinv in multiply_sigvec_pinv (pytdscf/_site_cls.py:734). */
 int tdvp_pinv(tdvp_handle_t h, int m, int n, const tdvp_c128* X, double rcond, tdvp_c128* out);
 

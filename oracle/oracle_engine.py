@@ -89,12 +89,32 @@ class OracleEngine:
         psi.copy_(self._wrap(y / np.linalg.norm(y)))
         return n
 
-    def qr_shift(self, gauge, psi):
+    def qr_shift(self, gauge, psi, regularize=False):
         if gauge == "A":
-            A, s = orc.shift_qr(psi.numpy())
+            A, s = orc.shift_qr(psi.numpy(), regularize)
             return self._wrap(A), self._wrap(s)
-        s, B = orc.shift_lq(psi.numpy())
+        s, B = orc.shift_lq(psi.numpy(), regularize)
         return self._wrap(B), self._wrap(s)
+
+    def svd(self, M):
+        U, s, Vh = np.linalg.svd(M.numpy(), full_matrices=False)
+        return self._wrap(U), s, self._wrap(Vh)
+
+    def svd_truncate(self, sigma, p, keepdim=False, regularize=False):
+        U, S, Vh, rank = orc.truncate_bond(None, sigma.numpy(), None, p, regularize, keepdim)
+        return self._wrap(U), self._wrap(S.astype(complex)), self._wrap(Vh), rank
+
+    def pinv(self, X, rcond=1e-13):
+        return self._wrap(np.linalg.pinv(X.numpy(), rcond=rcond))
+
+    def zgemm(self, A, B, transA=0, transB=0, alpha=1.0, beta=0.0, C_out=None):
+        a = {0: A.numpy(), 1: A.numpy().T, 2: A.numpy().conj().T}[transA]
+        b = {0: B.numpy(), 1: B.numpy().T, 2: B.numpy().conj().T}[transB]
+        out = alpha * (a @ b)
+        if C_out is not None:
+            C_out.copy_(self._wrap(out + beta * C_out.numpy()))
+            return C_out
+        return self._wrap(out)
 
     def absorb(self, gauge, sigma, site):
         if gauge == "A":

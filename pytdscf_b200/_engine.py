@@ -209,9 +209,21 @@ class Engine:
         return int(niter.value)
 
     # -- gauge -------------------------------------------------------------------------
-    def qr_shift(self, gauge: str, psi: torch.Tensor):
+    def regularize_site(self, psi: torch.Tensor) -> torch.Tensor:
+        """Floor the small singular values of the (Dl*Dr) x d matricisation (reference ``_site_cls.py:207-252``)."""
+        Dl, d, Dr = psi.shape
+        M = psi.permute(0, 2, 1).reshape(Dl * Dr, d).contiguous()
+        U, s, Vh = self.svd(M)
+        eps = 1.0e-4  # SQRT_EPSRHO
+        s_reg = np.where(s > eps, s, s + eps * np.exp(-s / eps))
+        Us = (U * torch.as_tensor(s_reg, dtype=torch.float64, device=U.device)[None, :]).contiguous()
+        return self.zgemm(Us, Vh).reshape(Dl, Dr, d).permute(0, 2, 1).contiguous()
+
+    def qr_shift(self, gauge: str, psi: torch.Tensor, regularize: bool = False):
         """'A': psi -> (A(Dl,d,k), sigma(k,Dr));  'B': psi -> (B(k,d,Dr), sigma(Dl,k))."""
         _chk_tensor(psi, "psi")
+        if regularize:
+            psi = self.regularize_site(psi)
         Dl, d, Dr = psi.shape
         if gauge == "A":
             if Dl * d < Dr:
@@ -255,6 +267,18 @@ class Engine:
         if keepdim:
             return U, S, Vh, r
         return U[:, :r].contiguous(), S.reshape(-1)[: r * r].reshape(r, r), Vh[:r, :].contiguous(), r
+
+    def svd(self, M: torch.Tensor):
+        """Thin SVD of a 2-D tensor: (U, s (host float64 array), Vh); wide matrices go through the conjugate transpose."""
+        _chk_tensor(M, "M")
+        m, n = M.shape
+        if m < n:
+            U2, s, Vh2 = self.svd(M.conj().T.contiguous())
+            return Vh2.conj().T.contiguous(), s, U2.conj().T.contiguous()
+        U, Vh = self.empty(m, n), self.empty(n, n)
+        s = (C.c_double * n)()
+        check(self.h, self.lib.tdvp_svd(self.h, m, n, _ptr(M), _ptr(U), s, _ptr(Vh)))
+        return U, np.array(s[:], dtype=np.float64), Vh
 
     def pinv(self, X: torch.Tensor, rcond: float = 1e-13) -> torch.Tensor:
         _chk_tensor(X, "X")

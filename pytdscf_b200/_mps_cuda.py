@@ -105,6 +105,8 @@ class MPSCoefCuda:
         self.niter_krylov: dict[int, int] = {}   # shared by the H and K solves of a site
         self.trace: list[tuple[int, int, int]] = []  # (0=H|1=K, site, niter)
         self.record_trace = False
+        self.site_offset = 0   # global index of local site 0 (site-parallel segments share one global MPO)
+        self.site_now = 0      # reference: helper._Debug.site_now, the key of the Krylov warm-up history
 
     # ------------------------------------------------------------------------------------------
     @classmethod
@@ -159,9 +161,9 @@ class MPSCoefCuda:
     def construct_op_zerosite() -> dict:
         return {"ovlp": Block(None, True, 1)}
 
-    def renormalize_op_psite(self, psite: int, blocks: dict, H: DeviceMPO, A_is_sys: bool) -> dict:
+    def renormalize_op_psite(self, psite: int, blocks: dict, H: DeviceMPO, A_is_sys: bool, site: SiteCoef | None = None) -> dict:
         eng = self.eng
-        site = self.sites[psite]
+        site = self.sites[psite] if site is None else site
         gauge = "A" if A_is_sys else "B"
         t = site.data
         nxt: dict = {}
@@ -172,7 +174,7 @@ class MPSCoefCuda:
         else:
             nxt["ovlp"] = Block(eng.env_update(gauge, t, t, ov.data, None), False)
             E_ovlp = ov.data
-        for term in H.calc_point[psite]:
+        for term in H.calc_point[psite + self.site_offset]:
             if (term.is_left and A_is_sys) or (term.is_right and not A_is_sys):
                 E = E_ovlp
             else:
@@ -191,11 +193,12 @@ class MPSCoefCuda:
                 nxt["summed"] = eng.env_update(gauge, t, t, blocks["summed"], None)
         return nxt
 
-    def construct_op_sites(self, begin_site: int, end_site: int, H: DeviceMPO) -> list:
+    def construct_op_sites(self, begin_site: int, end_site: int, H: DeviceMPO, op_initial_block: dict | None = None,
+                           superblock: list | None = None) -> list:
         left = begin_site < end_site
-        blocks = [self.construct_op_zerosite()]
+        blocks = [self.construct_op_zerosite() if op_initial_block is None else op_initial_block]
         for p in range(begin_site, end_site, 1 if left else -1):
-            blocks.append(self.renormalize_op_psite(p, blocks[-1], H, left))
+            blocks.append(self.renormalize_op_psite(p, blocks[-1], H, left, None if superblock is None else superblock[p]))
         return blocks
 
     @staticmethod
@@ -213,7 +216,7 @@ class MPSCoefCuda:
             terms.append((Lb["summed"], None, Ro, 1.0))
         if "summed" in Rb:
             terms.append((Lo, None, Rb["summed"], 1.0))
-        for term in H.calc_point[psite]:
+        for term in H.calc_point[psite + self.site_offset]:
             terms.append((Lb.get(term.key, Lo), term.core, Rb.get(term.key, Ro), 1.0))
         return terms
 
@@ -263,18 +266,22 @@ class MPSCoefCuda:
         return y
 
     # -- sweeps ------------------------------------------------------------------------------------
-    def propagate_along_sweep(self, H: DeviceMPO, dt: float, cfg, *, begin_site: int, end_site: int) -> dict:
+    def propagate_along_sweep(self, H: DeviceMPO, dt: float, cfg, *, begin_site: int, end_site: int,
+                              op_sys_initial: dict | None = None, skip_end_site: bool = False) -> dict:
         eng = self.eng
         A_is_sys = begin_site <= end_site
         step = 1 if A_is_sys else -1
         sites = self.sites
-        op_sys = self.construct_op_zerosite()
+        op_sys = self.construct_op_zerosite() if op_sys_initial is None else op_sys_initial
         if self.op_sys_sites is None:
             env_sites = self.construct_op_sites(end_site, begin_site, H)
         else:
             env_sites = self.op_sys_sites[:]
         self.op_sys_sites = [op_sys]
         for p in range(begin_site, end_site + step, step):
+            if skip_end_site and p == end_site:
+                return op_sys   # before site_now is touched, as in the reference (_mps_cls.py:878-880)
+            self.site_now = p
             op_env = env_sites.pop()
             hterms = self.operators_for_superH(p, op_sys, op_env, H, A_is_sys)
             psi = self._expm(cfg, -1.0j, dt, sites[p].data, p, 0, hterms=hterms)

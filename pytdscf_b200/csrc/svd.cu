@@ -311,6 +311,14 @@ int tdvp_svd_truncate(tdvp_handle_t hh, int m, int n, const tdvp_c128* sigma, do
   return 0;
 }
 
+int tdvp_svd(tdvp_handle_t hh, int m, int n, const tdvp_c128* A, tdvp_c128* U, double* s_host, tdvp_c128* Vh) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return TDVP_ERR_ARG;
+  h->err.clear();
+  if (!A || !U || !s_host || !Vh || m <= 0 || n <= 0 || m < n) { set_error(h, "svd: bad argument (needs m >= n)"); return TDVP_ERR_ARG; }
+  return svd_exec(h, m, n, (const c128*)A, (c128*)U, (c128*)Vh, s_host);
+}
+
 int tdvp_pinv(tdvp_handle_t hh, int m, int n, const tdvp_c128* X, double rcond, tdvp_c128* out) {
   Handle* h = reinterpret_cast<Handle*>(hh);
   if (!h) return TDVP_ERR_ARG;

@@ -37,7 +37,8 @@ class WFunc:
 
     def expectation(self, op) -> float:
         """Real part of <Psi|Op|Psi> (reference ``wavefunction.py:90-114`` also returns ``.real``)."""
-        return self.ci_coef.expectation(self.device_op(op)).real
+        val = self.ci_coef.expectation(self.device_op(op))
+        return None if val is None else val.real   # site-parallel runs: only rank 0 holds the value
 
     def autocorr(self) -> complex:
         return self.ci_coef.autocorr()
@@ -131,6 +132,28 @@ class Simulator:
             return WFunc(MPSCoefCuda(eng, [eng.to_device(c) for c in cores], gauges), eng)
         return WFunc(MPSCoefCuda.alloc_random(eng, self.model), eng)
 
+    def _distributed_wavefunction(self, split: list[tuple[int, ...]]) -> WFunc:
+        """Site-segment-parallel start: rank 0 canonicalises the serial initial MPS and scatters the segments."""
+        from . import parallel
+        from ._mps_parallel import Comm, MPSCoefParallelCuda
+
+        info = getattr(self, "rank_info", None) or parallel.init_from_env()
+        self.rank_info = info
+        if info.world != len(split) or info.world < 2:
+            raise ValueError(f"parallel_split_indices has {len(split)} segments but the process group has {info.world} "
+                             "ranks (launch with torchrun --nproc-per-node <segments>)")
+        n = self.model.get_ndof()
+        flat = [i for seg in split for i in seg]
+        if flat != list(range(n)):
+            raise ValueError("parallel_split_indices must partition 0..nsite-1 into consecutive segments")
+        eng = self._engine()
+        cores = None
+        if getattr(self, "_initial_mps", None) is not None:
+            cores = self._initial_mps[0]
+        mps = MPSCoefParallelCuda.distribute(eng, Comm(info, eng.torch_device), self.model, [seg[0] for seg in split],
+                                             cores=cores)
+        return WFunc(mps, eng)
+
     # -----------------------------------------------------------------------------------------------
     def propagate(self, stepsize: float = 0.1, maxstep: int = 5000, restart: bool = False, savefile_ext: str = "",
                   loadfile_ext: str = "_operate", backup_interval: int = 1000, autocorr: bool = True,
@@ -145,8 +168,13 @@ class Simulator:
         """Real-time propagation; returns ``(energy, wf)`` like the reference (energy of the last evaluated step)."""
         if reduced_density is not None:
             raise NotImplementedError("reduced densities are a 'next' row (SURVEY 8(f1)); not in backend='cuda' yet")
+        self._split = None
         if parallel_split_indices is not None:
-            raise NotImplementedError("site-parallel propagation is driven by pytdscf_b200.parallel (torchrun), not by this argument")
+            # reference: one MPI rank per tuple of consecutive sites (simulator_cls.py:243-249, _const_cls.py:236-251);
+            # here one torch.distributed rank (= one GPU) per tuple, launched by torchrun
+            if adaptive or restart:
+                raise NotImplementedError("site-parallel propagation supports neither adaptive bond dimensions nor restart")
+            self._split = [tuple(int(i) for i in seg) for seg in parallel_split_indices]
         return self._run(Δt if Δt is not None else stepsize, maxstep, False, restart, savefile_ext, loadfile_ext,
                          backup_interval, autocorr=autocorr, energy=energy, norm=norm, populations=populations,
                          observables=observables, thresh_sil=thresh_sil, integrator=integrator,
@@ -163,7 +191,13 @@ class Simulator:
                         verbose=self.verbose, space=self.model.space, integrator=integrator, conserve_norm=conserve_norm,
                         display_time_unit=display_time_unit, adaptive=adaptive)
         self.cfg = cfg
-        wf = self.get_initial_wavefunction(restart, loadfile_ext)
+        split = getattr(self, "_split", None) if not relax else None
+        if split is not None:
+            wf = self._distributed_wavefunction(split)
+            write_files = write_files and wf.ci_coef.rank == 0
+            savefile_ext += f"_rank{wf.ci_coef.rank}"
+        else:
+            wf = self.get_initial_wavefunction(restart, loadfile_ext)
         wf.ci_coef.record_trace = record_trace
         self.history = []
         files = self._open_files(cfg) if write_files else None

@@ -1,0 +1,83 @@
+"""Site-segment-parallel TDVP (pytdscf_b200/_mps_parallel.py) on CPU: world_size 2 and 4 over gloo, oracle kernels
+injected, checked against the UNMODIFIED reference's MPSCoefParallel runs (tests/golden/par_*.npz, generated under the
+file-based mpi4py stand-in by tests/golden/make_golden_parallel.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.golden_io import PAR_CASES, load_parallel
+
+
+def _worker(rank, world, port, name, tmp, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port), OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1")
+    try:
+        import torch
+
+        torch.set_num_threads(1)
+        import pytdscf_b200 as tb
+        from oracle.oracle_engine import OracleEngine
+        from pytdscf_b200 import parallel
+        from tests.test_host_sweep_cpu import _build_model
+
+        g = load_parallel(name)
+        os.chdir(tmp)
+        info = parallel.init_from_env("gloo")
+        model = _build_model(g)
+        sim = tb.Simulator(name + "_cpu", model, backend="cuda", verbose=0)
+        sim.eng = OracleEngine()
+        sim.rank_info = info
+        sim.set_initial_mps(g["init"])
+        ener, wf = sim.propagate(stepsize=g["dt_fs"], maxstep=g["nstep"], parallel_split_indices=g["split"], populations=False)
+        mps = wf.ci_coef
+        out = {"history": sim.history if rank == 0 else None, "sites": [s.numpy() for s in mps.sites],
+               "gauges": [s.gauge for s in mps.sites],
+               "joint": None if mps.joint_sigvec_not_pinv is None else mps.joint_sigvec_not_pinv.cpu().numpy(),
+               "files": sorted(os.listdir(name + "_cpu_prop")) if rank == 0 else None}
+        q.put((rank, out))
+        parallel.finalize(info)
+    except Exception:  # pragma: no cover
+        import traceback
+
+        q.put((rank, {"error": traceback.format_exc()}))
+
+
+@pytest.mark.parametrize("name", PAR_CASES)
+def test_site_parallel_matches_reference(name, tmp_path):
+    import torch.multiprocessing as mp
+
+    g = load_parallel(name)
+    P = g["nranks"]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31000 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, P, port, name, str(tmp_path), q)) for r in range(P)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=600) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    for r in range(P):
+        assert "error" not in res[r], res[r]["error"]
+    hist = res[0]["history"]
+    assert len(hist) == g["nstep"]
+    # the injected oracle kernels use the same LAPACK calls as the reference, so the host logic must reproduce the
+    # reference run to rounding (measured: <= 4e-15 on every observable)
+    if os.environ.get("PAR_DEBUG"):
+        print(name, "max dev", max(abs(rec["autocorr"] - complex(row[1], row[2])) for rec, row in zip(hist, g["props"])),
+              max(abs(rec["energy"] - row[3]) for rec, row in zip(hist, g["props"])),
+              max(abs(rec["norm"] - row[5]) for rec, row in zip(hist, g["props"])))
+    for rec, row in zip(hist, g["props"], strict=True):
+        assert abs(rec["autocorr"] - complex(row[1], row[2])) < 1e-12
+        assert abs(rec["energy"] - row[3]) < 1e-12 * max(1.0, abs(row[3]))
+        assert abs(rec["norm"] - row[5]) < 1e-12
+    for r in range(P):
+        assert res[r]["gauges"] == g["ranks"][r]["gauges"]
+        assert [s.shape for s in res[r]["sites"]] == [s.shape for s in g["ranks"][r]["sites"]]
+        if r < P - 1:
+            a, b = res[r]["joint"], g["ranks"][r]["joint_sigvec_not_pinv"]
+            np.testing.assert_allclose(a, b, rtol=0, atol=1e-11)
+        for a, b in zip(res[r]["sites"], g["ranks"][r]["sites"], strict=True):
+            np.testing.assert_allclose(a, b, rtol=0, atol=1e-10)
+    assert "main.log" in res[0]["files"] and "autocorr.dat" in res[0]["files"]
