@@ -48,6 +48,10 @@ def parse_args():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="c4", choices=["c2", "c3", "c4", "c5"])
     ap.add_argument("--bond-dim", type=int, default=None, help="override the workload's bond dimension (not a bench line)")
+    ap.add_argument("--parallel", default="auto", choices=["auto", "replicas", "sites"],
+                    help="N > 1: 'sites' = site-segment-parallel TDVP of ONE chain (strong scaling; default for c5), "
+                         "'replicas' = N independent chains (weak scaling; default otherwise)")
+    ap.add_argument("--sites", type=int, default=None, help="override the chain length of c5 (not a bench line)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -59,6 +63,8 @@ def make_workload(args):
     kw = {}
     if args.bond_dim is not None:
         kw["D"] = args.bond_dim
+    if getattr(args, "sites", None) is not None and args.workload == "c5":
+        kw["nsite"] = args.sites
     return workloads.by_name(args.workload, **kw)
 
 
@@ -296,7 +302,16 @@ def run_cuda(args):
     eng = Engine(local_rank)
     H = DeviceMPO(eng, model.hamiltonian)
     cfg = RunConfig(jobname="bench", space=wl.space, integrator=wl.integrator, conserve_norm=wl.conserve_norm)
-    mps = MPSCoefCuda.alloc_random(eng, model)
+    site_parallel = world > 1 and (args.parallel == "sites" or (args.parallel == "auto" and args.workload == "c5"))
+    if site_parallel:
+        # one chain, contiguous site segments, one per GPU (reference: MPSCoefParallel, _mps_parallel.py:106-268)
+        from pytdscf_b200._mps_parallel import Comm, MPSCoefParallelCuda
+
+        n = len(wl.dims)
+        split = [(r * n) // world for r in range(world)]
+        mps = MPSCoefParallelCuda.distribute(eng, Comm(info, eng.torch_device), model, split)
+    else:
+        mps = MPSCoefCuda.alloc_random(eng, model)
     dt = wl.dt_au
 
     def barrier():
@@ -336,21 +351,60 @@ def run_cuda(args):
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    sweeps = 2 * args.steps * world
+    jobs = 1 if site_parallel else world      # chains propagated by the whole job
+    sweeps = 2 * args.steps * jobs
     value = sweeps / (ms * 1e-3)
     nH = trace[trace[:, 0] == 0][:, 2]
     nK = trace[trace[:, 0] == 1][:, 2]
-    flops_per_sweep = st["flops"] / (2 * args.steps)
+    flops_all = st["flops"]
+    if site_parallel:
+        flops_all = parallel.sum_over_ranks(info, flops_all, device="cuda")
+    flops_per_sweep = flops_all / (2 * args.steps)
     stats = {"avg_matvecs_H": float(nH.mean()), "avg_matvecs_K": float(nK.mean()) if len(nK) else 0.0,
              "flops_per_sweep": flops_per_sweep, "source": "bench.py GPU run"}
-    if rank == 0:
+    if rank == 0 and not site_parallel:
         os.makedirs(STATS_DIR, exist_ok=True)
         with open(os.path.join(STATS_DIR, wl.name + ".json"), "w") as f:
             json.dump(stats, f, indent=1)
 
     # ---- e2e: host buffers in, host buffers out, every step ----
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and site_parallel:
+        # segment state (site tensors, both saved gauges, boundary bond matrices) lives in pinned host memory between
+        # steps; the environment blocks are caches derived from it and stay on the device
+        def state_refs():
+            refs = [(sc, "data") for grp in (mps.sites, mps.superblock_all_A, mps.superblock_all_B) for sc in grp]
+            if mps.joint_sigvec is not None:
+                refs += [(mps, "joint_sigvec"), (mps, "joint_sigvec_not_pinv")]
+            return refs
+
+        host = [torch.empty(getattr(o, a).shape, dtype=torch.complex128).pin_memory() for o, a in state_refs()]
+        for hb, (o, a) in zip(host, state_refs(), strict=True):
+            hb.copy_(getattr(o, a))
+        nbytes = sum(hb.numel() * 16 for hb in host)
+        e_steps = max(1, min(args.steps, 2))
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(e_steps):
+            for hb, (o, a) in zip(host, state_refs(), strict=True):
+                setattr(o, a, hb.to(eng.torch_device, non_blocking=True))
+            mps.propagate(dt, H, cfg)
+            refs = state_refs()
+            if len(refs) != len(host) or any(getattr(o, a).shape != hb.shape for hb, (o, a) in zip(host, refs)):
+                raise RuntimeError("segment state changed shape during a step")
+            for hb, (o, a) in zip(host, refs, strict=True):
+                hb.copy_(getattr(o, a), non_blocking=True)
+        e1.record()
+        barrier()
+        ems = e0.elapsed_time(e1)
+        t = torch.tensor([ems, float(nbytes)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t[:1], op=dist.ReduceOp.MAX)
+        dist.all_reduce(t[1:], op=dist.ReduceOp.SUM)
+        ems, tot = float(t[0].item()), int(t[1].item())
+        e2e = {"value": 2 * e_steps / (ems * 1e-3), "unit": "sweeps/s", "h2d_bytes_per_step": tot, "d2h_bytes_per_step": tot,
+               "steps": e_steps, "path": "pinned host segment state -> H2D -> MPSCoefParallelCuda.propagate -> D2H, every rank"}
+    elif not args.no_e2e:
         host = [torch.empty(s.data.shape, dtype=torch.complex128).pin_memory() for s in mps.sites]
         for hbuf, s in zip(host, mps.sites, strict=True):
             hbuf.copy_(s.data)
@@ -394,15 +448,18 @@ def run_cuda(args):
             ncu = json.load(f).get(wl.name)
     out = {
         "metric": "tdvp_sweeps_per_sec", "value": value, "unit": "sweeps/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "strong" if site_parallel else "weak",
         "vs_baseline": None, "dtype": "complex128", "data": "synthetic",
         "config": {"workload": wl.name, "description": wl.description, "sites": len(wl.dims), "bond_dim": wl.bond_dim,
                    "integrator": wl.integrator, "dt_au": wl.dt_au, "thresh_sil": cfg.thresh_exp,
                    "step": "1 time step = 2 half sweeps, properties off",
-                   "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (no collective)",
+                   "parallelism": "single GPU" if world == 1 else
+                   (f"site-parallel TDVP, {world} contiguous segments, NCCL p2p of boundary blocks" if site_parallel
+                    else f"{world} independent replicas (no collective)"),
                    "l2": "per-step working set (Krylov basis + contraction intermediates, GBs) >> 126 MB L2; no explicit flush"},
         "clocks": clocks,
-        "heff_tflops": st["flops"] / (ms * 1e-3) / 1e12,
+        "heff_tflops": flops_all / (ms * 1e-3) / 1e12,
         "heff_tflops_note": "algorithmic H_eff + K_eff + env-update flops (SURVEY 8(d)) / wall time of the timed region (all kernels)",
         "krylov": {"avg_matvecs_H": stats["avg_matvecs_H"], "avg_matvecs_K": stats["avg_matvecs_K"],
                    "solves_per_step": len(trace) / args.steps, "tflop_per_sweep": flops_per_sweep / 1e12},

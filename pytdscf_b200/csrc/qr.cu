@@ -115,10 +115,20 @@ __global__ void __launch_bounds__(PT, 1) k_qr_panel(PanelArgs p) {
     __syncthreads();
     // (d) zlarfg
     if (tx == 0 && ty == 0) {
-      const double xnorm = sqrt(fmax(gtot[c].x, 0.0));
+      // |x|^2 below 1e-200 cannot be formed accurately as a plain sum of squares (the terms are denormal); LAPACK's
+      // dznrm2 rescales, here such a tail (|x| < 1e-100 next to O(1) data) is treated as exactly zero: the reflector
+      // degenerates to a phase on the diagonal and Q stays an isometry to rounding.
+      const bool tiny_tail = gtot[c].x < 1.0e-200;
+      const double xnorm = tiny_tail ? 0.0 : sqrt(gtot[c].x);
       const double alphr = rowc[c].x, alphi = rowc[c].y;
       if (xnorm == 0.0 && alphi == 0.0) {
         s_tau[0] = 0.0; s_tau[1] = 0.0; s_scal[0] = 1.0; s_scal[1] = 0.0; s_beta = alphr;
+      } else if (tiny_tail) {
+        const double beta = (alphr >= 0.0) ? -hypot(alphr, alphi) : hypot(alphr, alphi);
+        s_tau[0] = (beta - alphr) / beta;
+        s_tau[1] = -alphi / beta;
+        s_scal[0] = 0.0; s_scal[1] = 0.0;                    // v = e_1: the tail is dropped
+        s_beta = beta;
       } else {
         double beta = dlapy3(alphr, alphi, xnorm);
         beta = (alphr >= 0.0) ? -beta : beta;               // -SIGN(norm, alphr)
@@ -292,10 +302,20 @@ __global__ void __launch_bounds__(CT, 1) k_qr_panel_cluster(PanelArgs p) {
     }
     __syncthreads();
     if (tx == 0 && ty == 0) {
-      const double xnorm = sqrt(fmax(gtot[c].x, 0.0));
+      // |x|^2 below 1e-200 cannot be formed accurately as a plain sum of squares (the terms are denormal); LAPACK's
+      // dznrm2 rescales, here such a tail (|x| < 1e-100 next to O(1) data) is treated as exactly zero: the reflector
+      // degenerates to a phase on the diagonal and Q stays an isometry to rounding.
+      const bool tiny_tail = gtot[c].x < 1.0e-200;
+      const double xnorm = tiny_tail ? 0.0 : sqrt(gtot[c].x);
       const double alphr = rowc[c].x, alphi = rowc[c].y;
       if (xnorm == 0.0 && alphi == 0.0) {
         s_tau[0] = 0.0; s_tau[1] = 0.0; s_scal[0] = 1.0; s_scal[1] = 0.0; s_beta = alphr;
+      } else if (tiny_tail) {
+        const double beta = (alphr >= 0.0) ? -hypot(alphr, alphi) : hypot(alphr, alphi);
+        s_tau[0] = (beta - alphr) / beta;
+        s_tau[1] = -alphi / beta;
+        s_scal[0] = 0.0; s_scal[1] = 0.0;                    // v = e_1: the tail is dropped
+        s_beta = beta;
       } else {
         double beta = dlapy3(alphr, alphi, xnorm);
         beta = (alphr >= 0.0) ? -beta : beta;

@@ -256,7 +256,10 @@ int svd_exec(Handle* h, int m, int n, const c128* sigma, c128* U, c128* Vh, doub
   std::stable_sort(hp.begin(), hp.end(), [&](int a, int b) { return hn[a] > hn[b]; });
   std::vector<double> hs(n);
   int r = 0;
-  for (int i = 0; i < n; ++i) { hs[i] = hn[hp[i]]; if (hs[i] > 0.0) r = i + 1; }
+  // Columns whose norm is below 1e-140 of the largest cannot be normalised reliably (their squares are denormal in
+  // the plain sums used by the rotations and by k_row_norms); their left vectors come from the orthonormal completion
+  // like those of exactly zero singular values.  The computed value is still reported.
+  for (int i = 0; i < n; ++i) { hs[i] = hn[hp[i]]; if (hs[i] > 0.0 && hs[i] >= 1.0e-140 * hs[0]) r = i + 1; }
   TDVP_CUDA(h, cudaMemcpyAsync(perm, hp.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
   TDVP_CUDA(h, cudaMemcpyAsync(svals, hs.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
   k_assemble_uv<<<148 * 2, 256, 0, st>>>(Gt, Vt, perm, svals, n, m, U, n, Vh, n);

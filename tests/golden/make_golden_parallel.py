@@ -18,7 +18,49 @@ CASES = {
     "par_exciton_P2": ("exciton", 2, [(0, 1), (2, 3)], 10, 0.05, 6),
     "par_hh8_P2": ("hh8", 2, [(0, 3), (4, 7)], 6, 0.05, 4),
     "par_hh8_P4": ("hh8", 4, [(0, 1), (2, 3), (4, 5), (6, 7)], 6, 0.05, 4),
+    # well-conditioned cases: an entangled random initial MPS that saturates every bond (no null space for the
+    # boundary pseudo-inverse / regularised SVD to amplify), so independent implementations can agree to 1e-10
+    "par_frenkel8_P2": ("frenkel8", 2, [(0, 1, 2, 3), (4, 5, 6, 7)], 4, 0.2, 10),
+    "par_frenkel8_P4": ("frenkel8", 4, [(0, 1), (2, 3), (4, 5), (6, 7)], 4, 0.2, 10),
 }
+
+
+def frenkel_model(n=8, D=4, seed=77):
+    """Frenkel-exciton chain  H = sum_i eps_i n_i + J sum_i (a+_i a_{i+1} + h.c.)  as a w = 4 nearest-neighbour MPO,
+    started from a random MPS of full bond dimension (3-D cores through the reference's lower-level init API,
+    _site_cls.py:459-472)."""
+    from pytdscf.basis import Exciton
+    from pytdscf.hamiltonian_cls import TensorHamiltonian
+    from pytdscf.dvr_operator_cls import TensorOperator
+
+    rng = np.random.default_rng(seed)
+    prim = [Exciton(nstate=2) for _ in range(n)]
+    a = np.array([[0.0, 1.0], [0.0, 0.0]], dtype=complex)
+    ad, one = a.T.copy(), np.eye(2, dtype=complex)
+    num = ad @ a
+    eps = 0.01 + 0.004 * rng.standard_normal(n)
+    J = 0.005
+    cores = []
+    for i in range(n):
+        W = np.zeros((4, 2, 2, 4), dtype=complex)
+        W[0, :, :, 0] = one
+        W[1, :, :, 0] = a
+        W[2, :, :, 0] = ad
+        W[3, :, :, 0] = eps[i] * num
+        W[3, :, :, 1] = J * ad
+        W[3, :, :, 2] = J * a
+        W[3, :, :, 3] = one
+        if i == 0:
+            W = W[3:4]
+        if i == n - 1:
+            W = W[:, :, :, 0:1]
+        cores.append(W)
+    key = tuple((i, i) for i in range(n))
+    legs = tuple(j for i in range(n) for j in (i, i))
+    ham = TensorHamiltonian(ndof=n, potential=[[{key: TensorOperator(mpo=cores, legs=legs)}]], backend="numpy")
+    dims = [1] + [min(D, 2 ** min(i, n - i)) for i in range(1, n)] + [1]
+    init = [(rng.standard_normal((dims[i], 2, dims[i + 1])) + 1j * rng.standard_normal((dims[i], 2, dims[i + 1]))) for i in range(n)]
+    return prim, {"hamiltonian": ham}, init
 
 
 def worker(case):
@@ -38,6 +80,9 @@ def worker(case):
     model_name, P, split, D, dt_fs, nstep = CASES[case]
     if model_name == "exciton":
         prim, ops, hartree = mg.exciton_model()
+        vib = None
+    elif model_name == "frenkel8":
+        prim, ops, hartree = frenkel_model(D=D)
         vib = None
     else:
         prim, ops, vib = mg.henon_heiles_model(2000, 1.0e-3, 8, 4)
@@ -82,7 +127,10 @@ def worker(case):
 
 def driver():
     sys.path.insert(0, ROOT)
+    only = os.environ.get("PAR_ONLY")
     for case, (model_name, P, split, D, dt_fs, nstep) in CASES.items():
+        if only and only not in case:
+            continue
         with tempfile.TemporaryDirectory() as tmp:
             procs = []
             for r in range(P):

@@ -351,3 +351,33 @@ def test_pinv(eng, K):
     Y[:, 30:] = 0
     ref = np.linalg.pinv(Y, rcond=1e-13)
     np.testing.assert_allclose(eng.pinv(eng.to_device(Y), 1e-13).cpu().numpy(), ref, atol=1e-11 * np.abs(ref).max())
+
+
+def _graded(rng, n, svals):
+    Q1, _ = np.linalg.qr(crand(rng, n, n))
+    Q2, _ = np.linalg.qr(crand(rng, n, n))
+    return (Q1 * np.asarray(svals)[None, :]) @ Q2.conj().T
+
+
+def test_svd_and_qr_denormal_directions(eng):
+    """Bond matrices of a padded Hartree-product start carry singular values like 1e-13, 1e-18, 1e-157 and exact zeros
+    (seen in the site-parallel runs): squares of the smallest are denormal, the factors must stay isometries."""
+    rng = np.random.default_rng(11)
+    # rows scaled like the bond matrices met in practice: lower-triangular with a 1, 2e-13, 8e-18, 7e-157, 0, 0 diagonal
+    L = np.tril(crand(rng, 6, 6)) * np.array([1.0, 2e-13, 8e-18, 7e-157, 0.0, 0.0])[:, None]
+    L[1:, 0] *= 1e-14
+    U, s, Vh = eng.svd(eng.to_device(L))
+    U, Vh = U.cpu().numpy(), Vh.cpu().numpy()
+    np.testing.assert_allclose(U.conj().T @ U, np.eye(6), atol=1e-13)
+    np.testing.assert_allclose(Vh @ Vh.conj().T, np.eye(6), atol=1e-13)
+    np.testing.assert_allclose((U * s[None, :]) @ Vh, L, atol=1e-15)
+    np.testing.assert_allclose(s[:3], np.linalg.svd(L, compute_uv=False)[:3], rtol=1e-10)
+    # LQ shift of a (6, 4, 6) centre tensor whose rows have those norms
+    psi = (crand(rng, 6, 24) * np.array([1.0, 2e-13, 8e-18, 7e-157, 0.0, 0.0])[:, None]).reshape(6, 4, 6)
+    B, sig = eng.qr_shift("B", eng.to_device(psi))
+    Bm = B.cpu().numpy().reshape(6, 24)
+    np.testing.assert_allclose(Bm @ Bm.conj().T, np.eye(6), atol=1e-13)
+    np.testing.assert_allclose(np.tensordot(sig.cpu().numpy(), B.cpu().numpy(), axes=(1, 0)), psi, atol=1e-15)
+    A, sig = eng.qr_shift("A", eng.to_device(np.ascontiguousarray(psi.transpose(2, 1, 0))))
+    Am = A.cpu().numpy().reshape(24, 6)
+    np.testing.assert_allclose(Am.conj().T @ Am, np.eye(6), atol=1e-13)

@@ -45,21 +45,12 @@ def _worker(rank, world, port, name, tmp, q):
 
 @pytest.mark.parametrize("name", PAR_CASES)
 def test_site_parallel_matches_reference(name, tmp_path):
-    import torch.multiprocessing as mp
+    from tests.mp_util import run_ranks
 
     g = load_parallel(name)
     P = g["nranks"]
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
     port = 31000 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_worker, args=(r, P, port, name, str(tmp_path), q)) for r in range(P)]
-    for p in procs:
-        p.start()
-    res = dict(q.get(timeout=600) for _ in procs)
-    for p in procs:
-        p.join(timeout=60)
-    for r in range(P):
-        assert "error" not in res[r], res[r]["error"]
+    res = run_ranks(_worker, P, (port, name, str(tmp_path)), timeout=600)
     hist = res[0]["history"]
     assert len(hist) == g["nstep"]
     # the injected oracle kernels use the same LAPACK calls as the reference, so the host logic must reproduce the
