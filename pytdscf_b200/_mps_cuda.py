@@ -333,5 +333,55 @@ class MPSCoefCuda:
     def norm(self) -> float:
         return math.sqrt(sum(self.pop_states()))
 
+    # -- reduced densities (reference _mps_cls.py:1208-1287, 1628-1678) ---------------------
+    def _pure_reduced_density(self, remain_nleg: tuple[int, ...]) -> np.ndarray:
+        """rho of the sites flagged in ``remain_nleg`` (0 = traced, 1 = diagonal only, 2 = ket and bra legs); index
+        order = site order, ket before bra.  Contracted right to left over the first len(remain_nleg) sites; the B-gauge
+        sites further right drop out.  Both contractions per site are DMMA GEMMs; index shuffles are strided copies."""
+        eng = self.eng
+        if self.sites[0].gauge != "Psi" or any(s.gauge != "B" for s in self.sites[1:]):
+            raise ValueError("the MPS must be canonical around site 0")
+        if len(remain_nleg) > self.nsite or not remain_nleg or remain_nleg[-1] not in (1, 2) or any(
+                n not in (0, 1, 2) for n in remain_nleg):
+            raise ValueError(f"invalid remain_nleg {remain_nleg}: entries 0/1/2, the last one 1 or 2")
+        cores = [s.data for s in self.sites[: len(remain_nleg)]]
+        C = cores.pop()
+        i, j, k = C.shape
+        Cm = C.reshape(i * j, k)
+        dens = eng.zgemm(Cm, Cm, 0, 2).reshape(i, j, i, j).permute(0, 2, 1, 3)   # [i, a, ket j, bra l]
+        if remain_nleg[-1] == 1:
+            dens = torch.diagonal(dens, dim1=2, dim2=3)
+        dens = dens.contiguous()
+        isite = len(remain_nleg) - 1
+        while cores:
+            isite -= 1
+            nleg = remain_nleg[isite]
+            C = cores.pop()
+            l, m, i = C.shape
+            a = dens.shape[1]
+            xshape = tuple(dens.shape[2:])
+            x = int(np.prod(xshape)) if xshape else 1
+            T = eng.zgemm(C.reshape(l * m, i), dens.reshape(i, a * x)).reshape(l, m, a, x)      # [l, m, a, X]
+            if nleg == 0:
+                T2 = T.permute(0, 3, 1, 2).reshape(l * x, m * a).contiguous()                  # [(l, X), (m, a)]
+                new = eng.zgemm(T2, C.reshape(l, m * a), 0, 2).reshape(l, x, l).permute(0, 2, 1)  # [l, b, X]
+                dens = new.reshape((l, l) + xshape).contiguous()
+            else:
+                T2 = T.permute(0, 1, 3, 2).reshape(l * m * x, a).contiguous()                  # [(l, m, X), a]
+                new = eng.zgemm(T2, C.reshape(l * m, a), 0, 2).reshape(l, m, x, l, m)          # [l, m, X, b, n]
+                new = new.permute(0, 3, 1, 4, 2)                                               # [l, b, m, n, X]
+                if nleg == 1:
+                    new = torch.diagonal(new, dim1=2, dim2=3).permute(0, 1, 3, 2)              # [l, b, m, X]
+                    dens = new.reshape((l, l, m) + xshape).contiguous()
+                else:
+                    dens = new.reshape((l, l, m, m) + xshape).contiguous()
+        return dens[0, 0].cpu().numpy()
+
+    def get_reduced_densities(self, remain_nleg) -> list[np.ndarray]:
+        """Reference ``MPSCoef.get_reduced_densities``: one key (tuple) or a list of keys -> list of arrays."""
+        if isinstance(remain_nleg, tuple):
+            remain_nleg = [remain_nleg]
+        return [self._pure_reduced_density(tuple(k)) for k in remain_nleg]
+
     def to_numpy(self) -> list[np.ndarray]:
         return [s.numpy() for s in self.sites]

@@ -52,6 +52,10 @@ class WFunc:
     def bonddim(self) -> list[int]:
         return self.ci_coef.bonddim()
 
+    def get_reduced_densities(self, remain_nleg) -> list[np.ndarray]:
+        """Reduced density matrices (reference ``wavefunction.py:67-88``); 0 = traced, 1 = diagonal, 2 = both legs."""
+        return self.ci_coef.get_reduced_densities(remain_nleg)
+
     def propagate_SM(self, matH, stepsize: float, cfg: RunConfig):
         self.ci_coef.propagate(stepsize, self.device_op(matH), cfg)
 
@@ -166,8 +170,22 @@ class Simulator:
                   display_time_unit: str = "fs", conserve_norm: bool = True, write_files: bool = True,
                   record_trace: bool = False):
         """Real-time propagation; returns ``(energy, wf)`` like the reference (energy of the last evaluated step)."""
+        self._rd = None
         if reduced_density is not None:
-            raise NotImplementedError("reduced densities are a 'next' row (SURVEY 8(f1)); not in backend='cuda' yet")
+            if self.model.space != "hilbert":
+                raise NotImplementedError("reduced densities of Liouville-space MPDOs (partial traces) are not implemented")
+            if parallel_split_indices is not None:
+                raise NotImplementedError("reduced densities are not implemented for site-parallel runs")
+            keys, rd_step = reduced_density
+            legs = []
+            for key in keys:   # site indices -> legs per site, as properties.py:64-83: (0, 0) -> (2,), (1, 2) -> (0, 1, 1)
+                cnt = [0] * (max(key) + 1)
+                for isite in key:
+                    cnt[isite] += 1
+                if any(c > 2 for c in cnt):
+                    raise ValueError(f"reduced_density key {key}: a site may appear at most twice")
+                legs.append(tuple(cnt))
+            self._rd = ([tuple(k) for k in keys], legs, int(rd_step))
         self._split = None
         if parallel_split_indices is not None:
             # reference: one MPI rank per tuple of consecutive sites (simulator_cls.py:243-249, _const_cls.py:236-251);
@@ -221,6 +239,9 @@ class Simulator:
                 rec["pops"] = wf.pop_states()
             if observables and istep % observables_per_step == 0:
                 rec["expectations"] = {k: wf.expectation(op) for k, op in self.model.observables.items()}
+            rd = getattr(self, "_rd", None)
+            if rd is not None and not relax and istep % rd[2] == 0:
+                rec["reduced_densities"] = dict(zip(rd[0], wf.get_reduced_densities(rd[1]), strict=True))
             self.history.append(rec)
             if files is not None:
                 self._export(files, cfg, rec, elapsed)
@@ -232,6 +253,12 @@ class Simulator:
             self.save_wavefunction(wf, savefile_ext)
             for f in files.values():
                 f.close()
+            rows = [r for r in self.history if "reduced_densities" in r]
+            if rows:   # the reference writes <job>/reduced_density.nc (netCDF4); same content as an .npz here
+                out = {"time_au": np.array([r["time_au"] for r in rows])}
+                for key in rows[0]["reduced_densities"]:
+                    out["rho_" + "_".join(map(str, key))] = np.stack([r["reduced_densities"][key] for r in rows])
+                np.savez(os.path.join(cfg.jobname, "reduced_density.npz"), **out)
         return (last_energy, wf)
 
     def relax(self, stepsize: float = 0.1, maxstep: int = 20, improved: bool = True, restart: bool = False,

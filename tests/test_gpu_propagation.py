@@ -204,3 +204,15 @@ def test_improved_relaxation_matches_reference(tmp_path):
     assert abs(ener - g["final_energy"].real) <= 1e-9 * abs(g["final_energy"].real)
     a, b = dense_state(wf.ci_coef.to_numpy()), dense_state(g["final"])
     assert abs(abs(np.vdot(a, b)) - 1.0) <= 1e-9
+
+
+def test_reduced_densities_gpu():
+    """Device reduced densities (two DMMA GEMMs per site) against the reference's get_reduced_densities goldens."""
+    from pytdscf_b200._engine import Engine
+    from pytdscf_b200._mps_cuda import MPSCoefCuda
+
+    eng = Engine(0)
+    from tests.golden_io import load_run
+    from tests.rdm_cases import check_rdms
+
+    check_rdms(eng, load_run, MPSCoefCuda, atol=1e-13)

@@ -133,3 +133,30 @@ def test_replicas_world_size_2_gloo():
         assert slowest == pytest.approx(max(secs))
         assert total == pytest.approx(2 * (2 * g["nstep"]) / max(secs))
         assert abs(e - g["final_energy"].real) < 1e-9  # energy is conserved; every replica ran the same physics
+
+
+def test_reduced_densities_host_logic():
+    """Index bookkeeping of the device reduced-density contraction against the reference's get_reduced_densities."""
+    from pytdscf_b200._mps_cuda import MPSCoefCuda
+    from tests.rdm_cases import check_rdms
+
+    check_rdms(OracleEngine(), load_run, MPSCoefCuda, atol=1e-14)
+
+
+def test_simulator_reduced_density_argument(tmp_path):
+    import pytdscf_b200 as tb
+
+    g = load_run("exciton_D6")
+    model = _build_model(g)
+    os.chdir(tmp_path)
+    sim = tb.Simulator("rd_cpu", model, backend="cuda")
+    sim.eng = OracleEngine()
+    sim.set_initial_mps(g["init"])
+    sim.propagate(stepsize=g["dt_au"] * tb.units.au_in_fs, maxstep=3, reduced_density=([(3, 3), (0,), (1, 2)], 2))
+    recs = [r for r in sim.history if "reduced_densities" in r]
+    assert len(recs) == 2
+    rho = recs[0]["reduced_densities"]
+    assert rho[(3, 3)].shape == (2, 2) and rho[(0,)].shape == (8,) and rho[(1, 2)].shape == (8, 8)
+    assert abs(np.trace(rho[(3, 3)]) - 1.0) < 1e-12 and abs(rho[(0,)].sum() - 1.0) < 1e-12
+    z = np.load(os.path.join("rd_cpu_prop", "reduced_density.npz"))
+    assert z["rho_3_3"].shape == (2, 2, 2) and len(z["time_au"]) == 2
