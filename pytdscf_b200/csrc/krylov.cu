@@ -541,6 +541,7 @@ int krylov_expm_exec(Handle* h, int kind, double scale_re, double scale_im, doub
   int cur = 0;          // ybuf[cur] receives the next Ritz vector
   bool have_prev = false;
   int nvec = 1;         // Krylov vectors stored (Arnoldi may stop appending)
+  int synced = 0;       // beta_[0 .. synced) are known on the host
   for (int l = 0; l < ndim; ++l) {
     c128* w = V + (size_t)(kind == TDVP_KRYLOV_ARNOLDI ? nvec : l + 1) * N;
     const c128* src = (l == 0) ? psi : (kind == TDVP_KRYLOV_ARNOLDI ? V + (size_t)(nvec - 1) * N : V + (size_t)l * N);
@@ -567,42 +568,58 @@ int krylov_expm_exec(Handle* h, int kind, double scale_re, double scale_im, doub
         TDVP_TRY(lc(h, "k_store_beta_hess"));
       }
     }
-    // w /= beta when beta >= EPS (Lanczos) / > EPS (Arnoldi): decided on device, mirrored on host below
+    // w /= beta when beta >= EPS (Lanczos) / > EPS (Arnoldi): decided on device, mirrored on host at the next read-back
     { ProfScope _ps(st, "vec.k_scale_dev"); k_scale_dev<<<vb, RED_THREADS, 0, st>>>(w, w, N, S + S_BETA + l, 0, kind == TDVP_KRYLOV_ARNOLDI ? nextafter(EPS_K, 1.0) : EPS_K); }
     TDVP_TRY(lc(h, "k_scale_dev"));
-    TDVP_CUDA(h, cudaMemcpyAsync(h->h_scal + S_BETA + l, S + S_BETA + l, sizeof(double), cudaMemcpyDeviceToHost, st));
-    TDVP_CUDA(h, cudaStreamSynchronize(st));
-    const double beta = h->h_scal[S_BETA + l];
-    if (!(beta == beta)) { set_error(h, "krylov_expm: NaN encountered in the Krylov recurrence"); return TDVP_ERR_NOT_CONVERGED; }
-    const bool conv = beta < EPS_K || (long long)(l + 1) == N;
-    if (kind == TDVP_KRYLOV_ARNOLDI && beta > EPS_K) ++nvec;
-    if (l < n_warm && !conv) continue;
+    // Warm-up iterations (the reference skips the Ritz step there, _integrator.py:560-575) need nothing on the host:
+    // the beta values are read back together with the first convergence scalar, so the stream keeps running ahead.
+    // A breakdown (beta < eps) inside the warm-up is detected at that read-back and replayed from the stored basis.
+    if (l < n_warm && (long long)(l + 1) < N) {
+      if (kind == TDVP_KRYLOV_ARNOLDI) ++nvec;    // speculative: beta > eps (checked below)
+      continue;
+    }
 
     // ---- Ritz step on device ----
     const int k = l + 1;
-    if (kind == TDVP_KRYLOV_LANCZOS_REF)
-      { ProfScope _ps(st, "vec.k_krylov_small_expm"); k_krylov_small_expm<<<1, 512, 0, st>>>(0, k, S + S_ALPHA, S + S_BETA, S + S_AREAL, nullptr, scale_re, scale_im, S + S_COEF); }
-    else
-      { ProfScope _ps(st, "vec.k_krylov_small_expm"); k_krylov_small_expm<<<1, 512, 0, st>>>(1, k, nullptr, nullptr, nullptr, S + S_HESS, scale_re, scale_im, S + S_COEF); }
-    TDVP_TRY(lc(h, "k_krylov_small_expm"));
+    auto ritz = [&](int kk, c128* yout, const c128* yprev) -> int {
+      if (kind == TDVP_KRYLOV_LANCZOS_REF)
+        { ProfScope _ps(st, "vec.k_krylov_small_expm"); k_krylov_small_expm<<<1, 512, 0, st>>>(0, kk, S + S_ALPHA, S + S_BETA, S + S_AREAL, nullptr, scale_re, scale_im, S + S_COEF); }
+      else
+        { ProfScope _ps(st, "vec.k_krylov_small_expm"); k_krylov_small_expm<<<1, 512, 0, st>>>(1, kk, nullptr, nullptr, nullptr, S + S_HESS, scale_re, scale_im, S + S_COEF); }
+      TDVP_TRY(lc(h, "k_krylov_small_expm"));
+      { ProfScope _ps(st, "vec.k_combine"); k_combine<<<nb, RED_THREADS, 0, st>>>(V, N, kk, S + S_COEF, yout, yprev, N, h->d_partial, h->d_counter, S + S_ERR, S + S_YNORM); }
+      return lc(h, "k_combine");
+    };
+    auto finish = [&](c128* yfin, int iters) -> int {
+      // rescale: y / |y| (conserve_norm) or y * b0, written back into psi
+      if (conserve_norm) { ProfScope _ps(st, "vec.k_scale_dev"); k_scale_dev<<<vb, RED_THREADS, 0, st>>>(yfin, psi, N, S + S_YNORM, 0, 0.0); }
+      else { ProfScope _ps(st, "vec.k_scale_dev"); k_scale_dev<<<vb, RED_THREADS, 0, st>>>(yfin, psi, N, S + S_B0, 1, 0.0); }
+      TDVP_TRY(lc(h, "k_scale_dev"));
+      if (niter) *niter = iters;
+      return 0;
+    };
     c128* y = ybuf[cur];
     const c128* prev = have_prev ? ybuf[cur ^ 1] : nullptr;
-    { ProfScope _ps(st, "vec.k_combine"); k_combine<<<nb, RED_THREADS, 0, st>>>(V, N, k, S + S_COEF, y, prev, N, h->d_partial, h->d_counter, S + S_ERR, S + S_YNORM); }
-    TDVP_TRY(lc(h, "k_combine"));
-    bool done = conv;
-    if (!done && have_prev) {
-      TDVP_CUDA(h, cudaMemcpyAsync(h->h_scal + S_ERR, S + S_ERR, sizeof(double), cudaMemcpyDeviceToHost, st));
-      TDVP_CUDA(h, cudaStreamSynchronize(st));
-      done = h->h_scal[S_ERR] < thresh;
+    TDVP_TRY(ritz(k, y, prev));
+    // one read-back per checked iteration: beta_[synced .. l] and the change of the Ritz vector
+    TDVP_CUDA(h, cudaMemcpyAsync(h->h_scal + S_BETA + synced, S + S_BETA + synced, sizeof(double) * (l + 1 - synced), cudaMemcpyDeviceToHost, st));
+    TDVP_CUDA(h, cudaMemcpyAsync(h->h_scal + S_ERR, S + S_ERR, sizeof(double), cudaMemcpyDeviceToHost, st));
+    TDVP_CUDA(h, cudaStreamSynchronize(st));
+    for (int j = synced; j <= l; ++j) {
+      const double bj = h->h_scal[S_BETA + j];
+      if (!(bj == bj)) { set_error(h, "krylov_expm: NaN encountered in the Krylov recurrence"); return TDVP_ERR_NOT_CONVERGED; }
+      if (j < l && bj < EPS_K) {
+        // the recurrence broke down at warm-up iteration j: the reference stops there with a (j+1)-vector Ritz step
+        TDVP_TRY(ritz(j + 1, y, nullptr));
+        return finish(y, j + 1);
+      }
     }
-    if (done) {
-      // rescale: y / |y| (conserve_norm) or y * b0, written back into psi
-      if (conserve_norm) { ProfScope _ps(st, "vec.k_scale_dev"); k_scale_dev<<<vb, RED_THREADS, 0, st>>>(y, psi, N, S + S_YNORM, 0, 0.0); }
-      else { ProfScope _ps(st, "vec.k_scale_dev"); k_scale_dev<<<vb, RED_THREADS, 0, st>>>(y, psi, N, S + S_B0, 1, 0.0); }
-      TDVP_TRY(lc(h, "k_scale_dev"));
-      if (niter) *niter = l + 1;
-      return 0;
-    }
+    synced = l + 1;
+    const double beta = h->h_scal[S_BETA + l];
+    const bool conv = beta < EPS_K || (long long)(l + 1) == N;
+    if (kind == TDVP_KRYLOV_ARNOLDI && beta > EPS_K) ++nvec;
+    const bool done = conv || (have_prev && h->h_scal[S_ERR] < thresh);
+    if (done) return finish(y, l + 1);
     have_prev = true;
     cur ^= 1;
   }

@@ -171,6 +171,42 @@ __global__ void k_diag_matrix(c128* __restrict__ S, int k, const double* __restr
   }
 }
 
+// max |off-diagonal| and max |diagonal| of an n x n matrix (one CTA; n <= a few thousand)
+__global__ void k_diag_probe(const c128* __restrict__ X, int n, double* __restrict__ out2) {
+  __shared__ double s_off[32], s_dia[32];
+  double off = 0.0, dia = 0.0;
+  const long long tot = (long long)n * n;
+  for (long long e = threadIdx.x; e < tot; e += blockDim.x) {
+    const c128 v = X[e];
+    const double a = fmax(fabs(v.x), fabs(v.y));
+    if (e / n == e % n) dia = fmax(dia, hypot(v.x, v.y)); else off = fmax(off, a);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    off = fmax(off, __shfl_xor_sync(0xffffffffu, off, o));
+    dia = fmax(dia, __shfl_xor_sync(0xffffffffu, dia, o));
+  }
+  if ((threadIdx.x & 31) == 0) { s_off[threadIdx.x >> 5] = off; s_dia[threadIdx.x >> 5] = dia; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { off = fmax(off, s_off[w]); dia = fmax(dia, s_dia[w]); }
+    out2[0] = off; out2[1] = dia;
+  }
+}
+
+// pseudo-inverse of a diagonal matrix: 1/d_i where |d_i| > rcond * max|d|, else 0
+__global__ void k_pinv_diag(const c128* __restrict__ X, int n, double cut, c128* __restrict__ out) {
+  const long long tot = (long long)n * n;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
+    c128 r = {0.0, 0.0};
+    if (e / n == e % n) {
+      const c128 v = X[e];
+      const double a2 = v.x * v.x + v.y * v.y;
+      if (sqrt(a2) > cut) r = {v.x / a2, -v.y / a2};
+    }
+    out[e] = r;
+  }
+}
+
 int ls(Handle* h, const char* what) {
   ++g_launch_count;
   cudaError_t e = cudaGetLastError();
@@ -327,6 +363,18 @@ int tdvp_pinv(tdvp_handle_t hh, int m, int n, const tdvp_c128* X, double rcond, 
   if (!h) return TDVP_ERR_ARG;
   h->err.clear();
   if (!X || !out || m <= 0 || n <= 0 || m != n) { set_error(h, "pinv: bad argument (square matrices only)"); return TDVP_ERR_ARG; }
+  // Bond matrices handed over by the site-parallel scheme are diagonal (the S of truncate_sigvec) in every step but
+  // the first: their pseudo-inverse needs no SVD.
+  {
+    k_diag_probe<<<1, 1024, 0, h->stream>>>((const c128*)X, n, h->d_scal + 4000);
+    TDVP_TRY(ls(h, "k_diag_probe"));
+    TDVP_CUDA(h, cudaMemcpyAsync(h->h_scal + 4000, h->d_scal + 4000, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    TDVP_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (h->h_scal[4000] == 0.0) {
+      k_pinv_diag<<<148, 256, 0, h->stream>>>((const c128*)X, n, rcond * h->h_scal[4001], (c128*)out);
+      return ls(h, "k_pinv_diag");
+    }
+  }
   c128 *U = nullptr, *Vh = nullptr;
   TDVP_CUDA(h, cudaMalloc((void**)&U, sizeof(c128) * (size_t)m * n));
   TDVP_CUDA(h, cudaMalloc((void**)&Vh, sizeof(c128) * (size_t)n * n));

@@ -110,13 +110,16 @@ size_t prof_json(char* out, size_t cap) {
 
 namespace {
 
-// Tile configurations.  The warp tile is always 32x32 complex (64 independent DMMA accumulations per k4-step).
-//   Big:   4x2 warps -> CTA tile 128x64, BK = 16, 3 stages (144 KiB), 1 CTA/SM      (bulk of the D >= 256 work)
-//   Small: 2x1 warps -> CTA tile  64x32, BK = 8,  4 stages ( 48 KiB), 4 CTAs/SM     (D <= 128: more CTAs, same 8 warps/SM)
-template <int WMW_, int WNW_, int BK_, int STAGES_>
+// Tile configurations.  Warp tile = (8 WI) x (8 WJ) complex, i.e. 4 WI WJ independent DMMA accumulations per k4-step.
+//   Big:   4x2 warps of 32x32 -> CTA tile 128x64, BK = 16, 3 stages (144 KiB), 1 CTA/SM   (bulk of the D >= 256 work)
+//   Small: 2x1 warps of 32x32 -> CTA tile  64x32, BK = 8,  4 stages ( 48 KiB), 4 CTAs/SM  (D <= 128: more CTAs, same 8 warps/SM)
+//   Tiny:  2x2 warps of 16x16 -> CTA tile  32x32, BK = 8,  3 stages ( 24 KiB), 4+ CTAs/SM  (D <= 64: a warp reaches only its
+//          SM sub-partition's quarter of the DMMA pipe, so latency-bound GEMMs want 4x less work per warp and 4x more warps)
+template <int WMW_, int WNW_, int BK_, int STAGES_, int WI_ = 4, int WJ_ = 4>
 struct Cfg {
-  static constexpr int WMW = WMW_, WNW = WNW_, BK = BK_, STAGES = STAGES_;
-  static constexpr int BM = 32 * WMW, BN = 32 * WNW, THREADS = 32 * WMW * WNW;
+  static constexpr int WMW = WMW_, WNW = WNW_, BK = BK_, STAGES = STAGES_, WI = WI_, WJ = WJ_;
+  static constexpr int WTM = 8 * WI, WTN = 8 * WJ;
+  static constexpr int BM = WTM * WMW, BN = WTN * WNW, THREADS = 32 * WMW * WNW;
   static constexpr int A_STAGE = BM * BK, B_STAGE = BN * BK;
   static constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) * (int)sizeof(c128);
   static constexpr int A_ITERS = A_STAGE / THREADS, B_ITERS = B_STAGE / THREADS;
@@ -124,6 +127,7 @@ struct Cfg {
 };
 using BigCfg = Cfg<4, 2, 16, 3>;
 using SmallCfg = Cfg<2, 1, 8, 4>;
+using TinyCfg = Cfg<2, 2, 8, 3, 2, 2>;
 
 __device__ __forceinline__ void cp_async16(c128* smem, const c128* gmem, bool pred) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -232,11 +236,12 @@ __global__ void __launch_bounds__(C::THREADS, C::THREADS == 256 ? 1 : 4) zgemm_d
     pb.issue(tid, Bs + stage * B_STAGE, Bg, d.b_k, k0, k_end);
   };
 
-  double cre[4][4][2], cim[4][4][2];
+  constexpr int WI = C::WI, WJ = C::WJ;
+  double cre[WI][WJ][2], cim[WI][WJ][2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < WI; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < WJ; ++j) {
       cre[i][j][0] = cre[i][j][1] = 0.0;
       cim[i][j][0] = cim[i][j][1] = 0.0;
     }
@@ -265,34 +270,34 @@ __global__ void __launch_bounds__(C::THREADS, C::THREADS == 256 ? 1 : 4) zgemm_d
 #pragma unroll
     for (int k4 = 0; k4 < BK / 4; ++k4) {
       const int kk = k4 * 4 + q;
-      double are[4], aim[4], naim[4], bre[4], bim[4];
+      double are[WI], aim[WI], naim[WI], bre[WJ], bim[WJ];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = wm * 32 + 8 * i + g;
+      for (int i = 0; i < WI; ++i) {
+        const int r = wm * C::WTM + 8 * i + g;
         const c128 v = as[tile_chunk<A_KMAJOR, BM, BK>(r, kk)];
         are[i] = v.x;
         aim[i] = flip_sign(v.y, sa);
         naim[i] = flip_sign(v.y, sa ^ 0x80000000u);
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int r = wn * 32 + 8 * j + g;
+      for (int j = 0; j < WJ; ++j) {
+        const int r = wn * C::WTN + 8 * j + g;
         const c128 v = bs[tile_chunk<B_KMAJOR, BN, BK>(r, kk)];
         bre[j] = v.x;
         bim[j] = flip_sign(v.y, sb);
       }
-      // two passes so that dependent accumulations into the same tile are 32 DMMAs apart
+      // two passes so that dependent accumulations into the same tile are 2 WI WJ DMMAs apart
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < WI; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < WJ; ++j) {
           dmma(cre[i][j][0], cre[i][j][1], are[i], bre[j]);
           dmma(cim[i][j][0], cim[i][j][1], are[i], bim[j]);
         }
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < WI; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < WJ; ++j) {
           dmma(cre[i][j][0], cre[i][j][1], naim[i], bim[j]);
           dmma(cim[i][j][0], cim[i][j][1], aim[i], bre[j]);
         }
@@ -304,15 +309,15 @@ __global__ void __launch_bounds__(C::THREADS, C::THREADS == 256 ? 1 : 4) zgemm_d
   const c128 alpha = d.alpha, beta = d.beta;
   const bool use_beta = (beta.x != 0.0) || (beta.y != 0.0);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = tile_m + wm * 32 + 8 * i + g;
+  for (int i = 0; i < WI; ++i) {
+    const int m = tile_m + wm * C::WTM + 8 * i + g;
     if (m >= d.M) continue;
     const long long roff = (long long)(m / d.c_m_inner) * d.c_m1 + (long long)(m % d.c_m_inner) * d.c_m0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < WJ; ++j) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int n = tile_n + wn * 32 + 8 * j + 2 * q + e;
+        const int n = tile_n + wn * C::WTN + 8 * j + 2 * q + e;
         if (n >= d.N) continue;
         c128* p = Cg + roff + (long long)n * d.c_n;
         c128 acc = {cre[i][j][e], cim[i][j][e]};
@@ -353,13 +358,16 @@ inline long long tiles_of(const GemmDesc& d, int bm, int bn) {
   return (long long)((d.M + bm - 1) / bm) * ((d.N + bn - 1) / bn) * d.batch;
 }
 
-// The small tile is used when the big one would occupy fewer than half of the SMs.
+// The small tile is used when the big one would occupy fewer than half of the SMs, the tiny one when even the small
+// tiling leaves SM sub-partitions without a warp (< 2 small CTAs = 4 warps per SM).
 inline bool use_small(const GemmDesc& d) { return tiles_of(d, BigCfg::BM, BigCfg::BN) < 74; }
+inline bool use_tiny(const GemmDesc& d) { return tiles_of(d, SmallCfg::BM, SmallCfg::BN) < 2 * 148; }
 
 }  // namespace
 
 cudaError_t zgemm_launch(const GemmDesc& d, cudaStream_t stream) {
   if (d.M <= 0 || d.N <= 0 || d.batch <= 0) return cudaSuccess;
+  if (use_tiny(d)) return launch_cfg<TinyCfg>(d, stream);
   return use_small(d) ? launch_cfg<SmallCfg>(d, stream) : launch_cfg<BigCfg>(d, stream);
 }
 
@@ -386,18 +394,20 @@ __global__ void k_splitk_reduce(const c128* __restrict__ P, int S, int M, int N,
 
 cudaError_t zgemm_auto(const GemmDesc& d, cudaStream_t stream, c128* scratch, size_t scratch_elems) {
   if (d.M <= 0 || d.N <= 0 || d.batch <= 0) return cudaSuccess;
-  const bool small = use_small(d);
-  const int bm = small ? SmallCfg::BM : BigCfg::BM, bn = small ? SmallCfg::BN : BigCfg::BN;
-  const int bk = small ? SmallCfg::BK : BigCfg::BK;
+  const bool tiny = use_tiny(d);
+  const bool small = !tiny && use_small(d);
+  const int bm = tiny ? TinyCfg::BM : (small ? SmallCfg::BM : BigCfg::BM), bn = tiny ? TinyCfg::BN : (small ? SmallCfg::BN : BigCfg::BN);
+  const int bk = (tiny || small) ? 8 : BigCfg::BK;
   const long long tiles = tiles_of(d, bm, bn);
-  const int min_chunk = small ? 64 : 128;
+  const int min_chunk = tiny ? 32 : (small ? 64 : 128);
   if (d.batch != 1 || d.K < 2 * min_chunk || scratch == nullptr || tiles >= 8 * 148) return zgemm_launch(d, stream);
   // Wave-aware split-K: model t(S) = waves(S) * (K/S + K0) * t_k + reduction traffic and pick the best S.
   // One SM sustains ~220 GFLOP/s of DMMA work: a 128x64 tile costs ~0.30 us per k; a 64x32 tile ~0.075 us per k when it
-  // has an SM to itself and 4 of them share an SM at the same aggregate rate (slots = 4 x 148, t_k x 4); K0 ~ prologue
-  // + epilogue in units of k.
-  const double t_k = small ? 0.30e-6 : 0.30e-6, K0 = small ? 24.0 : 32.0, bw = 5.0e12;
-  const int slots = small ? 4 * 148 : 148;
+  // has an SM to itself and 4 of them share an SM at the same aggregate rate (slots = 4 x 148, t_k x 4); a 32x32 tiny
+  // tile (4 warps of 16x16) ~0.02 us per k alone, 4 slots per SM; K0 ~ prologue + epilogue in units of k.
+  const double lone = tiny ? 0.02e-6 : 0.075e-6;
+  const double t_k = tiny ? 0.16e-6 : 0.30e-6, K0 = tiny ? 16.0 : (small ? 24.0 : 32.0), bw = 5.0e12;
+  const int slots = tiny ? 4 * 148 : (small ? 4 * 148 : 148);
   int best_s = 1;
   double best_t = 1e30;
   const int max_s = d.K / min_chunk < 16 ? d.K / min_chunk : 16;
@@ -410,8 +420,8 @@ cudaError_t zgemm_auto(const GemmDesc& d, cudaStream_t stream, c128* scratch, si
     const long long units = tiles * S;
     // fewer units than SMs: every CTA has its SM to itself (a lone small CTA runs 4x faster per k than when 4 share)
     double per_k = t_k;
-    if (small && units <= 148) per_k = 0.075e-6;
-    else if (small && units < slots) per_k = 0.075e-6 * (double)((units + 147) / 148);
+    if ((small || tiny) && units <= 148) per_k = lone;
+    else if ((small || tiny) && units < slots) per_k = lone * (double)((units + 147) / 148);
     const double waves = (double)((units + slots - 1) / slots);
     double t = waves * (chunk + K0) * per_k;
     if (S > 1) t += (double)(S + 2) * d.M * d.N * 16.0 / bw + 4.0e-6;
