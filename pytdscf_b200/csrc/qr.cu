@@ -38,6 +38,7 @@ struct PanelArgs {
   double* gpart;   // 2 buffers x G x (2*NB complex): [buf][cta][0..NB) partial g, [NB..2NB) diagonal row broadcast
   double* zpart;   // G x NB x NB complex partial Gram for T
   int rows_per_cta;
+  int dbg;         // timing experiments only (TDVP_QR_DEBUG): bit 0 skips the column loop, bit 1 the T factor
 };
 
 __device__ __forceinline__ double dlapy3(double x, double y, double z) {
@@ -247,8 +248,8 @@ __global__ void __launch_bounds__(CT, 1) k_qr_panel_cluster(PanelArgs p) {
   __shared__ c128 red[CTY][NB + 1];
   __shared__ c128 pbuf[2][NB];   // this CTA's partial g (double-buffered by column parity)
   __shared__ c128 rbuf[2][NB];   // diagonal row broadcast (valid in the owner CTA)
-  __shared__ c128 gtot[NB], rowc[NB], wv[NB];
-  __shared__ double s_tau[2], s_scal[2], s_beta;
+  __shared__ c128 gtot[NB], rowc[NB];
+  __shared__ double s_zl[5];     // zlarfg scalars of the current column: tau, 1/(alpha - beta), beta
   cg::cluster_group cluster = cg::this_cluster();
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int G = gridDim.x, b = blockIdx.x;
@@ -264,98 +265,120 @@ __global__ void __launch_bounds__(CT, 1) k_qr_panel_cluster(PanelArgs p) {
   }
   __syncthreads();
 
-  for (int c = 0; c < jb; ++c) {
+  // partial g for column 0; for c > 0 it is accumulated while column c-1 is applied (one pass over the slab per column)
+  c128 acc = {0.0, 0.0};
+  if (tx < jb) {
+    for (int i = ty; i < nrow; i += CTY) {
+      if (r0 + i > j0) {
+        const c128 x = S[i * NB + 0], y = S[i * NB + tx];
+        acc.x += x.x * y.x + x.y * y.y;
+        acc.y += x.x * y.y - x.y * y.x;
+      }
+    }
+  }
+  for (int c = 0; c < ((p.dbg & 1) ? 0 : jb); ++c) {
     const int grow = j0 + c;
     const int buf = c & 1;
     const int owner = (grow - j0) / p.rows_per_cta;
-    c128 acc = {0.0, 0.0};
-    if (tx >= c && tx < jb) {
-      for (int i = ty; i < nrow; i += CTY) {
-        if (r0 + i > grow) {
-          const c128 x = S[i * NB + c], y = S[i * NB + tx];
-          acc.x += x.x * y.x + x.y * y.y;
-          acc.y += x.x * y.y - x.y * y.x;
-        }
-      }
-    }
     red[ty][tx] = acc;
     __syncthreads();
-    if (ty == 0) {
-      c128 t = {0.0, 0.0};
+    {
+      // warp ty reduces column ty over the 32 row groups (fixed butterfly order), lane 0 publishes it
+      c128 t = red[tx][ty];
 #pragma unroll
-      for (int q = 0; q < CTY; ++q) { t.x += red[q][tx].x; t.y += red[q][tx].y; }
-      pbuf[buf][tx] = t;
-      if (b == owner) rbuf[buf][tx] = S[(grow - r0) * NB + tx];
+      for (int o = 16; o > 0; o >>= 1) {
+        t.x += __shfl_xor_sync(0xffffffffu, t.x, o);
+        t.y += __shfl_xor_sync(0xffffffffu, t.y, o);
+      }
+      if (tx == 0) pbuf[buf][ty] = t;
+      if (ty == 0 && b == owner) rbuf[buf][tx] = S[(grow - r0) * NB + tx];
     }
     cluster.sync();
     if (ty == 0) {
-      c128 t = {0.0, 0.0};
-      for (int q = 0; q < G; ++q) {
-        const c128* remote = cluster.map_shared_rank(&pbuf[buf][0], q);
-        const c128 v = remote[tx];
-        t.x += v.x;
-        t.y += v.y;
+      // all remote partials are requested before the first one is consumed (DSMEM latency ~215 cycles each)
+      c128 part[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        part[q] = {0.0, 0.0};
+        if (q < G) part[q] = cluster.map_shared_rank(&pbuf[buf][0], q)[tx];
       }
+      const c128 rc = cluster.map_shared_rank(&rbuf[buf][0], owner)[tx];
+      c128 t = {0.0, 0.0};
+#pragma unroll
+      for (int q = 0; q < 16; ++q) { t.x += part[q].x; t.y += part[q].y; }
       gtot[tx] = t;
-      const c128* rrow = cluster.map_shared_rank(&rbuf[buf][0], owner);
-      rowc[tx] = rrow[tx];
-    }
-    __syncthreads();
-    if (tx == 0 && ty == 0) {
+      rowc[tx] = rc;
+      // zlarfg by this warp (every lane the same values), published through shared memory
+      const double g2 = __shfl_sync(0xffffffffu, t.x, c);
+      const double alphr = __shfl_sync(0xffffffffu, rc.x, c), alphi = __shfl_sync(0xffffffffu, rc.y, c);
       // |x|^2 below 1e-200 cannot be formed accurately as a plain sum of squares (the terms are denormal); LAPACK's
       // dznrm2 rescales, here such a tail (|x| < 1e-100 next to O(1) data) is treated as exactly zero: the reflector
       // degenerates to a phase on the diagonal and Q stays an isometry to rounding.
-      const bool tiny_tail = gtot[c].x < 1.0e-200;
-      const double xnorm = tiny_tail ? 0.0 : sqrt(gtot[c].x);
-      const double alphr = rowc[c].x, alphi = rowc[c].y;
+      const bool tiny_tail = g2 < 1.0e-200;
+      const double xnorm = tiny_tail ? 0.0 : sqrt(g2);
+      c128 tau_, sc_;
+      double hb_;
       if (xnorm == 0.0 && alphi == 0.0) {
-        s_tau[0] = 0.0; s_tau[1] = 0.0; s_scal[0] = 1.0; s_scal[1] = 0.0; s_beta = alphr;
+        tau_ = {0.0, 0.0}; sc_ = {1.0, 0.0}; hb_ = alphr;
       } else if (tiny_tail) {
         const double beta = (alphr >= 0.0) ? -hypot(alphr, alphi) : hypot(alphr, alphi);
-        s_tau[0] = (beta - alphr) / beta;
-        s_tau[1] = -alphi / beta;
-        s_scal[0] = 0.0; s_scal[1] = 0.0;                    // v = e_1: the tail is dropped
-        s_beta = beta;
+        tau_ = {(beta - alphr) / beta, -alphi / beta};
+        sc_ = {0.0, 0.0};                                    // v = e_1: the tail is dropped
+        hb_ = beta;
       } else {
         double beta = dlapy3(alphr, alphi, xnorm);
         beta = (alphr >= 0.0) ? -beta : beta;
-        s_tau[0] = (beta - alphr) / beta;
-        s_tau[1] = -alphi / beta;
+        tau_ = {(beta - alphr) / beta, -alphi / beta};
         const double dr = alphr - beta, di = alphi;
         const double den = dr * dr + di * di;
-        s_scal[0] = dr / den; s_scal[1] = -di / den;
-        s_beta = beta;
+        sc_ = {dr / den, -di / den};
+        hb_ = beta;
       }
-      if (b == 0) { p.tau[2 * (j0 + c)] = s_tau[0]; p.tau[2 * (j0 + c) + 1] = s_tau[1]; }
+      if (tx == 0) {
+        s_zl[0] = tau_.x; s_zl[1] = tau_.y; s_zl[2] = sc_.x; s_zl[3] = sc_.y; s_zl[4] = hb_;
+        if (b == 0) { p.tau[2 * (j0 + c)] = tau_.x; p.tau[2 * (j0 + c) + 1] = tau_.y; }
+      }
     }
     __syncthreads();
-    const c128 tau = {s_tau[0], s_tau[1]};
-    const c128 sc = {s_scal[0], s_scal[1]};
+    const c128 tau = {s_zl[0], s_zl[1]}, sc = {s_zl[2], s_zl[3]};
+    const double hbeta = s_zl[4];
     const bool trivial = (tau.x == 0.0 && tau.y == 0.0);
-    if (ty == 0 && tx > c && tx < jb) {
+    c128 wv = {0.0, 0.0};
+    if (tx > c && tx < jb) {
       const c128 cs = {sc.x, -sc.y};
-      wv[tx] = cadd(rowc[tx], cmul(cs, gtot[tx]));
+      wv = cadd(rowc[tx], cmul(cs, gtot[tx]));               // w_j = a_cj + conj(s) g_j
     }
-    __syncthreads();
-    if (!trivial) {
-      const c128 ctau = {tau.x, -tau.y};
-      for (int i = ty; i < nrow; i += CTY) {
-        const int gr = r0 + i;
-        if (gr < grow) continue;
+    // apply H^H = I - conj(tau) v v^H to the remaining columns, store v / beta in column c, and in the same pass
+    // accumulate the next column's partial g (lane c+1 holds the freshly updated a_{i,c+1})
+    const c128 ctau = {tau.x, -tau.y};
+    acc = {0.0, 0.0};
+    const int cn = (c + 1 < NB) ? c + 1 : c;
+    for (int i = ty; i < nrow; i += CTY) {
+      const int gr = r0 + i;
+      if (gr < grow) continue;                               // uniform per warp (ty selects the row)
+      c128 mine = S[i * NB + tx];
+      if (!trivial) {
         c128 v;
         if (gr == grow) v = {1.0, 0.0};
         else v = cmul(S[i * NB + c], sc);
         if (tx > c && tx < jb) {
-          const c128 f = cmul(ctau, cmul(v, wv[tx]));
-          S[i * NB + tx].x -= f.x;
-          S[i * NB + tx].y -= f.y;
+          const c128 f = cmul(ctau, cmul(v, wv));
+          mine.x -= f.x;
+          mine.y -= f.y;
         }
-        __syncwarp();
-        if (tx == c) S[i * NB + c] = (gr == grow) ? c128{s_beta, 0.0} : v;
+        if (tx == c) mine = (gr == grow) ? c128{hbeta, 0.0} : v;
+        __syncwarp();                                        // every lane has read S[i][c] before lane c overwrites it
+        if (tx >= c) S[i * NB + tx] = mine;
+      }
+      const double xr = __shfl_sync(0xffffffffu, mine.x, cn);
+      const double xi = __shfl_sync(0xffffffffu, mine.y, cn);
+      if (gr > grow + 1 && tx > c && tx < jb) {
+        acc.x += xr * mine.x + xi * mine.y;
+        acc.y += xr * mine.y - xi * mine.x;
       }
     }
-    __syncthreads();
   }
+  __syncthreads();
 
   for (int i = ty; i < nrow; i += CTY) {
     const int gr = r0 + i;
@@ -402,7 +425,7 @@ __global__ void __launch_bounds__(CT, 1) k_qr_panel_cluster(PanelArgs p) {
     T[a * NB + tx] = {0.0, 0.0};
   }
   __syncthreads();
-  for (int c = 0; c < jb; ++c) {
+  for (int c = 0; c < ((p.dbg & 2) ? 0 : jb); ++c) {
     const c128 tau = {__ldcg(&p.tau[2 * (j0 + c)]), __ldcg(&p.tau[2 * (j0 + c) + 1])};
     if (ty == 0 && tx < c) {
       c128 s = {0.0, 0.0};
@@ -499,6 +522,7 @@ int qr_factor(Handle* h, c128* A, int m, int n, int lda, c128* Q, int ldq) {
     max_coop = nsm;
     configured = true;
   }
+  static const int qr_dbg = getenv("TDVP_QR_DEBUG") ? atoi(getenv("TDVP_QR_DEBUG")) : 0;
   const int np = (n + NB - 1) / NB;
   c128* Vall = (c128*)ws_alloc(h, sizeof(c128) * (size_t)m * lda);
   c128* Tall = (c128*)ws_alloc(h, sizeof(c128) * (size_t)np * NB * NB);
@@ -522,7 +546,7 @@ int qr_factor(Handle* h, c128* A, int m, int n, int lda, c128* Q, int ldq) {
       while (G < max_cluster && (mp + G - 1) / G > 128) G *= 2;
       while ((mp + G - 1) / G > CL_ROWS) G *= 2;
       const int rpc = (mp + G - 1) / G;
-      PanelArgs pa{A, lda, m, n, j0, jb, tau, Vall, Tall, gpart, zpart, rpc};
+      PanelArgs pa{A, lda, m, n, j0, jb, tau, Vall, Tall, gpart, zpart, rpc, qr_dbg};
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(G);
       cfg.blockDim = dim3(32, CTY);
@@ -541,7 +565,7 @@ int qr_factor(Handle* h, c128* A, int m, int n, int lda, c128* Q, int ldq) {
       if (G > max_coop) { set_error(h, "qr_factor: matrix too tall for the cooperative panel kernel"); return TDVP_ERR_UNSUPPORTED; }
       if (G < 1) G = 1;
       rpc = (mp + G - 1) / G;  // spread rows evenly
-      PanelArgs pa{A, lda, m, n, j0, jb, tau, Vall, Tall, gpart, zpart, rpc};
+      PanelArgs pa{A, lda, m, n, j0, jb, tau, Vall, Tall, gpart, zpart, rpc, qr_dbg};
       void* args[] = {&pa};
       const size_t smem = sizeof(c128) * (size_t)(rpc > 2 * NB ? rpc : 2 * NB) * NB;
       { ProfScope _ps(h->stream, "qr.k_qr_panel"); e = cudaLaunchCooperativeKernel((void*)k_qr_panel, dim3(G), dim3(32, PTY), args, smem, h->stream); }
