@@ -499,7 +499,9 @@ def run_cuda(args):
                    "l2": "per-step working set (Krylov basis + contraction intermediates, GBs) >> 126 MB L2; no explicit flush"},
         "clocks": clocks,
         "heff_tflops": flops_all / (ms * 1e-3) / 1e12,
-        "heff_tflops_note": "algorithmic H_eff + K_eff + env-update flops (SURVEY 8(d)) / wall time of the timed region (all kernels)",
+        "heff_tflops_note": "algorithmic H_eff + K_eff + env-update flops of the reference's contraction (SURVEY 8(d) formula, identity "
+                            "MPO channels included) / wall time of the timed region (all kernels); the roofline entry counts "
+                            "the flops the GEMM launches actually execute",
         "krylov": {"avg_matvecs_H": stats["avg_matvecs_H"], "avg_matvecs_K": stats["avg_matvecs_K"],
                    "solves_per_step": len(trace) / args.steps, "tflop_per_sweep": flops_per_sweep / 1e12},
         "gpu_launches": int(launches),

@@ -37,21 +37,26 @@ enum { TDVP_GAUGE_A = 0, TDVP_GAUGE_B = 1 };
  * placeholders.  L: NULL (identity) or (Dl, wl, Dl).  W: NULL (identity; then wl == wr == 1), diagonal
  * (wl, d, wr) when w_kind == TDVP_KIND_DIAG, full (wl, d, d, wr) when TDVP_KIND_FULL.  R: NULL or
  * (Dr, wr, Dr).  `Wp` is an optional pre-permuted copy of a full core, Wp[c,j,i,t] = W[c,i,j,t]
- * (NULL: permuted on the fly).  `coef` scales the term (the reference's coupleJ on the "ovlp" term). */
+ * (NULL: permuted on the fly).  `coef` scales the term (the reference's coupleJ on the "ovlp" term).
+ * `id_channels` = (l_id + 1) | ((r_id + 1) << 16), 0 = none: optional promise by the caller that MPO channel l_id of L
+ * (resp. r_id of R) is the identity matrix -- the "nothing happened yet / everything done" channel of an MPO whose
+ * block was built from canonical (isometric) site tensors, where the reference contracts an explicit, numerically
+ * unit block.  The library then copies instead of multiplying for that channel (large tensors only). */
 typedef struct {
   const tdvp_c128* L;
   const tdvp_c128* W;
   const tdvp_c128* Wp;
   const tdvp_c128* R;
-  int32_t wl, wr, w_kind, reserved;
+  int32_t wl, wr, w_kind, id_channels;
   double coef_re, coef_im;
 } tdvp_heff_term;
 
-/* One term of K_eff (pytdscf/_contraction.py:1297-1352, `_op_lr_dot`): L NULL or (D_l, w, D_l), R NULL or (D_r, w, D_r). */
+/* One term of K_eff (pytdscf/_contraction.py:1297-1352, `_op_lr_dot`): L NULL or (D_l, w, D_l), R NULL or (D_r, w, D_r);
+ * `id_channels` as in tdvp_heff_term. */
 typedef struct {
   const tdvp_c128* L;
   const tdvp_c128* R;
-  int32_t w, reserved;
+  int32_t w, id_channels;
   double coef_re, coef_im;
 } tdvp_keff_term;
 

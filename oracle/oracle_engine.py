@@ -56,7 +56,7 @@ class OracleEngine:
 
     def keff_apply(self, terms, sigma):
         out = None
-        for (L, R, coef) in terms:
+        for (L, R, coef, *_ids) in terms:
             add = orc.keff_term(_np(L), _np(R), sigma.numpy())
             if complex(coef) != 1.0:
                 add = add * complex(coef)

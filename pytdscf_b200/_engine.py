@@ -23,6 +23,8 @@ class DeviceCore:
 
     data: torch.Tensor | None  # (wl,d,wr) diagonal or (wl,d,d,wr) full; None = identity gap core
     perm: torch.Tensor | None = None  # full cores: Wp[c,j,i,t] = W[c,i,j,t], made once at upload
+    l_id: int = -1  # channel of the incoming MPO bond whose left block is the identity (canonical MPS), -1 = none
+    r_id: int = -1  # channel of the outgoing MPO bond whose right block is the identity, -1 = none
 
     @property
     def kind(self) -> int:
@@ -115,15 +117,20 @@ class Engine:
                     raise ValueError("left block / core bond dimension mismatch")
                 if R is not None and int(R.shape[1]) != core.wr:
                     raise ValueError("right block / core bond dimension mismatch")
+                t.id_channels = ((core.l_id + 1) if L is not None else 0) | (((core.r_id + 1) if R is not None else 0) << 16)
             c = complex(coef)
             t.coef_re, t.coef_im = c.real, c.imag
         return arr
 
     def keff_terms(self, terms):
-        """terms: iterable of (L | None, R | None, coef)."""
+        """terms: iterable of (L | None, R | None, coef[, (l_id, r_id)]) -- the optional pair names the MPO channels whose
+        left / right block is the identity (see ``tdvp_keff_term.id_channels``)."""
         arr = (KeffTerm * len(terms))()
-        for i, (L, R, coef) in enumerate(terms):
+        for i, term in enumerate(terms):
+            L, R, coef = term[:3]
             t = arr[i]
+            if len(term) > 3 and term[3] is not None and L is not None and R is not None:
+                t.id_channels = (term[3][0] + 1) | ((term[3][1] + 1) << 16)
             t.L = None if L is None else L.data_ptr()
             t.R = None if R is None else R.data_ptr()
             if L is not None and R is not None and L.shape[1] != R.shape[1]:

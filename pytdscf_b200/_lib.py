@@ -34,14 +34,14 @@ class c128(C.Structure):
 class HeffTerm(C.Structure):
     _fields_ = [
         ("L", C.c_void_p), ("W", C.c_void_p), ("Wp", C.c_void_p), ("R", C.c_void_p),
-        ("wl", C.c_int32), ("wr", C.c_int32), ("w_kind", C.c_int32), ("reserved", C.c_int32),
+        ("wl", C.c_int32), ("wr", C.c_int32), ("w_kind", C.c_int32), ("id_channels", C.c_int32),
         ("coef_re", C.c_double), ("coef_im", C.c_double),
     ]
 
 
 class KeffTerm(C.Structure):
     _fields_ = [
-        ("L", C.c_void_p), ("R", C.c_void_p), ("w", C.c_int32), ("reserved", C.c_int32),
+        ("L", C.c_void_p), ("R", C.c_void_p), ("w", C.c_int32), ("id_channels", C.c_int32),
         ("coef_re", C.c_double), ("coef_im", C.c_double),
     ]
 

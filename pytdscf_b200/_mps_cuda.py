@@ -16,6 +16,7 @@ hand-over between sweeps); all arithmetic is ``Engine`` calls into libtdvp_b200 
 from __future__ import annotations
 
 import math
+import dataclasses
 from dataclasses import dataclass
 
 import numpy as np
@@ -63,6 +64,42 @@ class DeviceTerm:
     is_right: bool
 
 
+def identity_channels(cores: list[np.ndarray]) -> tuple[list[int], list[int]]:
+    """For the cores of one MPO term return ``(pre, suf)``: ``pre[k]`` = channel of the bond LEFT of core k that carries
+    nothing but identity operators from the left end (its left environment block is <A|A> = 1 for canonical tensors),
+    ``suf[k]`` = channel of the bond RIGHT of core k that carries only identities up to the right end; -1 = none.
+    Exact comparisons only: a channel qualifies when its single incoming (outgoing) block is exactly the unit matrix."""
+    n = len(cores)
+
+    def is_unit(b: np.ndarray) -> bool:
+        return bool(np.array_equal(b, np.ones_like(b))) if b.ndim == 1 else bool(np.array_equal(b, np.eye(b.shape[0])))
+
+    bond = [-1] * (n + 1)           # bond[k]: identity-prefix channel of the bond left of core k
+    bond[0] = 0 if cores[0].shape[0] == 1 else -1
+    for k, W in enumerate(cores):
+        if bond[k] < 0:
+            break
+        for t in range(W.shape[-1]):
+            col = W[..., t]
+            nz = [c for c in range(W.shape[0]) if np.any(col[c] != 0)]
+            if nz == [bond[k]] and is_unit(col[bond[k]]):
+                bond[k + 1] = t
+                break
+    dnob = [-1] * (n + 1)           # dnob[k]: identity-suffix channel of the bond left of core k (right of core k-1)
+    dnob[n] = 0 if cores[-1].shape[-1] == 1 else -1
+    for k in range(n - 1, -1, -1):
+        W = cores[k]
+        if dnob[k + 1] < 0:
+            break
+        for c in range(W.shape[0]):
+            row = W[c]
+            nz = [t for t in range(W.shape[-1]) if np.any(row[..., t] != 0)]
+            if nz == [dnob[k + 1]] and is_unit(row[..., dnob[k + 1]]):
+                dnob[k] = c
+                break
+    return bond[:n], dnob[1:]
+
+
 class DeviceMPO:
     """MPO cores of a ``TensorHamiltonian`` uploaded to HBM once (complex128; float cores are widened)."""
 
@@ -71,6 +108,17 @@ class DeviceMPO:
         self.coupleJ = complex(ham.coupleJ[0][0])
         self.nsite = mpo.nsite
         self.calc_point: list[list[DeviceTerm]] = []
+        ids = {}      # (key, site) -> (l_id, r_id)
+        self.bond_ids: dict = {}   # (key, bond b between sites b-1 and b) -> (prefix channel, suffix channel)
+        for key, cores in mpo.operators.items():
+            sites = [ind[0] if isinstance(ind, tuple) else int(ind) for ind in key]
+            if any(isinstance(c, int) for c in cores):
+                continue
+            pre, suf = identity_channels([np.asarray(c) for c in cores])
+            for k, s in enumerate(sites):
+                ids[(key, s)] = (pre[k], suf[k])
+                if k > 0 and sites[k - 1] == s - 1:
+                    self.bond_ids[(key, s)] = (pre[k], suf[k - 1])
         for cores in mpo.calc_point:
             terms = []
             for c in cores:
@@ -78,7 +126,9 @@ class DeviceMPO:
                     raise NotImplementedError(
                         f"MPO key {c.key} skips site {c.psite}: identity gap cores fail in the reference's H_eff apply "
                         "as well (pytdscf/_contraction.py:1067); give full-length cores instead")
-                terms.append(DeviceTerm(c.key, eng.upload_core(c.data), c.is_left_side, c.is_right_side))
+                dc = eng.upload_core(c.data)
+                dc.l_id, dc.r_id = ids.get((c.key, c.psite), (-1, -1))
+                terms.append(DeviceTerm(c.key, dc, c.is_left_side, c.is_right_side))
             self.calc_point.append(terms)
 
 
@@ -217,10 +267,15 @@ class MPSCoefCuda:
         if "summed" in Rb:
             terms.append((Lo, None, Rb["summed"], 1.0))
         for term in H.calc_point[psite + self.site_offset]:
-            terms.append((Lb.get(term.key, Lo), term.core, Rb.get(term.key, Ro), 1.0))
+            core = term.core
+            # the identity-channel promise holds only while the overlap blocks themselves are identities (canonical MPS)
+            if (core.l_id >= 0 and Lo is not None) or (core.r_id >= 0 and Ro is not None):
+                core = dataclasses.replace(core, l_id=core.l_id if Lo is None else -1, r_id=core.r_id if Ro is None else -1)
+            terms.append((Lb.get(term.key, Lo), core, Rb.get(term.key, Ro), 1.0))
         return terms
 
-    def operators_for_superK(self, op_sys: dict, op_env: dict, H: DeviceMPO, A_is_sys: bool) -> list:
+    def operators_for_superK(self, op_sys: dict, op_env: dict, H: DeviceMPO, A_is_sys: bool, bond: int | None = None) -> list:
+        """``bond`` = local index b of the bond between sites b-1 and b (enables the identity-channel shortcut)."""
         Lb, Rb = (op_sys, op_env) if A_is_sys else (op_env, op_sys)
         Lo, Ro = self._ovlp(Lb), self._ovlp(Rb)
         terms = []
@@ -234,7 +289,10 @@ class MPSCoefCuda:
             if key in ("summed", "ovlp"):
                 continue
             assert key in Lb and key in Rb, f"key {key} should be included in summed"
-            terms.append((Lb[key], Rb[key], 1.0))
+            ids = None
+            if bond is not None and Lo is None and Ro is None:
+                ids = getattr(H, "bond_ids", {}).get((key, bond + self.site_offset))
+            terms.append((Lb[key], Rb[key], 1.0, ids))
         return terms
 
     # -- local exponentials ----------------------------------------------------------------------
@@ -292,7 +350,7 @@ class MPSCoefCuda:
             new_site, sigma = eng.qr_shift(gauge, psi)
             sites[p] = SiteCoef(new_site, gauge, p)
             op_sys = self.renormalize_op_psite(p, op_sys, H, A_is_sys)
-            kterms = self.operators_for_superK(op_sys, op_env, H, A_is_sys)
+            kterms = self.operators_for_superK(op_sys, op_env, H, A_is_sys, bond=p + 1 if A_is_sys else p)
             sigma = self._expm(cfg, +1.0j, dt, sigma, p, 1, kterms=kterms)
             q = p + step
             sites[q] = SiteCoef(eng.absorb(gauge, sigma, sites[q].data), "Psi", q)

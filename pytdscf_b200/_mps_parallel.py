@@ -414,7 +414,7 @@ class MPSCoefParallelCuda(MPSCoefCuda):
         A_data, sigma = eng.qr_shift("A", pair[0].data, regularize=True)
         pair[0] = SiteCoef(A_data, "A", n - 1)
         op_sys = self.renormalize_op_psite(n - 1, op_sys_previous, H, True, site=pair[0])
-        kterms = self.operators_for_superK(op_sys, op_env, H, True)
+        kterms = self.operators_for_superK(op_sys, op_env, H, True, bond=n)
         sigma = self._expm(cfg, +1.0j, dt, sigma, key, 1, kterms=kterms)
         # half step on Psi_R
         pair[1] = SiteCoef(eng.absorb("A", sigma, pair[1].data), "Psi", n)
@@ -423,7 +423,7 @@ class MPSCoefParallelCuda(MPSCoefCuda):
         B_data, sigma = eng.qr_shift("B", pair[1].data)
         pair[1] = SiteCoef(B_data, "B", n)
         op_env = self.renormalize_op_psite(n, op_env_previous, H, False, site=pair[1])
-        kterms = self.operators_for_superK(op_sys, op_env, H, True)
+        kterms = self.operators_for_superK(op_sys, op_env, H, True, bond=n)
         sigma = self._expm(cfg, +1.0j, dt, sigma, key, 1, kterms=kterms)
         # truncate_sigvec(A, sigma, B, p_svd, regularize=True, keepdim=True)
         U, S, Vh, _rank = eng.svd_truncate(sigma, P_SVD, keepdim=True, regularize=True)
@@ -561,7 +561,7 @@ class MPSCoefParallelCuda(MPSCoefCuda):
         if rank == mid - 1:
             right = c.recv(rank + 1)
             sig = self.joint_sigvec_not_pinv
-            kterms = self.operators_for_superK(blockA, right, H, True)
+            kterms = self.operators_for_superK(blockA, right, H, True, bond=self.nsite)
             val = self.eng.inner(sig, self.eng.keff_apply(kterms, sig), True)
             if rank != 0:
                 c.send({"v": (val.real, val.imag)}, 0)

@@ -101,6 +101,21 @@ __global__ void axpby_kernel(const c128* __restrict__ x, c128* __restrict__ y, l
   }
 }
 
+// y[r, c] = alpha * x[r, c] + beta * y[r, c] on row-strided 2-D views (cols contiguous)
+__global__ void axpby2d_kernel(const c128* __restrict__ x, long long ldx, c128* __restrict__ y, long long ldy, long long rows,
+                               int cols, c128 alpha, c128 beta) {
+  const bool use_beta = beta.x != 0.0 || beta.y != 0.0;
+  const long long tot = rows * cols;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / cols;
+    const int c = (int)(e % cols);
+    c128 o = cmul(alpha, x[r * ldx + c]);
+    c128* p = y + r * ldy + c;
+    if (use_beta) o = cadd(o, cmul(beta, *p));
+    *p = o;
+  }
+}
+
 inline int grid_for(long long n, int threads, int cap = 148 * 8) {
   long long b = (n + threads - 1) / threads;
   if (b < 1) b = 1;
@@ -119,6 +134,56 @@ int gemm(Handle* h, const GemmDesc& g) {
   cudaError_t e = zgemm_auto(g, h->stream, h->d_splitk, SPLITK_SCRATCH_ELEMS);
   if (e != cudaSuccess) return cuda_fail(h, e, "zgemm_launch", __FILE__, __LINE__);
   return 0;
+}
+
+int axpby2d(Handle* h, const c128* x, long long ldx, c128* y, long long ldy, long long rows, int cols, c128 alpha, c128 beta) {
+  { ProfScope _ps(h->stream, "aux.axpby2d_kernel"); axpby2d_kernel<<<grid_for(rows * cols, 256), 256, 0, h->stream>>>(x, ldx, y, ldy, rows, cols, alpha, beta); }
+  return launch_check(h, "axpby2d_kernel");
+}
+
+// Identity-channel shortcuts pay only when the skipped GEMM slice is worth more than the extra copy / add launch.
+constexpr long long ID_CHANNEL_MIN_ELEMS = 1ll << 17;
+
+// C[(a, c), n] = sum_b L[(a, c), b] X[b, n] for every MPO channel c except `skip` (two-level rows: a outer with the
+// full stride, c inner over the remaining channels), and C[(a, skip), :] = X[a, :]  (L[:, skip, :] is the identity).
+int left_apply_skip(Handle* h, const c128* L, int D, int w, int skip, const c128* X, long long ncols, c128* C, const char* tag) {
+  int rc = 0;
+  for (int part = 0; part < 2; ++part) {
+    const int c0 = part == 0 ? 0 : skip + 1, c1 = part == 0 ? skip : w;
+    if (c1 <= c0) continue;
+    GemmDesc g;
+    g.M = D * (c1 - c0); g.N = (int)ncols; g.K = D;
+    g.A = L + (long long)c0 * D; g.a_m_inner = c1 - c0; g.a_m1 = (long long)w * D; g.a_m0 = D; g.a_k = 1;
+    g.B = X; g.b_n_inner = 1; g.b_n1 = 1; g.b_n0 = 0; g.b_k = ncols;
+    g.C = C + (long long)c0 * ncols; g.c_m_inner = c1 - c0; g.c_m1 = (long long)w * ncols; g.c_m0 = ncols; g.c_n = 1;
+    g.tag = tag;
+    if ((rc = gemm(h, g))) return rc;
+  }
+  { ProfScope _ps(h->stream, "aux.id_channel_copy");
+    cudaError_t e = cudaMemcpy2DAsync(C + (long long)skip * ncols, sizeof(c128) * (size_t)w * ncols, X, sizeof(c128) * (size_t)ncols,
+                                      sizeof(c128) * (size_t)ncols, (size_t)D, cudaMemcpyDeviceToDevice, h->stream);
+    if (e != cudaSuccess) return cuda_fail(h, e, "cudaMemcpy2DAsync(id channel)", __FILE__, __LINE__); }
+  ++g_launch_count;
+  return 0;
+}
+
+// out[m, r] = coef * sum_{(t, s), t != skip} T[m, (t, s)] R[r, (t, s)] + coef * T[m, skip, r] + beta * out[m, r]
+// (R[:, skip, :] is the identity); T rows have w * Dr entries.
+int right_apply_skip(Handle* h, const c128* T, long long rows, int Dr, int w, int skip, const c128* R, c128* out, c128 coef,
+                     c128 beta_out, const char* tag) {
+  int rc = 0;
+  c128 beta = beta_out;
+  const c128 one = {1.0, 0.0};
+  for (int part = 0; part < 2; ++part) {
+    const int t0 = part == 0 ? 0 : skip + 1, t1 = part == 0 ? skip : w;
+    if (t1 <= t0) continue;
+    GemmDesc g = gemm_rowmajor((int)rows, Dr, (t1 - t0) * Dr, T + (long long)t0 * Dr, (long long)w * Dr, false, false,
+                               R + (long long)t0 * Dr, (long long)w * Dr, true, out, Dr, coef, beta);
+    g.tag = tag;
+    if ((rc = gemm(h, g))) return rc;
+    beta = one;
+  }
+  return axpby2d(h, T + (long long)skip * Dr, (long long)w * Dr, out, Dr, rows, Dr, coef, beta);
 }
 
 int axpby(Handle* h, const c128* x, c128* y, long long n, c128 alpha, c128 beta) {
@@ -196,6 +261,10 @@ int heff_term_exec(Handle* h, const tdvp_heff_term& t, int Dl, int d, int Dr, co
   }
   const size_t top = h->ws_top;
   const long long N = (long long)Dl * d * Dr;
+  // identity channels promised by the caller (see tdvp_heff_term::id_channels); ignored for small tensors
+  int l_id = (t.id_channels & 0xffff) - 1, r_id = ((t.id_channels >> 16) & 0xffff) - 1;
+  if (N < ID_CHANNEL_MIN_ELEMS || !L || wl < 2 || l_id >= wl) l_id = -1;
+  if (N < ID_CHANNEL_MIN_ELEMS || !R || wr < 2 || r_id >= wr) r_id = -1;
   // algorithmic flops
   double fl = 0.0;
   if (L) fl += 8.0 * Dl * (double)Dl * Dr * d * wl;
@@ -210,10 +279,14 @@ int heff_term_exec(Handle* h, const tdvp_heff_term& t, int Dl, int d, int Dr, co
     const bool last = !W && !R;
     c128* dst = last ? out : (c128*)ws_alloc(h, sizeof(c128) * (size_t)Dl * wl * d * Dr);
     if (!dst) { set_error(h, "workspace exhausted (heff T1)"); return TDVP_ERR_ARG; }
-    GemmDesc g = gemm_rowmajor(Dl * wl, d * Dr, Dl, L, Dl, false, false, cur, (long long)d * Dr, false, dst,
-                               (long long)d * Dr, last ? coef : one, last ? beta_out : zero);
-    g.tag = "heff.s1";
-    if ((rc = gemm(h, g))) return rc;
+    if (l_id >= 0 && !last) {
+      if ((rc = left_apply_skip(h, L, Dl, wl, l_id, cur, (long long)d * Dr, dst, "heff.s1"))) return rc;
+    } else {
+      GemmDesc g = gemm_rowmajor(Dl * wl, d * Dr, Dl, L, Dl, false, false, cur, (long long)d * Dr, false, dst,
+                                 (long long)d * Dr, last ? coef : one, last ? beta_out : zero);
+      g.tag = "heff.s1";
+      if ((rc = gemm(h, g))) return rc;
+    }
     cur = dst;
   }
   // ---- stage 2 ----
@@ -239,10 +312,14 @@ int heff_term_exec(Handle* h, const tdvp_heff_term& t, int Dl, int d, int Dr, co
   }
   // ---- stage 3 ----
   if (R) {
-    GemmDesc g = gemm_rowmajor(Dl * d, Dr, wr * Dr, cur, (long long)wr * Dr, false, false, R, (long long)wr * Dr, true,
-                               out, Dr, coef, beta_out);
-    g.tag = "heff.s3";
-    if ((rc = gemm(h, g))) return rc;
+    if (r_id >= 0 && cur != psi) {
+      if ((rc = right_apply_skip(h, cur, (long long)Dl * d, Dr, wr, r_id, R, out, coef, beta_out, "heff.s3"))) return rc;
+    } else {
+      GemmDesc g = gemm_rowmajor(Dl * d, Dr, wr * Dr, cur, (long long)wr * Dr, false, false, R, (long long)wr * Dr, true,
+                                 out, Dr, coef, beta_out);
+      g.tag = "heff.s3";
+      if ((rc = gemm(h, g))) return rc;
+    }
   } else if (!L && !W) {
     if ((rc = axpby(h, psi, out, N, coef, beta_out))) return rc;
   }
@@ -269,12 +346,24 @@ int keff_term_exec(Handle* h, const tdvp_keff_term& t, int Dl, int Dr, const c12
     h->heff_flops += 8.0 * w * ((double)Dl * Dl * Dr + (double)Dl * Dr * Dr);
     c128* T = (c128*)ws_alloc(h, sizeof(c128) * (size_t)Dl * w * Dr);
     if (!T) { set_error(h, "workspace exhausted (keff T)"); return TDVP_ERR_ARG; }
-    GemmDesc g1 = gemm_rowmajor(Dl * w, Dr, Dl, L, Dl, false, false, sigma, Dr, false, T, Dr);
-    g1.tag = "keff.g1";
-    if ((rc = gemm(h, g1))) return rc;
-    GemmDesc g2 = gemm_rowmajor(Dl, Dr, w * Dr, T, (long long)w * Dr, false, false, R, (long long)w * Dr, true, out, Dr, coef, beta_out);
-    g2.tag = "keff.g2";
-    if ((rc = gemm(h, g2))) return rc;
+    int l_id = (t.id_channels & 0xffff) - 1, r_id = ((t.id_channels >> 16) & 0xffff) - 1;
+    const bool big = (long long)Dl * Dr * w >= ID_CHANNEL_MIN_ELEMS && w >= 2;
+    if (!big || l_id >= w) l_id = -1;
+    if (!big || r_id >= w) r_id = -1;
+    if (l_id >= 0) {
+      if ((rc = left_apply_skip(h, L, Dl, w, l_id, sigma, Dr, T, "keff.g1"))) return rc;
+    } else {
+      GemmDesc g1 = gemm_rowmajor(Dl * w, Dr, Dl, L, Dl, false, false, sigma, Dr, false, T, Dr);
+      g1.tag = "keff.g1";
+      if ((rc = gemm(h, g1))) return rc;
+    }
+    if (r_id >= 0) {
+      if ((rc = right_apply_skip(h, T, Dl, Dr, w, r_id, R, out, coef, beta_out, "keff.g2"))) return rc;
+    } else {
+      GemmDesc g2 = gemm_rowmajor(Dl, Dr, w * Dr, T, (long long)w * Dr, false, false, R, (long long)w * Dr, true, out, Dr, coef, beta_out);
+      g2.tag = "keff.g2";
+      if ((rc = gemm(h, g2))) return rc;
+    }
   } else if (L || R) {
     if (w != 1) {
       set_error(h, "keff term: one-sided term requires w == 1");

@@ -45,7 +45,7 @@ class CheckedEngine:
 
     def keff_apply(self, terms, sigma):
         out = self.eng.keff_apply(terms, sigma)
-        ref = self.orc.keff_apply([(_c(L), _c(R), k) for L, R, k in terms], _c(sigma))
+        ref = self.orc.keff_apply([(_c(t[0]), _c(t[1]), t[2]) for t in terms], _c(sigma))
         self._rec("keff_apply", (out.cpu() - ref).abs().max() / max(1e-300, ref.abs().max()), tuple(sigma.shape))
         return out
 
@@ -65,7 +65,7 @@ class CheckedEngine:
         if hterms is not None:
             kw["hterms"] = [(_c(L), _core(c), _c(R), k) for L, c, R, k in hterms]
         else:
-            kw["kterms"] = [(_c(L), _c(R), k) for L, R, k in kterms]
+            kw["kterms"] = [(_c(t[0]), _c(t[1]), t[2]) for t in kterms]
         n_ref = self.orc.krylov_expm(kind, scale, thresh, n_warmup, conserve_norm, x0, **kw)
         self._rec("krylov_expm", (psi.cpu() - x0).abs().max() / max(1e-300, x0.abs().max()), (tuple(psi.shape), n, n_ref))
         self._rec("krylov_niter", abs(n - n_ref), (tuple(psi.shape), n, n_ref))

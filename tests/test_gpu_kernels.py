@@ -381,3 +381,48 @@ def test_svd_and_qr_denormal_directions(eng):
     A, sig = eng.qr_shift("A", eng.to_device(np.ascontiguousarray(psi.transpose(2, 1, 0))))
     Am = A.cpu().numpy().reshape(24, 6)
     np.testing.assert_allclose(Am.conj().T @ Am, np.eye(6), atol=1e-13)
+
+
+@pytest.mark.parametrize("diag", [False, True])
+@pytest.mark.parametrize("l_id,r_id", [(0, 2), (1, 0), (2, 1), (-1, 1), (0, -1)])
+def test_heff_identity_channel_shortcut(eng, l_id, r_id, diag):
+    """id_channels: the flagged channel of L / R is an exact unit block; the shortcut (copy instead of GEMM slice,
+    two-level row GEMMs for the other channels) must equal the full contraction."""
+    import dataclasses
+
+    rng = np.random.default_rng(100 + 10 * l_id + r_id + diag)
+    Dl, d, Dr, wl, wr = 96, 16, 96, 3, 3          # N = 147456 >= the 2^17 threshold of the shortcut
+    psi = crand(rng, Dl, d, Dr)
+    L, R = crand(rng, Dl, wl, Dl), crand(rng, Dr, wr, Dr)
+    if l_id >= 0:
+        L[:, l_id, :] = np.eye(Dl)
+    if r_id >= 0:
+        R[:, r_id, :] = np.eye(Dr)
+    W = crand(rng, wl, d, wr) if diag else crand(rng, wl, d, d, wr)
+    ref = orc.heff_term(L, core_of(W), R, psi)
+    core = dataclasses.replace(eng.upload_core(W), l_id=l_id, r_id=r_id)
+    base = eng.stats()["launches"]
+    out = eng.heff_apply([(eng.to_device(L), core, eng.to_device(R), 0.7 - 0.2j)], eng.to_device(psi))
+    assert relerr(out.cpu().numpy(), (0.7 - 0.2j) * ref) < 1e-12
+    # accumulation into an existing output (second term) goes through the same path
+    out2 = eng.heff_apply([(eng.to_device(L), eng.upload_core(W), eng.to_device(R), 1.0), (eng.to_device(L), core, eng.to_device(R), 1.0)],
+                          eng.to_device(psi))
+    assert relerr(out2.cpu().numpy(), 2 * ref) < 1e-12
+    assert eng.stats()["launches"] > base
+
+
+@pytest.mark.parametrize("l_id,r_id", [(0, 3), (3, 0), (1, 2), (-1, 2), (1, -1)])
+def test_keff_identity_channel_shortcut(eng, l_id, r_id):
+    rng = np.random.default_rng(200 + 10 * l_id + r_id)
+    D, w = 192, 4                                  # D * D * w = 147456
+    sig = crand(rng, D, D)
+    L, R = crand(rng, D, w, D), crand(rng, D, w, D)
+    if l_id >= 0:
+        L[:, l_id, :] = np.eye(D)
+    if r_id >= 0:
+        R[:, r_id, :] = np.eye(D)
+    ref = orc.keff_term(L, R, sig)
+    out = eng.keff_apply([(eng.to_device(L), eng.to_device(R), 1.0, (l_id, r_id))], eng.to_device(sig))
+    assert relerr(out.cpu().numpy(), ref) < 1e-12
+    out = eng.keff_apply([(eng.to_device(L), eng.to_device(R), 0.5j), (eng.to_device(L), eng.to_device(R), 1.0, (l_id, r_id))], eng.to_device(sig))
+    assert relerr(out.cpu().numpy(), (1 + 0.5j) * ref) < 1e-12

@@ -160,3 +160,44 @@ def test_simulator_reduced_density_argument(tmp_path):
     assert abs(np.trace(rho[(3, 3)]) - 1.0) < 1e-12 and abs(rho[(0,)].sum() - 1.0) < 1e-12
     z = np.load(os.path.join("rd_cpu_prop", "reduced_density.npz"))
     assert z["rho_3_3"].shape == (2, 2, 2) and len(z["time_au"]) == 2
+
+
+@pytest.mark.parametrize("name", ["exciton_D6", "henon_heiles_f6", "h2co_D16", "liouville_spin3"])
+def test_identity_channel_analysis_matches_the_environments(name):
+    """``identity_channels`` (MPO structure only) must name exactly channels whose environment block, contracted the
+    reference's way from canonical tensors, IS the unit matrix -- that is what lets H_eff / K_eff copy instead of multiply."""
+    from pytdscf_b200._mps_cuda import DeviceMPO, MPSCoefCuda
+
+    g = load_run(name)
+    eng = OracleEngine()
+    model = _build_model(g)
+    H = DeviceMPO(eng, model.hamiltonian)
+    mps = MPSCoefCuda(eng, [eng.to_device(c) for c in g["final"]])      # Psi B B ... B
+    n = mps.nsite
+    right = mps.construct_op_sites(n - 1, 0, H)                             # right[k]: block right of site n-1-k ... built from B
+    found = 0
+    for p in range(n - 1):
+        blocks = right[n - 1 - p]                                           # environment of site p (sites p+1 .. n-1)
+        for term in H.calc_point[p]:
+            if term.core.r_id >= 0 and term.key in blocks:
+                E = blocks[term.key].numpy()
+                np.testing.assert_allclose(E[:, term.core.r_id, :], np.eye(E.shape[0]), atol=1e-12)
+                found += 1
+    # left blocks from A tensors: shift the centre to the right end first
+    cfg_sites = [s.data for s in mps.sites]
+    for i in range(n - 1):
+        A, sig = eng.qr_shift("A", cfg_sites[i])
+        cfg_sites[i] = A
+        cfg_sites[i + 1] = eng.absorb("A", sig, cfg_sites[i + 1])
+    mpsA = MPSCoefCuda(eng, cfg_sites, ["A"] * (n - 1) + ["Psi"])
+    left = mpsA.construct_op_sites(0, n - 1, H)                             # left[p]: block of sites 0 .. p-1
+    for p in range(1, n):
+        for term in H.calc_point[p]:
+            if term.core.l_id >= 0 and term.key in left[p]:
+                E = left[p][term.key].numpy()
+                np.testing.assert_allclose(E[:, term.core.l_id, :], np.eye(E.shape[0]), atol=1e-12)
+                found += 1
+        for (key, b), (lid, rid) in H.bond_ids.items():
+            if b == p and key in left[p] and lid >= 0:
+                np.testing.assert_allclose(left[p][key].numpy()[:, lid, :], np.eye(left[p][key].shape[0]), atol=1e-12)
+    assert found > 0, "no identity channel detected in an MPO that has prefix/suffix channels"
