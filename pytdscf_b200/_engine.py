@@ -67,6 +67,7 @@ class Engine:
             raise _lib.TdvpError(rc, "tdvp_create failed")
         self.h = h
         self._keep: list = []  # tensors referenced by descriptors of the call in flight
+        self.reorder_mpo_channels = True  # DeviceMPO puts identity-prefix / -suffix channels first / last (see id_channels)
 
     def close(self):
         if getattr(self, "h", None):

@@ -162,16 +162,25 @@ def test_simulator_reduced_density_argument(tmp_path):
     assert z["rho_3_3"].shape == (2, 2, 2) and len(z["time_au"]) == 2
 
 
+@pytest.mark.parametrize("reorder", [False, True])
 @pytest.mark.parametrize("name", ["exciton_D6", "henon_heiles_f6", "h2co_D16", "liouville_spin3"])
-def test_identity_channel_analysis_matches_the_environments(name):
+def test_identity_channel_analysis_matches_the_environments(name, reorder):
     """``identity_channels`` (MPO structure only) must name exactly channels whose environment block, contracted the
     reference's way from canonical tensors, IS the unit matrix -- that is what lets H_eff / K_eff copy instead of multiply."""
     from pytdscf_b200._mps_cuda import DeviceMPO, MPSCoefCuda
 
     g = load_run(name)
     eng = OracleEngine()
+    eng.reorder_mpo_channels = reorder
     model = _build_model(g)
     H = DeviceMPO(eng, model.hamiltonian)
+    if reorder:   # flagged channels sit at the ends of the bond, and the operator is unchanged
+        for terms in H.calc_point:
+            for term in terms:
+                assert term.core.l_id in (-1, 0) and term.core.r_id in (-1, term.core.wr - 1)
+        H0 = DeviceMPO(OracleEngine(), model.hamiltonian)
+        m0 = MPSCoefCuda(eng, [eng.to_device(c) for c in g["final"]])
+        assert abs(m0.expectation(H) - m0.expectation(H0)) < 1e-13 * max(1.0, abs(m0.expectation(H0)))
     mps = MPSCoefCuda(eng, [eng.to_device(c) for c in g["final"]])      # Psi B B ... B
     n = mps.nsite
     right = mps.construct_op_sites(n - 1, 0, H)                             # right[k]: block right of site n-1-k ... built from B
