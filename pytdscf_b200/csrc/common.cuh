@@ -64,6 +64,7 @@ struct GemmDesc {
   int splitk = 1;
   int k_chunk = 0;
   long long c_split = 0;
+  int c_stream = 0;   // set by the launcher: outputs larger than half of L2 are stored with evict-first (st.global.cs)
 };
 
 // Launch the DMMA ZGEMM on `stream`.  Returns cudaGetLastError() of the launch.

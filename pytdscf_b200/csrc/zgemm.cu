@@ -217,7 +217,20 @@ __global__ void __launch_bounds__(C::THREADS, C::THREADS == 256 ? 1 : 4) zgemm_d
   const int warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, q = lane & 3;
   const int wm = warp % C::WMW, wn = warp / C::WMW;
-  const int tile_m = blockIdx.y * BM, tile_n = blockIdx.x * BN;
+  // Grouped rasterisation: consecutive CTAs walk 16 M-tiles for one N-tile before moving to the next N-tile, so a wave of
+  // 148 CTAs works on a 16 x ~9 block of tiles (A rows stay in L2 for the whole group, B columns are read once per
+  // group) instead of ~2 full tile rows that stream all of B through L2 every wave.
+  int tile_m, tile_n;
+  {
+    constexpr int GROUP_M = 16;
+    const int npm = gridDim.y, npn = gridDim.x;
+    const int pid = blockIdx.y * npn + blockIdx.x;
+    const int in_group = GROUP_M * npn;
+    const int first_m = (pid / in_group) * GROUP_M;
+    const int gsz = (npm - first_m) < GROUP_M ? (npm - first_m) : GROUP_M;
+    tile_m = (first_m + (pid % in_group) % gsz) * BM;
+    tile_n = ((pid % in_group) / gsz) * BN;
+  }
   const long long bz = blockIdx.z / d.splitk;
   const int split = blockIdx.z % d.splitk;
   const int k_begin = split * d.k_chunk;                       // k_chunk is a multiple of BK (or covers all of K)
@@ -323,7 +336,8 @@ __global__ void __launch_bounds__(C::THREADS, C::THREADS == 256 ? 1 : 4) zgemm_d
         c128 acc = {cre[i][j][e], cim[i][j][e]};
         c128 out = cmul(alpha, acc);
         if (use_beta) out = cadd(out, cmul(beta, *p));
-        *p = out;
+        if (d.c_stream) __stcs(reinterpret_cast<double2*>(p), make_double2(out.x, out.y));
+        else *p = out;
       }
     }
   }
@@ -365,8 +379,10 @@ inline bool use_tiny(const GemmDesc& d) { return tiles_of(d, SmallCfg::BM, Small
 
 }  // namespace
 
-cudaError_t zgemm_launch(const GemmDesc& d, cudaStream_t stream) {
-  if (d.M <= 0 || d.N <= 0 || d.batch <= 0) return cudaSuccess;
+cudaError_t zgemm_launch(const GemmDesc& d0, cudaStream_t stream) {
+  if (d0.M <= 0 || d0.N <= 0 || d0.batch <= 0) return cudaSuccess;
+  GemmDesc d = d0;
+  d.c_stream = (d.splitk == 1 && (double)d.M * d.N * d.batch * 16.0 > 64.0e6) ? 1 : 0;
   if (use_tiny(d)) return launch_cfg<TinyCfg>(d, stream);
   return use_small(d) ? launch_cfg<SmallCfg>(d, stream) : launch_cfg<BigCfg>(d, stream);
 }
