@@ -159,6 +159,71 @@ def bond_dims(dims: list[int], isite: int, m: int) -> tuple[int, int]:
     return min(dim_left, dc * dim_right, m), min(dim_left * dc, dim_right, m)
 
 
+# ---------------------------------------------------------------------------------------------------------
+# canonicalisation helpers on device tensors (_mps_cls.py:3470-3630)
+# ---------------------------------------------------------------------------------------------------------
+def canonicalizeA(eng, sb: list):
+    sval = None
+    for i, coef in enumerate(sb):
+        if sval is not None:
+            coef.data = eng.absorb("A", sval, coef.data)
+        coef.gauge = "Psi"
+        if i != len(sb) - 1:
+            coef.data, sval = eng.qr_shift("A", coef.data)
+            coef.gauge = "A"
+
+
+def canonicalizeB(eng, sb: list):
+    sval = None
+    for i, coef in enumerate(sb[::-1]):
+        if sval is not None:
+            coef.data = eng.absorb("B", sval, coef.data)
+        coef.gauge = "Psi"
+        if i != len(sb) - 1:
+            coef.data, sval = eng.qr_shift("B", coef.data)
+            coef.gauge = "B"
+
+
+def cc2_a_lambda_b(eng, left: SiteCoef, right: SiteCoef) -> np.ndarray:
+    """SVD of the two-site tensor: left <- U (gauge A), right <- Vh (gauge B); returns the singular values (host)."""
+    a, b, c = left.data.shape
+    _, d, e = right.data.shape
+    two = eng.zgemm(left.data.reshape(a * b, c).contiguous(), right.data.reshape(c, d * e).contiguous())
+    U, lam, Vh = eng.svd(two)
+    left.data = U[:, :c].contiguous().reshape(a, b, c)
+    left.gauge = "A"
+    right.data = Vh[:c, :].contiguous().reshape(c, d, e)
+    right.gauge = "B"
+    return np.asarray(lam[:c])
+
+
+def canonicalize(eng, sb: list, center: int, incremental: bool = False):
+    n = len(sb)
+    if n == 1:
+        return
+    if incremental:
+        cur = [i for i, s in enumerate(sb) if s.gauge == "Psi"]
+        if len(cur) != 1:
+            raise ValueError("canonicalize(incremental): exactly one Psi site expected")
+        cur = cur[0]
+        if cur == center:
+            return
+        if cur < center:
+            canonicalizeA(eng, sb[cur:center + 1])
+        else:
+            canonicalizeB(eng, sb[center:cur + 1])
+        return
+    canonicalizeB(eng, sb[center:])
+    if center == 0:
+        return
+    canonicalizeA(eng, sb[:center])
+    lam = cc2_a_lambda_b(eng, sb[center - 1], sb[center])
+    lam_t = torch.as_tensor(lam, dtype=torch.float64, device=sb[center].data.device)
+    sb[center].data = (lam_t[:, None, None] * sb[center].data).contiguous()
+    sb[center].gauge = "Psi"
+
+
+
 class MPSCoefCuda:
     """Device-resident MPS in mixed-canonical form with the orthogonality centre at site 0 between steps."""
 
@@ -375,11 +440,38 @@ class MPSCoefCuda:
             self.op_sys_sites.append(op_sys)
         return op_sys
 
-    def propagate(self, stepsize: float, H: DeviceMPO, cfg):
-        """One time step: forward and backward half sweeps (the last site gets two consecutive half steps)."""
+    def propagate(self, stepsize: float, H: DeviceMPO, cfg, one_gate: DeviceMPO | None = None):
+        """One time step: forward and backward half sweeps (the last site gets two consecutive half steps); one-site
+        gates, if any, act between the two (reference ``_mps_cls.py:452-503``)."""
         n = self.nsite
         self.propagate_along_sweep(H, stepsize, cfg, begin_site=0, end_site=n - 1)
+        if one_gate is not None:
+            self.apply_one_gate(one_gate, reorth_center=n - 1)
         self.propagate_along_sweep(H, stepsize, cfg, begin_site=n - 1, end_site=0)
+
+    def apply_one_gate(self, gate: DeviceMPO, reorth_center: int):
+        """U_p on the physical leg of every site that has a gate core, then re-canonicalise around ``reorth_center`` and
+        drop the cached environments (reference ``apply_one_gate`` / ``_apply_one_gate_isite``, _mps_cls.py:2314-2451).
+        The contraction new[a,i,c] = sum_j U[i,j] old[a,j,c] is stage 2 of the H_eff chain with a (1, d, d, 1) core."""
+        sb = self.sites
+        changed = []
+        for isite in range(self.nsite):
+            terms = gate.calc_point[isite + self.site_offset]
+            if not terms:
+                continue
+            if len(terms) >= 2:
+                raise ValueError("Multiple one gate on same site is not supported. Contract gates in advance!")
+            core = terms[0].core
+            if core.wl != 1 or core.wr != 1:
+                raise ValueError("one-site gates must be (1, d, d, 1) or (1, d, 1) cores")
+            sb[isite].data = self.eng.heff_apply([(None, core, None, 1.0)], sb[isite].data)
+            if sb[isite].gauge != "Psi":
+                sb[isite].gauge = "C"
+                changed.append(isite)
+        if changed:
+            canonicalizeB(self.eng, sb[reorth_center: max(changed) + 1])
+            canonicalizeA(self.eng, sb[min(changed): reorth_center + 1])
+            self.op_sys_sites = None
 
     # -- observables ---------------------------------------------------------------------------------
     def expectation(self, H: DeviceMPO) -> complex:

@@ -23,7 +23,8 @@ import math
 import numpy as np
 import torch
 
-from ._mps_cuda import Block, DeviceMPO, MPSCoefCuda, SiteCoef
+from ._mps_cuda import (Block, DeviceMPO, MPSCoefCuda, SiteCoef, canonicalize, canonicalizeA, canonicalizeB,  # noqa: F401
+                        cc2_a_lambda_b)
 
 RCOND = 1e-13        # _site_cls.py:24
 P_SVD = 1.0e-07      # Simulator.propagate(adaptive_p_svd=...) default, used by the joint truncation
@@ -131,70 +132,6 @@ class Comm:
 
 def _clone_sites(sites):
     return [SiteCoef(s.data.clone(), s.gauge, s.isite) for s in sites]
-
-
-# ---------------------------------------------------------------------------------------------------------
-# canonicalisation helpers on device tensors (_mps_cls.py:3470-3630)
-# ---------------------------------------------------------------------------------------------------------
-def canonicalizeA(eng, sb: list):
-    sval = None
-    for i, coef in enumerate(sb):
-        if sval is not None:
-            coef.data = eng.absorb("A", sval, coef.data)
-        coef.gauge = "Psi"
-        if i != len(sb) - 1:
-            coef.data, sval = eng.qr_shift("A", coef.data)
-            coef.gauge = "A"
-
-
-def canonicalizeB(eng, sb: list):
-    sval = None
-    for i, coef in enumerate(sb[::-1]):
-        if sval is not None:
-            coef.data = eng.absorb("B", sval, coef.data)
-        coef.gauge = "Psi"
-        if i != len(sb) - 1:
-            coef.data, sval = eng.qr_shift("B", coef.data)
-            coef.gauge = "B"
-
-
-def cc2_a_lambda_b(eng, left: SiteCoef, right: SiteCoef) -> np.ndarray:
-    """SVD of the two-site tensor: left <- U (gauge A), right <- Vh (gauge B); returns the singular values (host)."""
-    a, b, c = left.data.shape
-    _, d, e = right.data.shape
-    two = eng.zgemm(left.data.reshape(a * b, c).contiguous(), right.data.reshape(c, d * e).contiguous())
-    U, lam, Vh = eng.svd(two)
-    left.data = U[:, :c].contiguous().reshape(a, b, c)
-    left.gauge = "A"
-    right.data = Vh[:c, :].contiguous().reshape(c, d, e)
-    right.gauge = "B"
-    return np.asarray(lam[:c])
-
-
-def canonicalize(eng, sb: list, center: int, incremental: bool = False):
-    n = len(sb)
-    if n == 1:
-        return
-    if incremental:
-        cur = [i for i, s in enumerate(sb) if s.gauge == "Psi"]
-        if len(cur) != 1:
-            raise ValueError("canonicalize(incremental): exactly one Psi site expected")
-        cur = cur[0]
-        if cur == center:
-            return
-        if cur < center:
-            canonicalizeA(eng, sb[cur:center + 1])
-        else:
-            canonicalizeB(eng, sb[center:cur + 1])
-        return
-    canonicalizeB(eng, sb[center:])
-    if center == 0:
-        return
-    canonicalizeA(eng, sb[:center])
-    lam = cc2_a_lambda_b(eng, sb[center - 1], sb[center])
-    lam_t = torch.as_tensor(lam, dtype=torch.float64, device=sb[center].data.device)
-    sb[center].data = (lam_t[:, None, None] * sb[center].data).contiguous()
-    sb[center].gauge = "Psi"
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -55,8 +55,10 @@ class Model:
             raise TypeError("basinfo must be BasInfo instance or list.")
         if build_td_hamiltonian is not None:
             raise NotImplementedError("time-dependent Hamiltonians are not part of the MPO hot path")
-        if one_gate_to_apply is not None or kraus_op is not None:
-            raise NotImplementedError("gates / Kraus maps are a 'next' row (SURVEY 8(f3)); not in backend='cuda' yet")
+        if kraus_op is not None:
+            raise NotImplementedError("Kraus maps are a 'next' row (SURVEY 8(f3)); not in backend='cuda' yet")
+        if one_gate_to_apply is not None and not isinstance(one_gate_to_apply, TensorHamiltonian):
+            raise TypeError("one_gate_to_apply must be a TensorHamiltonian of one-site cores")
         if isinstance(operators, (TensorHamiltonian, list)):
             operators = {"hamiltonian": operators}
         ops = self.operators_to_tensor_hamiltonian(dict(operators))
@@ -78,7 +80,9 @@ class Model:
             for op in self.observables.values():
                 op.project_subspace(subspace_inds)
             self.hamiltonian.project_subspace(subspace_inds)
-        self.one_gate_to_apply = None
+        self.one_gate_to_apply = one_gate_to_apply
+        if one_gate_to_apply is not None and self.subspace_inds is not None:
+            one_gate_to_apply.project_subspace(self.subspace_inds)
         self.kraus_op = None
 
     # -- basis passthroughs ------------------------------------------------------------------------
@@ -146,6 +150,8 @@ class Model:
         self.hamiltonian.apply_backend(backend)
         for ob in self.observables.values():
             ob.apply_backend(backend)
+        if self.one_gate_to_apply is not None:
+            self.one_gate_to_apply.apply_backend(backend)
 
     # -- initial condition (reference: MPSCoef._get_initial_condition, _mps_cls.py:133-215) -----------
     def initial_core_weights(self) -> tuple[list, float, int]:

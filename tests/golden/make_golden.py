@@ -113,11 +113,30 @@ def _reset_reference_state():
     _Debug.site_now = 0
 
 
+def _skip(name):
+    only = os.environ.get("GOLDEN_ONLY")
+    return bool(only) and only not in name
+
+
 def run_reference(name, basis, operators, *, bond_dim, hartree, dt_fs, nstep, space="hilbert",
-                  integrator="lanczos", conserve_norm=True, vibstate=None, thresh_sil=1e-9, relax=None):
-    """Run Simulator.propagate and dump inputs + outputs to tests/golden/<name>.npz."""
+                  integrator="lanczos", conserve_norm=True, vibstate=None, thresh_sil=1e-9, relax=None, gates=None):
+    """Run Simulator.propagate and dump inputs + outputs to tests/golden/<name>.npz.
+    ``gates``: {site: d x d matrix or length-d diagonal} applied once per step between the half sweeps
+    (Model(one_gate_to_apply=...), pytdscf/_mps_cls.py:489-490, 2314-2373)."""
+    if _skip(name):
+        return
     _reset_reference_state()
-    model = Model(basis, operators, bond_dim=bond_dim, space=space)
+    gate_op = None
+    if gates:
+        pot = {}
+        for site, U in gates.items():
+            U = np.asarray(U, dtype=np.complex128)
+            if U.ndim == 1:
+                pot[(site,)] = TensorOperator(mpo=[U.reshape(1, -1, 1)], legs=(site,))
+            else:
+                pot[((site, site),)] = TensorOperator(mpo=[U.reshape(1, U.shape[0], U.shape[1], 1)], legs=(site, site))
+        gate_op = TensorHamiltonian(ndof=len(basis), potential=[[pot]], kinetic=None, backend="numpy")
+    model = Model(basis, operators, bond_dim=bond_dim, space=space, one_gate_to_apply=gate_op)
     if hartree is not None:
         model.init_HartreeProduct = [hartree]
     if vibstate is not None:
@@ -176,6 +195,8 @@ def run_reference(name, basis, operators, *, bond_dim, hartree, dt_fs, nstep, sp
     if hartree is not None:
         for i, h in enumerate(hartree):
             out[f"hartree{i}"] = np.asarray(h, dtype=np.complex128)
+    for site, U in (gates or {}).items():
+        out[f"gate{site}"] = np.asarray(U, dtype=np.complex128)
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
     print(f"[golden] {name}: E_final={ener!r} steps={nstep} solves={len(RECORD['trace'])}")
 
@@ -446,7 +467,8 @@ def kernel_fixtures():
 
 
 def main():
-    kernel_fixtures()
+    if not os.environ.get("GOLDEN_ONLY"):
+        kernel_fixtures()
     prim, ops, hartree = exciton_model()
     run_reference("exciton_D2", prim, ops, bond_dim=2, hartree=hartree, dt_fs=0.1, nstep=20)
     prim, ops, hartree = exciton_model()
@@ -461,6 +483,11 @@ def main():
     run_reference("relax_improved_hh4", prims, ops, bond_dim=6, hartree=None, vibstate=vib, dt_fs=0.1, nstep=4, relax="improved")
     prims, ops, vib = henon_heiles_model(2000, 1.0e-3, 4, 6)
     run_reference("relax_imag_hh4", prims, ops, bond_dim=6, hartree=None, vibstate=vib, dt_fs=0.5, nstep=4, relax="imag")
+    prim, ops, hartree = exciton_model()
+    th = 0.3
+    rot = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]], dtype=complex)   # kick on the exciton site
+    phase = np.exp(1j * 0.05 * np.arange(8))                                               # diagonal gate on mode 1
+    run_reference("gate_exciton_D6", prim, ops, bond_dim=6, hartree=hartree, dt_fs=0.1, nstep=5, gates={3: rot, 1: phase})
     basis, ops, hartree = liouville_model()
     run_reference("liouville_spin3", basis, ops, bond_dim=8, hartree=hartree, dt_fs=2.0, nstep=5,
                   space="liouville", integrator="arnoldi")

@@ -54,8 +54,59 @@ def run(name, eps, seed):
     return np.array(autos), np.array(ens), dense_state(o.mps), list(o.trace)
 
 
+def run_host(name, eps, seed):
+    """Gate runs: the oracle class has no gate support, so the product's host logic with the oracle's kernels is used
+    (it reproduces the reference run to 1e-13, tests/test_host_sweep_cpu.py)."""
+    import tempfile
+
+    import torch
+
+    import pytdscf_b200 as tb
+    from oracle.oracle_engine import OracleEngine
+    from tests.test_host_sweep_cpu import _build_model
+
+    g = load_run(name)
+    eng = OracleEngine()
+    if eps:
+        rng = np.random.default_rng(seed)
+        orig = eng.heff_apply
+
+        def noisy(terms, psi):
+            out = orig(terms, psi)
+            return out * torch.as_tensor(1 + eps * rng.standard_normal(tuple(out.shape)))
+
+        eng.heff_apply = noisy
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)
+        try:
+            sim = tb.Simulator(name, _build_model(g), backend="cuda", verbose=0)
+            sim.eng = eng
+            sim.set_initial_mps(g["init"])
+            ener, wf = sim.propagate(stepsize=g["dt_au"] * tb.units.au_in_fs, maxstep=g["nstep"], populations=False,
+                                     write_files=False, record_trace=True)
+        finally:
+            os.chdir(cwd)
+    return (np.array([r["autocorr"] for r in sim.history]), np.array([r["energy"] for r in sim.history]),
+            dense_state(wf.ci_coef.to_numpy()), list(wf.ci_coef.trace))
+
+
 def main():
+    from tests.golden_io import GATE_CASES
+
     out = {}
+    for name in GATE_CASES:
+        a0, e0, s0, t0 = run_host(name, 0.0, 0)
+        fa = fe = fs = 0.0
+        same_trace = True
+        for seed in range(5):
+            a1, e1, s1, t1 = run_host(name, 2e-16, seed)
+            fa = max(fa, float(np.abs(a1 - a0).max()))
+            fe = max(fe, float(np.abs((e1 - e0) / e0).max()))
+            fs = max(fs, float(np.abs(s1 - s0).max()))
+            same_trace &= t1 == t0
+        out[name] = {"autocorr_abs": fa, "energy_rel": fe, "state_abs": fs, "trace_stable": bool(same_trace)}
+        print(name, out[name])
     for name in RUN_CASES:
         a0, e0, s0, t0 = run(name, 0.0, 0)
         fa = fe = fs = 0.0

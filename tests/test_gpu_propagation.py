@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from oracle import tdvp_oracle as orc
-from tests.golden_io import RUN_CASES, load_run
+from tests.golden_io import GATE_CASES, RUN_CASES, load_run
 
 pytestmark = pytest.mark.gpu
 REL = 1e-10  # north-star tolerance (complex128)
@@ -57,7 +57,16 @@ def build_model(g):
     if g["coupleJ"] != 0:
         pot[()] = g["coupleJ"]
     ham = tb.TensorHamiltonian(ndof=len(basis), potential=[[pot]], backend="cuda")
-    return tb.Model(basis, {"hamiltonian": ham}, bond_dim=g["bond_dim"], space=g["space"])
+    gate = None
+    if g.get("gates"):
+        gp = {}
+        for site, U in g["gates"].items():
+            if U.ndim == 1:
+                gp[(site,)] = tb.TensorOperator(mpo=[U.reshape(1, -1, 1)], legs=(site,))
+            else:
+                gp[((site, site),)] = tb.TensorOperator(mpo=[U.reshape(1, U.shape[0], U.shape[1], 1)], legs=(site, site))
+        gate = tb.TensorHamiltonian(ndof=len(basis), potential=[[gp]], backend="cuda")
+    return tb.Model(basis, {"hamiltonian": ham}, bond_dim=g["bond_dim"], space=g["space"], one_gate_to_apply=gate)
 
 
 def run_cuda(g, tmp_path, use_golden_init=True):
@@ -77,7 +86,7 @@ def run_cuda(g, tmp_path, use_golden_init=True):
     return sim, ener, wf
 
 
-@pytest.mark.parametrize("name", RUN_CASES)
+@pytest.mark.parametrize("name", RUN_CASES + GATE_CASES)
 def test_propagation_matches_reference(name, tmp_path):
     g = load_run(name)
     sim, ener, wf = run_cuda(g, tmp_path)

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle.oracle_engine import OracleEngine
-from tests.golden_io import RUN_CASES, load_run
+from tests.golden_io import GATE_CASES, RUN_CASES, load_run
 
 
 def _build_model(g):
@@ -16,7 +16,16 @@ def _build_model(g):
     basis = [tb.Exciton(nstate=d) for d in g["dims"]]
     pot = {key: tb.TensorOperator(mpo=[np.asarray(c) for c in cores]) for key, cores in g["operators"].items()}
     ham = tb.TensorHamiltonian(ndof=len(basis), potential=[[pot]], backend="cuda")
-    return tb.Model(basis, {"hamiltonian": ham}, bond_dim=g["bond_dim"], space=g["space"])
+    gate = None
+    if g.get("gates"):
+        gp = {}
+        for site, U in g["gates"].items():
+            if U.ndim == 1:
+                gp[(site,)] = tb.TensorOperator(mpo=[U.reshape(1, -1, 1)], legs=(site,))
+            else:
+                gp[((site, site),)] = tb.TensorOperator(mpo=[U.reshape(1, U.shape[0], U.shape[1], 1)], legs=(site, site))
+        gate = tb.TensorHamiltonian(ndof=len(basis), potential=[[gp]], backend="cuda")
+    return tb.Model(basis, {"hamiltonian": ham}, bond_dim=g["bond_dim"], space=g["space"], one_gate_to_apply=gate)
 
 
 def _run(g, tmp_path, relax=None):
@@ -38,7 +47,7 @@ def _run(g, tmp_path, relax=None):
     return sim, ener, wf
 
 
-@pytest.mark.parametrize("name", RUN_CASES)
+@pytest.mark.parametrize("name", RUN_CASES + GATE_CASES)
 def test_host_sweep_logic_reproduces_reference(name, tmp_path):
     """Same kernels as the oracle => the product's bookkeeping must reproduce the reference run exactly."""
     g = load_run(name)
