@@ -545,10 +545,45 @@ class MPSCoefCuda:
                     dens = new.reshape((l, l, m, m) + xshape).contiguous()
         return dens[0, 0].cpu().numpy()
 
-    def get_reduced_densities(self, remain_nleg) -> list[np.ndarray]:
-        """Reference ``MPSCoef.get_reduced_densities``: one key (tuple) or a list of keys -> list of arrays."""
+    def _partial_trace(self, remain_nleg: tuple[int, ...]) -> np.ndarray:
+        """Liouville-space MPDO (physical index = vectorised d x d matrix): partial trace keeping the flagged sites
+        (reference ``get_partial_trace``, _mps_cls.py:1438-1510; no canonical form needed).  Traced sites contribute the
+        D x D transfer matrix sum_j core[:, (j, j), :]; everything is O(n D^2 d^2) index work on the device tensors."""
+        center = max((i for i, n in enumerate(remain_nleg) if n in (1, 2)), default=None)
+        if center is None:
+            raise ValueError("No site with 2 legs found in remain_nleg")
+        four = []
+        for s in self.sites:
+            Dl, dd, Dr = s.data.shape
+            q = math.isqrt(dd)
+            if q * q != dd:
+                raise ValueError("Liouville-space sites need a square physical dimension")
+            four.append(s.data.reshape(Dl, q, q, Dr))
+        left = torch.ones(1, dtype=torch.complex128, device=four[0].device)
+        for isite in range(center):
+            t = four[isite]
+            if remain_nleg[isite] == 0:
+                m = torch.diagonal(t, dim1=1, dim2=2).sum(-1)                          # ijjl -> il
+            elif remain_nleg[isite] == 1:
+                m = torch.diagonal(t, dim1=1, dim2=2).permute(0, 2, 1)                 # ijjl -> ijl
+            elif remain_nleg[isite] == 2:
+                m = t
+            else:
+                raise ValueError(f"Invalid number of legs: {remain_nleg[isite]}")
+            left = torch.tensordot(left, m, dims=([left.dim() - 1], [0]))
+        right = torch.ones(1, dtype=torch.complex128, device=four[0].device)
+        for isite in range(self.nsite - 1, center, -1):
+            right = torch.diagonal(four[isite], dim1=1, dim2=2).sum(-1) @ right
+        dm = torch.tensordot(left, torch.tensordot(four[center], right, dims=([3], [0])), dims=([left.dim() - 1], [0]))
+        return dm.cpu().numpy()
+
+    def get_reduced_densities(self, remain_nleg, space: str = "hilbert") -> list[np.ndarray]:
+        """Reference ``MPSCoef.get_reduced_densities``: one key (tuple) or a list of keys -> list of arrays; pure-state
+        reduced densities in Hilbert space, partial traces of the MPDO in Liouville space."""
         if isinstance(remain_nleg, tuple):
             remain_nleg = [remain_nleg]
+        if space == "liouville":
+            return [self._partial_trace(tuple(k)) for k in remain_nleg]
         return [self._pure_reduced_density(tuple(k)) for k in remain_nleg]
 
     def to_numpy(self) -> list[np.ndarray]:

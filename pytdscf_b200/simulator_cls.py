@@ -24,9 +24,10 @@ from .model_cls import Model
 class WFunc:
     """Wavefunction = device MPS + the operators it is measured against (reference ``wavefunction.py:34-598``)."""
 
-    def __init__(self, ci_coef: MPSCoefCuda, eng: Engine):
+    def __init__(self, ci_coef: MPSCoefCuda, eng: Engine, space: str = "hilbert"):
         self.ci_coef = ci_coef
         self.eng = eng
+        self.space = space
         self._dev_ops: dict[int, DeviceMPO] = {}
 
     def device_op(self, op) -> DeviceMPO:
@@ -54,7 +55,7 @@ class WFunc:
 
     def get_reduced_densities(self, remain_nleg) -> list[np.ndarray]:
         """Reduced density matrices (reference ``wavefunction.py:67-88``); 0 = traced, 1 = diagonal, 2 = both legs."""
-        return self.ci_coef.get_reduced_densities(remain_nleg)
+        return self.ci_coef.get_reduced_densities(remain_nleg, space=self.space)
 
     def propagate_SM(self, matH, stepsize: float, cfg: RunConfig, one_gate_to_apply=None):
         if one_gate_to_apply is None:
@@ -124,7 +125,7 @@ class Simulator:
         with open(path, "rb") as f:
             d = pickle.load(f)
         eng = self._engine()
-        return WFunc(MPSCoefCuda(eng, [eng.to_device(c) for c in d["cores"]], d["gauges"]), eng)
+        return WFunc(MPSCoefCuda(eng, [eng.to_device(c) for c in d["cores"]], d["gauges"]), eng, self.model.space)
 
     def set_initial_mps(self, cores: list, gauges: list[str] | None = None):
         """Lower-level entry: start from explicit site tensors (site 0 = centre, the rest right-canonical)."""
@@ -136,8 +137,8 @@ class Simulator:
         eng = self._engine()
         if getattr(self, "_initial_mps", None) is not None:
             cores, gauges = self._initial_mps
-            return WFunc(MPSCoefCuda(eng, [eng.to_device(c) for c in cores], gauges), eng)
-        return WFunc(MPSCoefCuda.alloc_random(eng, self.model), eng)
+            return WFunc(MPSCoefCuda(eng, [eng.to_device(c) for c in cores], gauges), eng, self.model.space)
+        return WFunc(MPSCoefCuda.alloc_random(eng, self.model), eng, self.model.space)
 
     def _distributed_wavefunction(self, split: list[tuple[int, ...]]) -> WFunc:
         """Site-segment-parallel start: rank 0 canonicalises the serial initial MPS and scatters the segments."""
@@ -175,8 +176,6 @@ class Simulator:
         """Real-time propagation; returns ``(energy, wf)`` like the reference (energy of the last evaluated step)."""
         self._rd = None
         if reduced_density is not None:
-            if self.model.space != "hilbert":
-                raise NotImplementedError("reduced densities of Liouville-space MPDOs (partial traces) are not implemented")
             if parallel_split_indices is not None:
                 raise NotImplementedError("reduced densities are not implemented for site-parallel runs")
             keys, rd_step = reduced_density

@@ -46,6 +46,26 @@ def main():
         many = mps.get_reduced_densities(list(keys[:3]))
         for k, rd in enumerate(many):
             out[f"{name}__multi{k}__rdm"] = np.array(rd)
+    # Liouville space: partial traces of the MPDO (get_partial_trace, _mps_cls.py:1438-1510)
+    import importlib
+
+    from pytdscf.model_cls import Model
+
+    mg = importlib.import_module("tests.golden.make_golden")
+    name = "liouville_spin3"
+    g = load_run(name)
+    basis, ops, hartree = mg.liouville_model()
+    model = Model(basis, ops, bond_dim=g["bond_dim"], space="liouville")
+    model.init_HartreeProduct = [hartree]
+    const.set_runtype(jobname="golden_rdm_liouville", space="liouville", verbose=0)
+    mps = MPSCoefMPO.alloc_random(model)
+    for site, c in zip(mps.superblock_states[0], g["final"], strict=True):
+        site.data = np.array(c)
+    for k, key in enumerate([(2,), (0, 2), (0, 0, 2), (2, 0, 2), (1, 2), (0, 1, 2)]):
+        rd = mps.get_reduced_densities(key)[0]
+        out[f"{name}__{k}__key"] = np.array(key)
+        out[f"{name}__{k}__rdm"] = np.array(rd)
+        print(name, key, rd.shape, "trace", np.trace(rd.reshape(int(np.sqrt(rd.size)), -1)) if rd.ndim % 2 == 0 else None)
     np.savez_compressed(os.path.join(HERE, "rdm.npz"), **out)
 
 

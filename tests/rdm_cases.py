@@ -23,10 +23,10 @@ def check_rdms(eng, load_run, MPSCoefCuda, atol):
         if name not in seen:
             g = load_run(name)
             seen[name] = MPSCoefCuda(eng, [eng.to_device(c) for c in g["final"]])
-        got = seen[name].get_reduced_densities(key)[0]
+        got = seen[name].get_reduced_densities(key, space="liouville" if name.startswith("liouville") else "hilbert")[0]
         assert got.shape == ref.shape, (name, key, got.shape, ref.shape)
         np.testing.assert_allclose(got, ref, rtol=0, atol=atol, err_msg=f"{name} {key}")
     # list form = one array per key
-    name, key, ref = rdm_cases()[0]
+    name, key, ref = [c for c in rdm_cases() if not c[0].startswith("liouville")][0]
     many = seen[name].get_reduced_densities([key, key])
     assert len(many) == 2 and np.allclose(many[1], ref, atol=atol)
