@@ -21,6 +21,7 @@
 #include <string>
 #include <vector>
 
+#include <cstdlib>
 #include "common.cuh"
 
 namespace tdvp {
@@ -374,8 +375,66 @@ inline long long tiles_of(const GemmDesc& d, int bm, int bn) {
 
 // The small tile is used when the big one would occupy fewer than half of the SMs, the tiny one when even the small
 // tiling leaves SM sub-partitions without a warp (< 2 small CTAs = 4 warps per SM).
-inline bool use_small(const GemmDesc& d) { return tiles_of(d, BigCfg::BM, BigCfg::BN) < 74; }
-inline bool use_tiny(const GemmDesc& d) { return tiles_of(d, SmallCfg::BM, SmallCfg::BN) < 2 * 148; }
+// TDVP_GEMM_CFG=big|small|tiny forces one configuration (tuning experiments, scripts/microbench/zgemm_shapes.py)
+inline int forced_cfg() {
+  static const int f = [] {
+    const char* e = getenv("TDVP_GEMM_CFG");
+    if (!e) return 0;
+    return e[0] == 'b' ? 1 : (e[0] == 's' ? 2 : (e[0] == 't' ? 3 : 0));
+  }();
+  return f;
+}
+
+// Cost model of one launch (measured constants, profiles/r1_zgemm_cfg_sweep.json): a CTA tile of configuration c costs
+// `lone` seconds per unit of k when it has an SM to itself and `full` when `cps` of them share the SM; K0 = prologue +
+// epilogue in units of k.  time = waves * (k_chunk + K0) * per_k  (+ the fixed-order reduction for split-K).
+struct CfgModel { int id, bm, bn, bk, cps, min_chunk; double lone, full, K0, bias; };
+constexpr CfgModel MODELS[3] = {
+    {1, 128, 64, 16, 1, 128, 0.282e-6, 0.282e-6, 32.0, 1.00},  // big   (8.33 ms / 28 waves / 1056 k on 8192x4096x1024)
+    {2, 64, 32, 8, 4, 64, 0.075e-6, 0.30e-6, 24.0, 1.00},      // small (only when forced: never the best in the sweep)
+    {3, 32, 32, 8, 4, 32, 0.040e-6, 0.140e-6, 16.0, 1.00},     // tiny  (832 us / 10.9 waves / 528 k on 1536x4096x512)
+};
+struct Choice { int cfg = 1, S = 1, chunk = 0; double t = 1e30; };
+
+inline Choice choose(const GemmDesc& d, bool allow_split, size_t scratch_elems) {
+  Choice best;
+  const double bw = 5.0e12;
+  // >= 8 full waves of big tiles: wave quantisation is < 6 % and the big tiles need the least L2 traffic per flop
+  const bool large = tiles_of(d, 128, 64) >= 8 * 148;
+  for (const CfgModel& m : MODELS) {
+    if (forced_cfg() ? forced_cfg() != m.id : (m.id == 2 || (large && m.id != 1))) continue;
+    const long long tiles = tiles_of(d, m.bm, m.bn);
+    const int slots = 148 * m.cps;
+    int max_s = 1;
+    if (allow_split && d.batch == 1 && d.K >= 2 * m.min_chunk && tiles < 8 * 148) {
+      max_s = d.K / m.min_chunk < 16 ? d.K / m.min_chunk : 16;
+    }
+    for (int S = 1; S <= max_s; ++S) {
+      int chunk = (d.K + S - 1) / S;
+      chunk = (chunk + m.bk - 1) / m.bk * m.bk;
+      if ((d.K + chunk - 1) / chunk != S) continue;
+      if (S > 1 && (size_t)S * d.M * d.N > scratch_elems) break;
+      const long long units = tiles * S;
+      double per_k = m.full;
+      if (units <= 148) per_k = m.lone;
+      else if (units < slots) per_k = m.lone * (double)((units + 147) / 148);
+      // big tiles run in lock-step waves (1 CTA per SM); the 4-per-SM tiny CTAs are scheduled dynamically, which the
+      // sweep fits as fractional waves + half a wave of tail
+      double waves = (double)((units + slots - 1) / slots);
+      if (m.id == 3 && units >= slots) waves = (double)units / slots + 0.5;
+      double t = waves * (chunk + m.K0) * per_k * m.bias;
+      if (S > 1) t += (double)(S + 2) * d.M * d.N * 16.0 / bw + 4.0e-6;
+      if (t < best.t * (S > 1 && best.cfg == m.id ? 0.97 : 1.0)) { best.t = t; best.cfg = m.id; best.S = S; best.chunk = chunk; }
+    }
+  }
+  return best;
+}
+
+inline cudaError_t launch_by_cfg(int cfg, const GemmDesc& d, cudaStream_t stream) {
+  if (cfg == 3) return launch_cfg<TinyCfg>(d, stream);
+  if (cfg == 2) return launch_cfg<SmallCfg>(d, stream);
+  return launch_cfg<BigCfg>(d, stream);
+}
 
 }  // namespace
 
@@ -383,8 +442,7 @@ cudaError_t zgemm_launch(const GemmDesc& d0, cudaStream_t stream) {
   if (d0.M <= 0 || d0.N <= 0 || d0.batch <= 0) return cudaSuccess;
   GemmDesc d = d0;
   d.c_stream = (d.splitk == 1 && (double)d.M * d.N * d.batch * 16.0 > 64.0e6) ? 1 : 0;
-  if (use_tiny(d)) return launch_cfg<TinyCfg>(d, stream);
-  return use_small(d) ? launch_cfg<SmallCfg>(d, stream) : launch_cfg<BigCfg>(d, stream);
+  return launch_by_cfg(choose(d, false, 0).cfg, d, stream);
 }
 
 namespace {
@@ -410,43 +468,14 @@ __global__ void k_splitk_reduce(const c128* __restrict__ P, int S, int M, int N,
 
 cudaError_t zgemm_auto(const GemmDesc& d, cudaStream_t stream, c128* scratch, size_t scratch_elems) {
   if (d.M <= 0 || d.N <= 0 || d.batch <= 0) return cudaSuccess;
-  const bool tiny = use_tiny(d);
-  const bool small = !tiny && use_small(d);
-  const int bm = tiny ? TinyCfg::BM : (small ? SmallCfg::BM : BigCfg::BM), bn = tiny ? TinyCfg::BN : (small ? SmallCfg::BN : BigCfg::BN);
-  const int bk = (tiny || small) ? 8 : BigCfg::BK;
-  const long long tiles = tiles_of(d, bm, bn);
-  const int min_chunk = tiny ? 32 : (small ? 64 : 128);
-  if (d.batch != 1 || d.K < 2 * min_chunk || scratch == nullptr || tiles >= 8 * 148) return zgemm_launch(d, stream);
-  // Wave-aware split-K: model t(S) = waves(S) * (K/S + K0) * t_k + reduction traffic and pick the best S.
-  // One SM sustains ~220 GFLOP/s of DMMA work: a 128x64 tile costs ~0.30 us per k; a 64x32 tile ~0.075 us per k when it
-  // has an SM to itself and 4 of them share an SM at the same aggregate rate (slots = 4 x 148, t_k x 4); a 32x32 tiny
-  // tile (4 warps of 16x16) ~0.02 us per k alone, 4 slots per SM; K0 ~ prologue + epilogue in units of k.
-  const double lone = tiny ? 0.02e-6 : 0.075e-6;
-  const double t_k = tiny ? 0.16e-6 : 0.30e-6, K0 = tiny ? 16.0 : (small ? 24.0 : 32.0), bw = 5.0e12;
-  const int slots = tiny ? 4 * 148 : (small ? 4 * 148 : 148);
-  int best_s = 1;
-  double best_t = 1e30;
-  const int max_s = d.K / min_chunk < 16 ? d.K / min_chunk : 16;
-  for (int S = 1; S <= max_s; ++S) {
-    int chunk = (d.K + S - 1) / S;
-    chunk = (chunk + bk - 1) / bk * bk;
-    const int s_eff = (d.K + chunk - 1) / chunk;
-    if (s_eff != S) continue;
-    if (S > 1 && (size_t)S * d.M * d.N > scratch_elems) break;
-    const long long units = tiles * S;
-    // fewer units than SMs: every CTA has its SM to itself (a lone small CTA runs 4x faster per k than when 4 share)
-    double per_k = t_k;
-    if ((small || tiny) && units <= 148) per_k = lone;
-    else if ((small || tiny) && units < slots) per_k = lone * (double)((units + 147) / 148);
-    const double waves = (double)((units + slots - 1) / slots);
-    double t = waves * (chunk + K0) * per_k;
-    if (S > 1) t += (double)(S + 2) * d.M * d.N * 16.0 / bw + 4.0e-6;
-    if (t < best_t * 0.97) { best_t = t; best_s = S; }   // prefer fewer splits unless >= 3 % better
+  // wave-aware choice of the tile configuration AND the split-K factor (see choose())
+  const Choice ch = choose(d, scratch != nullptr, scratch_elems);
+  const int S = ch.S, chunk = ch.chunk;
+  if (S < 2) {
+    GemmDesc g1 = d;
+    g1.c_stream = ((double)d.M * d.N * d.batch * 16.0 > 64.0e6) ? 1 : 0;
+    return launch_by_cfg(ch.cfg, g1, stream);
   }
-  int S = best_s;
-  if (S < 2) return zgemm_launch(d, stream);
-  int chunk = (d.K + S - 1) / S;
-  chunk = (chunk + bk - 1) / bk * bk;
   GemmDesc g = d;
   g.C = scratch;
   g.c_m_inner = 1; g.c_m1 = d.N; g.c_m0 = 0; g.c_n = 1; g.c_batch = 0;
@@ -455,7 +484,7 @@ cudaError_t zgemm_auto(const GemmDesc& d, cudaStream_t stream, c128* scratch, si
   g.splitk = S;
   g.k_chunk = chunk;
   g.c_split = (long long)d.M * d.N;
-  cudaError_t e = zgemm_launch(g, stream);
+  cudaError_t e = launch_by_cfg(ch.cfg, g, stream);
   if (e != cudaSuccess) return e;
   const long long tot = (long long)d.M * d.N;
   int blocks = (int)((tot + 255) / 256);

@@ -21,6 +21,14 @@ SHAPES = [
     ("c3 env  step3   CN", 256, 1280, 2560, 2, 0),
     ("c3 keff gemm1   NN", 1280, 256, 256, 0, 0),
     ("c3 keff gemm2   NT", 256, 256, 1280, 0, 1),
+    ("c3s heff stage1 NN (id skip)", 1024, 2560, 256, 0, 0),
+    ("c3s heff stage3 NT (id skip)", 2560, 256, 1024, 0, 1),
+    ("c5 heff stage1  NN pot", 1536, 4096, 512, 0, 0),
+    ("c5 heff stage1  NN kin", 512, 4096, 512, 0, 0),
+    ("c5 heff stage3  NT pot", 4096, 512, 1536, 0, 1),
+    ("c5 heff stage3  NT kin", 4096, 512, 512, 0, 1),
+    ("c5 keff gemm1   NN", 1536, 512, 512, 0, 0),
+    ("c5 keff gemm2   NT", 512, 512, 1536, 0, 1),
     ("square 4096     NN", 4096, 4096, 4096, 0, 0),
     ("square 8192     NN", 8192, 8192, 8192, 0, 0),
 ]
