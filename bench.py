@@ -396,7 +396,9 @@ def run_cuda(args):
     flops_per_sweep = flops_all / (2 * args.steps)
     stats = {"avg_matvecs_H": float(nH.mean()), "avg_matvecs_K": float(nK.mean()) if len(nK) else 0.0,
              "flops_per_sweep": flops_per_sweep, "source": "bench.py GPU run"}
-    if rank == 0 and not site_parallel:
+    if rank == 0 and not site_parallel and not os.path.exists(os.path.join(STATS_DIR, wl.name + ".json")):
+        # the committed files (Krylov counts of the named workloads) keep the CPU legs of both arms on the same sample;
+        # only workloads without one (e.g. --bond-dim overrides) record theirs here
         os.makedirs(STATS_DIR, exist_ok=True)
         with open(os.path.join(STATS_DIR, wl.name + ".json"), "w") as f:
             json.dump(stats, f, indent=1)
