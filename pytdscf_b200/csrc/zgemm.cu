@@ -399,8 +399,9 @@ struct Choice { int cfg = 1, S = 1, chunk = 0; double t = 1e30; };
 inline Choice choose(const GemmDesc& d, bool allow_split, size_t scratch_elems) {
   Choice best;
   const double bw = 5.0e12;
-  // >= 8 full waves of big tiles: wave quantisation is < 6 % and the big tiles need the least L2 traffic per flop
-  const bool large = tiles_of(d, 128, 64) >= 8 * 148;
+  // >= 8 full waves of big tiles with a long K: wave quantisation is < 6 % and the big tiles need the least L2 traffic
+  // per flop (short-K GEMMs such as H_eff stage 2 are prologue-bound and keep the free choice)
+  const bool large = tiles_of(d, 128, 64) >= 8 * 148 && d.K >= 512;
   for (const CfgModel& m : MODELS) {
     if (forced_cfg() ? forced_cfg() != m.id : (m.id == 2 || (large && m.id != 1))) continue;
     const long long tiles = tiles_of(d, m.bm, m.bn);

@@ -13,6 +13,8 @@ SHAPES = [
     ("c4 heff stage1  NN", 8192, 4096, 1024, 0, 0),
     ("c4 heff stage3  NT", 4096, 1024, 8192, 0, 1),
     ("c4 env  step3   CN", 1024, 8192, 4096, 2, 0),
+    ("c4 heff stage2  NN (d=16,w=8)", 1048576, 128, 128, 0, 0),
+    ("c4 heff stage2  NN (d=4,w=8)", 1048576, 32, 32, 0, 0),
     ("c4 keff gemm1   NN", 8192, 1024, 1024, 0, 0),
     ("c4 keff gemm2   NT", 1024, 1024, 8192, 0, 1),
     ("c4e heff stage1 NN", 8192, 16384, 1024, 0, 0),
