@@ -440,14 +440,49 @@ class MPSCoefCuda:
             self.op_sys_sites.append(op_sys)
         return op_sys
 
-    def propagate(self, stepsize: float, H: DeviceMPO, cfg, one_gate: DeviceMPO | None = None):
+    def propagate(self, stepsize: float, H: DeviceMPO, cfg, one_gate: DeviceMPO | None = None, kraus_op: dict | None = None):
         """One time step: forward and backward half sweeps (the last site gets two consecutive half steps); one-site
-        gates, if any, act between the two (reference ``_mps_cls.py:452-503``)."""
+        gates and Kraus maps, if any, act between the two (reference ``_mps_cls.py:452-503``)."""
         n = self.nsite
         self.propagate_along_sweep(H, stepsize, cfg, begin_site=0, end_site=n - 1)
         if one_gate is not None:
             self.apply_one_gate(one_gate, reorth_center=n - 1)
+        if kraus_op is not None:
+            self.apply_kraus(kraus_op, reorth_center=n - 1)
         self.propagate_along_sweep(H, stepsize, cfg, begin_site=n - 1, end_site=0)
+
+    def apply_kraus(self, kraus_op: dict, reorth_center: int):
+        """One-site Kraus maps on a purified MPS (reference ``apply_kraus`` + ``kraus_contract_single_site``,
+        _mps_cls.py:2375-2418, kraus.py:146-222).  The site's physical index is (system d) x (ancilla K); the k Kraus
+        operators B[k, x, d] act on the system part, the (k, K) pair is compressed back to K ancilla states by an SVD of
+        the (m n x) x (k K) matrix (U S of the K largest singular values).  GEMM + thin SVD on the device."""
+        eng = self.eng
+        sb = self.sites
+        lo, hi = 10**9, 0
+        for site_inds, B in kraus_op.items():
+            if len(site_inds) != 1:
+                raise NotImplementedError("only one-site Kraus maps are implemented (two-site maps: reference kraus.py:258-330)")
+            isite = int(site_inds[0])
+            lo, hi = min(lo, isite), max(hi, isite)
+            Bd = B if isinstance(B, torch.Tensor) else eng.to_device(np.asarray(B, dtype=np.complex128))
+            k, x, d = Bd.shape
+            A = sb[isite].data
+            m, dK, n = A.shape
+            if x != d or dK % d:
+                raise ValueError(f"Kraus contract: dK={dK} must be divisible by d={d}")
+            K = dK // d
+            if m * n * x < K:
+                raise ValueError("Kraus contract: fewer rows than ancilla states")
+            A2 = A.reshape(m, d, K * n).permute(1, 0, 2).reshape(d, m * K * n).contiguous()       # [d, (m, K, n)]
+            G = eng.zgemm(Bd.reshape(k * x, d).contiguous(), A2)                                   # [(k, x), (m, K, n)]
+            Cm = G.reshape(k, x, m, K, n).permute(2, 4, 1, 0, 3).reshape(m * n * x, k * K).contiguous()
+            U, sv, _ = eng.svd(Cm)
+            scale = torch.as_tensor(sv[:K], dtype=torch.float64, device=U.device)
+            new = (U[:, :K] * scale[None, :]).reshape(m, n, x * K).permute(0, 2, 1).contiguous()   # (m, x K, n)
+            sb[isite].data = new
+        canonicalizeB(eng, sb[reorth_center: hi + 1])
+        canonicalizeA(eng, sb[lo: reorth_center + 1])
+        self.op_sys_sites = None
 
     def apply_one_gate(self, gate: DeviceMPO, reorth_center: int):
         """U_p on the physical leg of every site that has a gate core, then re-canonicalise around ``reorth_center`` and

@@ -56,7 +56,8 @@ class Model:
         if build_td_hamiltonian is not None:
             raise NotImplementedError("time-dependent Hamiltonians are not part of the MPO hot path")
         if kraus_op is not None:
-            raise NotImplementedError("Kraus maps are a 'next' row (SURVEY 8(f3)); not in backend='cuda' yet")
+            if not isinstance(kraus_op, dict) or any(len(k) != 1 for k in kraus_op):
+                raise NotImplementedError("kraus_op must be {(site,): B[k, d, d]}; two-site Kraus maps are not implemented")
         if one_gate_to_apply is not None and not isinstance(one_gate_to_apply, TensorHamiltonian):
             raise TypeError("one_gate_to_apply must be a TensorHamiltonian of one-site cores")
         if isinstance(operators, (TensorHamiltonian, list)):
@@ -83,7 +84,8 @@ class Model:
         self.one_gate_to_apply = one_gate_to_apply
         if one_gate_to_apply is not None and self.subspace_inds is not None:
             one_gate_to_apply.project_subspace(self.subspace_inds)
-        self.kraus_op = None
+        self.kraus_op = None if kraus_op is None else {tuple(int(i) for i in k): np.asarray(v, dtype=np.complex128)
+                                                       for k, v in kraus_op.items()}
 
     # -- basis passthroughs ------------------------------------------------------------------------
     def get_nstate(self) -> int:

@@ -57,11 +57,15 @@ class WFunc:
         """Reduced density matrices (reference ``wavefunction.py:67-88``); 0 = traced, 1 = diagonal, 2 = both legs."""
         return self.ci_coef.get_reduced_densities(remain_nleg, space=self.space)
 
-    def propagate_SM(self, matH, stepsize: float, cfg: RunConfig, one_gate_to_apply=None):
-        if one_gate_to_apply is None:
+    def propagate_SM(self, matH, stepsize: float, cfg: RunConfig, one_gate_to_apply=None, kraus_op=None):
+        if one_gate_to_apply is None and kraus_op is None:
             self.ci_coef.propagate(stepsize, self.device_op(matH), cfg)
         else:
-            self.ci_coef.propagate(stepsize, self.device_op(matH), cfg, one_gate=self.device_op(one_gate_to_apply))
+            if kraus_op is not None and getattr(self, "_kraus_dev", None) is None:
+                self._kraus_dev = {k: self.eng.to_device(v) for k, v in kraus_op.items()}     # uploaded once
+            self.ci_coef.propagate(stepsize, self.device_op(matH), cfg,
+                                   one_gate=None if one_gate_to_apply is None else self.device_op(one_gate_to_apply),
+                                   kraus_op=None if kraus_op is None else self._kraus_dev)
 
 
 class _DatFile:
@@ -192,7 +196,7 @@ class Simulator:
         if parallel_split_indices is not None:
             # reference: one MPI rank per tuple of consecutive sites (simulator_cls.py:243-249, _const_cls.py:236-251);
             # here one torch.distributed rank (= one GPU) per tuple, launched by torchrun
-            if adaptive or restart or self.model.one_gate_to_apply is not None:
+            if adaptive or restart or self.model.one_gate_to_apply is not None or self.model.kraus_op is not None:
                 raise NotImplementedError("site-parallel propagation supports neither adaptive bond dimensions, restart nor gates")
             self._split = [tuple(int(i) for i in seg) for seg in parallel_split_indices]
         return self._run(Δt if Δt is not None else stepsize, maxstep, False, restart, savefile_ext, loadfile_ext,
@@ -248,7 +252,8 @@ class Simulator:
             if files is not None:
                 self._export(files, cfg, rec, elapsed)
             t0 = _time.perf_counter()
-            wf.propagate_SM(ham, stepsize_au, cfg, one_gate_to_apply=None if relax else self.model.one_gate_to_apply)
+            wf.propagate_SM(ham, stepsize_au, cfg, one_gate_to_apply=None if relax else self.model.one_gate_to_apply,
+                            kraus_op=None if relax else self.model.kraus_op)
             elapsed += _time.perf_counter() - t0
             time_au += stepsize_au
         if files is not None:

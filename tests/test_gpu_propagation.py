@@ -225,3 +225,23 @@ def test_reduced_densities_gpu():
     from tests.rdm_cases import check_rdms
 
     check_rdms(eng, load_run, MPSCoefCuda, atol=1e-13)
+
+
+def test_kraus_map_gpu(tmp_path):
+    """One-site Kraus map on a purified MPS (device GEMM + Jacobi SVD) against the reference run: Krylov trace, per-step
+    energy / norm and the system reduced density of the Kraus site (ancilla phases are an SVD gauge, traced out)."""
+    import pytdscf_b200 as tb
+    from tests.golden_io import KRAUS_CASES
+    from tests.test_host_sweep_cpu import _kraus_model, kraus_observables
+
+    g = load_run(KRAUS_CASES[0])
+    os.chdir(tmp_path)
+    sim = tb.Simulator("kraus_gpu", _kraus_model(g), backend="cuda")
+    sim.set_initial_mps(g["init"])
+    ener, wf = sim.propagate(stepsize=g["dt_au"] * tb.units.au_in_fs, maxstep=g["nstep"], autocorr=False, populations=False,
+                             conserve_norm=False, record_trace=True)
+    assert (np.array(wf.ci_coef.trace) == g["trace"]).all()
+    obs, rho, ref = kraus_observables(sim, wf, g)
+    for (e, n), row in zip(obs, g["props"], strict=True):
+        assert abs(e - row[3]) <= REL * max(1.0, abs(row[3])) and abs(n - row[5]) <= REL
+    np.testing.assert_allclose(rho, ref, atol=1e-10)

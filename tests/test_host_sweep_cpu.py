@@ -219,3 +219,44 @@ def test_identity_channel_analysis_matches_the_environments(name, reorder):
             if b == p and key in left[p] and lid >= 0:
                 np.testing.assert_allclose(left[p][key].numpy()[:, lid, :], np.eye(left[p][key].shape[0]), atol=1e-12)
     assert found > 0, "no identity channel detected in an MPO that has prefix/suffix channels"
+
+
+def _kraus_model(g):
+    import pytdscf_b200 as tb
+
+    basis = [tb.Exciton(nstate=d) for d in g["dims"]]
+    pot = {key: tb.TensorOperator(mpo=[np.asarray(c) for c in cores]) for key, cores in g["operators"].items()}
+    ham = tb.TensorHamiltonian(ndof=len(basis), potential=[[pot]], backend="cuda")
+    return tb.Model(basis, {"hamiltonian": ham}, bond_dim=g["bond_dim"], kraus_op=g["kraus"])
+
+
+def kraus_observables(sim, wf, g):
+    """Quantities that do not depend on the phases of the ancilla basis the SVD picks: per-step energy and norm, and the
+    system part of the Kraus site's reduced density (ancilla traced out)."""
+    K = g["kraus_K"]
+    rd = wf.get_reduced_densities((0, 2))[0]
+    d = rd.shape[0] // K
+    rho = np.einsum("akbk->ab", rd.reshape(d, K, d, K))
+    ref = np.einsum("akbk->ab", g["rdm_site1"].reshape(d, K, d, K))
+    return [(r["energy"], r["norm"]) for r in sim.history], rho, ref
+
+
+def test_host_kraus_logic(tmp_path):
+    """One-site Kraus map between the half sweeps: with the oracle's kernels (same LAPACK SVD) the product reproduces the
+    reference run, Krylov trace included."""
+    import pytdscf_b200 as tb
+    from tests.golden_io import KRAUS_CASES
+
+    g = load_run(KRAUS_CASES[0])
+    os.chdir(tmp_path)
+    sim = tb.Simulator("kraus_cpu", _kraus_model(g), backend="cuda")
+    sim.eng = OracleEngine()
+    sim.set_initial_mps(g["init"])
+    ener, wf = sim.propagate(stepsize=g["dt_au"] * tb.units.au_in_fs, maxstep=g["nstep"], autocorr=False, populations=False,
+                             conserve_norm=False, record_trace=True)
+    assert (np.array(wf.ci_coef.trace) == g["trace"]).all()
+    obs, rho, ref = kraus_observables(sim, wf, g)
+    for (e, n), row in zip(obs, g["props"], strict=True):
+        assert abs(e - row[3]) < 1e-12 and abs(n - row[5]) < 1e-12
+    np.testing.assert_allclose(rho, ref, atol=1e-12)
+    assert [s.shape for s in wf.ci_coef.sites] == [c.shape for c in g["final"]]
