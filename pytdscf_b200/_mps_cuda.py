@@ -452,34 +452,60 @@ class MPSCoefCuda:
         self.propagate_along_sweep(H, stepsize, cfg, begin_site=n - 1, end_site=0)
 
     def apply_kraus(self, kraus_op: dict, reorth_center: int):
-        """One-site Kraus maps on a purified MPS (reference ``apply_kraus`` + ``kraus_contract_single_site``,
-        _mps_cls.py:2375-2418, kraus.py:146-222).  The site's physical index is (system d) x (ancilla K); the k Kraus
-        operators B[k, x, d] act on the system part, the (k, K) pair is compressed back to K ancilla states by an SVD of
-        the (m n x) x (k K) matrix (U S of the K largest singular values).  GEMM + thin SVD on the device."""
+        """Kraus maps on a purified MPS (reference ``apply_kraus`` + ``kraus_contract_single_site / _two_site``,
+        _mps_cls.py:2375-2418, kraus.py:146-355).  One-site key: the site's physical index is (system d) x (ancilla K);
+        two-site key: system site followed by its ancilla site.  The k Kraus operators B[k, x, d] act on the system
+        part, the (k, K) pair is compressed back to K ancilla states by an SVD of the (m n x) x (k K) matrix (U S of the K
+        largest singular values); the two-site form splits the pair again with a second SVD.  GEMMs + thin SVDs on the device."""
         eng = self.eng
         sb = self.sites
         lo, hi = 10**9, 0
         for site_inds, B in kraus_op.items():
-            if len(site_inds) != 1:
-                raise NotImplementedError("only one-site Kraus maps are implemented (two-site maps: reference kraus.py:258-330)")
-            isite = int(site_inds[0])
-            lo, hi = min(lo, isite), max(hi, isite)
             Bd = B if isinstance(B, torch.Tensor) else eng.to_device(np.asarray(B, dtype=np.complex128))
             k, x, d = Bd.shape
-            A = sb[isite].data
-            m, dK, n = A.shape
-            if x != d or dK % d:
-                raise ValueError(f"Kraus contract: dK={dK} must be divisible by d={d}")
-            K = dK // d
+            if len(site_inds) == 1:
+                isite = int(site_inds[0])
+                lo, hi = min(lo, isite), max(hi, isite)
+                A = sb[isite].data
+                m, dK, n = A.shape
+                if x != d or dK % d:
+                    raise ValueError(f"Kraus contract: dK={dK} must be divisible by d={d}")
+                K = dK // d
+                T = A.reshape(m, d, K * n)
+            elif len(site_inds) == 2:
+                # system site (d) followed by its ancilla site (K): contract the pair first (kraus.py:258-355)
+                i1, i2 = int(site_inds[0]), int(site_inds[1])
+                if i1 + 1 != i2:
+                    raise ValueError(f"site_inds={site_inds} is not nearest neighbour")
+                lo, hi = min(lo, i1), max(hi, i2)
+                A1, A2 = sb[i1].data, sb[i2].data
+                m, d1, bond = A1.shape
+                _, K, n = A2.shape
+                if x != d or d1 != d:
+                    raise ValueError("Kraus contract: operator and system site dimensions differ")
+                T = eng.zgemm(A1.reshape(m * d, bond), A2.reshape(bond, K * n)).reshape(m, d, K * n)
+            else:
+                raise ValueError(f"site_inds={site_inds} is not yet implemented")
             if m * n * x < K:
                 raise ValueError("Kraus contract: fewer rows than ancilla states")
-            A2 = A.reshape(m, d, K * n).permute(1, 0, 2).reshape(d, m * K * n).contiguous()       # [d, (m, K, n)]
-            G = eng.zgemm(Bd.reshape(k * x, d).contiguous(), A2)                                   # [(k, x), (m, K, n)]
-            Cm = G.reshape(k, x, m, K, n).permute(2, 4, 1, 0, 3).reshape(m * n * x, k * K).contiguous()
-            U, sv, _ = eng.svd(Cm)
-            scale = torch.as_tensor(sv[:K], dtype=torch.float64, device=U.device)
-            new = (U[:, :K] * scale[None, :]).reshape(m, n, x * K).permute(0, 2, 1).contiguous()   # (m, x K, n)
-            sb[isite].data = new
+            T2 = T.permute(1, 0, 2).reshape(d, m * K * n).contiguous()                              # [d, (m, K, n)]
+            G = eng.zgemm(Bd.reshape(k * x, d).contiguous(), T2).reshape(k, x, m, K, n)              # [k, x, m, K, n]
+            if len(site_inds) == 1:
+                Cm = G.permute(2, 4, 1, 0, 3).reshape(m * n * x, k * K).contiguous()                 # rows (m, n, x)
+                U, sv, _ = eng.svd(Cm)
+                scale = torch.as_tensor(sv[:K], dtype=torch.float64, device=U.device)
+                sb[isite].data = (U[:, :K] * scale[None, :]).reshape(m, n, x * K).permute(0, 2, 1).contiguous()   # (m, x K, n)
+            else:
+                Cm = G.permute(2, 1, 4, 0, 3).reshape(m * x * n, k * K).contiguous()                 # rows (m, x, n)
+                U, sv, _ = eng.svd(Cm)
+                scale = torch.as_tensor(sv[:K], dtype=torch.float64, device=U.device)
+                C2 = (U[:, :K] * scale[None, :]).reshape(m, x, n, K).permute(0, 1, 3, 2).reshape(m * x, K * n).contiguous()
+                U2, s2, Vh2 = eng.svd(C2)                                                             # split the pair again
+                if len(s2) < bond:
+                    raise ValueError("Kraus contract: the pair matrix has fewer singular values than the bond dimension")
+                sc2 = torch.as_tensor(s2[:bond], dtype=torch.float64, device=U2.device)
+                sb[i1].data = (U2[:, :bond] * sc2[None, :]).reshape(m, x, bond).contiguous()
+                sb[i2].data = Vh2[:bond, :].reshape(bond, K, n).contiguous()
         canonicalizeB(eng, sb[reorth_center: hi + 1])
         canonicalizeA(eng, sb[lo: reorth_center + 1])
         self.op_sys_sites = None

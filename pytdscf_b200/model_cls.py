@@ -56,8 +56,8 @@ class Model:
         if build_td_hamiltonian is not None:
             raise NotImplementedError("time-dependent Hamiltonians are not part of the MPO hot path")
         if kraus_op is not None:
-            if not isinstance(kraus_op, dict) or any(len(k) != 1 for k in kraus_op):
-                raise NotImplementedError("kraus_op must be {(site,): B[k, d, d]}; two-site Kraus maps are not implemented")
+            if not isinstance(kraus_op, dict) or any(len(k) not in (1, 2) for k in kraus_op):
+                raise ValueError("kraus_op must be {(site,): B[k, d, d]} or {(site, site + 1): B[k, d, d]}")
         if one_gate_to_apply is not None and not isinstance(one_gate_to_apply, TensorHamiltonian):
             raise TypeError("one_gate_to_apply must be a TensorHamiltonian of one-site cores")
         if isinstance(operators, (TensorHamiltonian, list)):

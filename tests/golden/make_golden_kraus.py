@@ -31,30 +31,50 @@ from pytdscf_b200.mpo_tools import sop_to_mpo  # noqa: E402  (only builds the in
 
 
 def main():
+    run_case(two_site=False)
+    run_case(two_site=True)
+
+
+def run_case(two_site):
     K, d = 3, 2
     sx = np.array([[0, 1], [1, 0]], dtype=complex) / 2
     sy = np.array([[0, -1j], [1j, 0]], dtype=complex) / 2
     sz = np.array([[1, 0], [0, -1]], dtype=complex) / 2
     eK = np.eye(K, dtype=complex)
-    dims = [2, d * K, 2, 2]
-    op = lambda s, m: np.kron(m, eK) if s == 1 else m  # noqa: E731
     terms = []
-    for i in range(3):
-        for m in (sx, sy, sz):
-            terms.append((2.0e-3, {i: op(i, m), i + 1: op(i + 1, m)}))
-    for i, h in enumerate([1.0e-3, 3.0e-3, -2.0e-3, 0.5e-3]):
-        terms.append((h, {i: op(i, sz)}))
+    if two_site:
+        # the ancilla is its own site (index 2, dimension K) right of the system site 1; H acts on sites 0, 1, 3
+        dims = [2, d, K, 2]
+        phys = [0, 1, 3]
+        for a, b in ((0, 1), (1, 3)):
+            for m in (sx, sy, sz):
+                terms.append((2.0e-3, {a: m, b: m}))
+        for i, h in zip(phys, [1.0e-3, 3.0e-3, 0.5e-3]):
+            terms.append((h, {i: sz}))
+        terms.append((0.0, {2: eK}))
+    else:
+        dims = [2, d * K, 2, 2]
+        op = lambda s, m: np.kron(m, eK) if s == 1 else m  # noqa: E731
+        for i in range(3):
+            for m in (sx, sy, sz):
+                terms.append((2.0e-3, {i: op(i, m), i + 1: op(i + 1, m)}))
+        for i, h in enumerate([1.0e-3, 3.0e-3, -2.0e-3, 0.5e-3]):
+            terms.append((h, {i: op(i, sz)}))
     cores = sop_to_mpo(dims, terms)
     gam = 0.08
     B = np.array([[[1, 0], [0, np.sqrt(1 - gam)]], [[0, np.sqrt(gam)], [0, 0]]], dtype=complex)   # amplitude damping, (k, x, d)
     basis = [Exciton(nstate=n) for n in dims]
-    model = Model(basis, {"hamiltonian": cores}, bond_dim=6, kraus_op={(1,): B})
+    kkey = (1, 2) if two_site else (1,)
+    model = Model(basis, {"hamiltonian": cores}, bond_dim=6, kraus_op={kkey: B})
     up, mix = [1.0, 0.0], [np.sqrt(0.5), np.sqrt(0.5)]
-    site1 = np.zeros(d * K)
-    site1[1 * K + 0] = 1.0          # system |1>, ancilla |0>
-    hartree = [mix, site1.tolist(), up, mix]
+    if two_site:
+        hartree = [mix, [0.0, 1.0], [1.0] + [0.0] * (K - 1), mix]
+    else:
+        site1 = np.zeros(d * K)
+        site1[1 * K + 0] = 1.0          # system |1>, ancilla |0>
+        hartree = [mix, site1.tolist(), up, mix]
     model.init_HartreeProduct = [hartree]
-    name, dt_fs, nstep = "kraus_spin4", 2.0, 6
+    name, dt_fs, nstep = ("kraus2_spin4" if two_site else "kraus_spin4"), 2.0, 6
     mg._reset_reference_state()
     cwd = os.getcwd()
     with tempfile.TemporaryDirectory() as tmp:
@@ -73,7 +93,7 @@ def main():
            "thresh_sil": np.array(1e-9), "coupleJ": np.array(complex(model.hamiltonian.coupleJ[0][0])), "nkeys": np.array(len(mpo.operators)),
            "props": np.array([[t, 0.0, 0.0, e.real, e.imag, n] for (t, a, e, n) in mg.RECORD["props"]]),
            "trace": np.array(mg.RECORD["trace"], dtype=np.int64), "final_energy": np.array(complex(ener)),
-           "kraus_site": np.array(1), "kraus_B": B, "kraus_K": np.array(K)}
+           "kraus_site": np.array(kkey), "kraus_B": B, "kraus_K": np.array(K)}
     for ik, (key, cs) in enumerate(mpo.operators.items()):
         out[f"key{ik}"] = np.array(repr(key))
         for ic, c in enumerate(cs):
@@ -84,12 +104,12 @@ def main():
         out[f"final{i}"] = np.array(s.data)
     for i, h in enumerate(hartree):
         out[f"hartree{i}"] = np.asarray(h, dtype=np.complex128)
-    rd = wf.ci_coef.get_reduced_densities((0, 2))[0]           # (dK, dK) of the Kraus site
+    rd = wf.ci_coef.get_reduced_densities((0, 2))[0]           # Kraus site: (dK, dK), or the system site (d, d)
     out["rdm_site1"] = np.array(rd)
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
-    rho = rd.reshape(d, K, d, K)
+    rho = rd if two_site else np.einsum("akbk->ab", rd.reshape(d, K, d, K))
     print(f"[golden] {name}: E_final={ener!r} norm_last={mg.RECORD['props'][-1][3]:.10f} solves={len(mg.RECORD['trace'])} "
-          f"rho_sys=\n{np.einsum('akbk->ab', rho)}")
+          f"rho_sys=\n{rho}")
 
 
 if __name__ == "__main__":

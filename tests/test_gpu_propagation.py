@@ -227,14 +227,14 @@ def test_reduced_densities_gpu():
     check_rdms(eng, load_run, MPSCoefCuda, atol=1e-13)
 
 
-def test_kraus_map_gpu(tmp_path):
+@pytest.mark.parametrize("case", ["kraus_spin4", "kraus2_spin4"])
+def test_kraus_map_gpu(case, tmp_path):
     """One-site Kraus map on a purified MPS (device GEMM + Jacobi SVD) against the reference run: Krylov trace, per-step
     energy / norm and the system reduced density of the Kraus site (ancilla phases are an SVD gauge, traced out)."""
     import pytdscf_b200 as tb
-    from tests.golden_io import KRAUS_CASES
     from tests.test_host_sweep_cpu import _kraus_model, kraus_observables
 
-    g = load_run(KRAUS_CASES[0])
+    g = load_run(case)
     os.chdir(tmp_path)
     sim = tb.Simulator("kraus_gpu", _kraus_model(g), backend="cuda")
     sim.set_initial_mps(g["init"])

@@ -235,19 +235,22 @@ def kraus_observables(sim, wf, g):
     system part of the Kraus site's reduced density (ancilla traced out)."""
     K = g["kraus_K"]
     rd = wf.get_reduced_densities((0, 2))[0]
-    d = rd.shape[0] // K
-    rho = np.einsum("akbk->ab", rd.reshape(d, K, d, K))
-    ref = np.einsum("akbk->ab", g["rdm_site1"].reshape(d, K, d, K))
+    if len(next(iter(g["kraus"]))) == 2:      # two-site form: site 1 is the bare system site
+        rho, ref = rd, g["rdm_site1"]
+    else:
+        d = rd.shape[0] // K
+        rho = np.einsum("akbk->ab", rd.reshape(d, K, d, K))
+        ref = np.einsum("akbk->ab", g["rdm_site1"].reshape(d, K, d, K))
     return [(r["energy"], r["norm"]) for r in sim.history], rho, ref
 
 
-def test_host_kraus_logic(tmp_path):
-    """One-site Kraus map between the half sweeps: with the oracle's kernels (same LAPACK SVD) the product reproduces the
+@pytest.mark.parametrize("case", ["kraus_spin4", "kraus2_spin4"])
+def test_host_kraus_logic(case, tmp_path):
+    """Kraus maps between the half sweeps: with the oracle's kernels (same LAPACK SVD) the product reproduces the
     reference run, Krylov trace included."""
     import pytdscf_b200 as tb
-    from tests.golden_io import KRAUS_CASES
 
-    g = load_run(KRAUS_CASES[0])
+    g = load_run(case)
     os.chdir(tmp_path)
     sim = tb.Simulator("kraus_cpu", _kraus_model(g), backend="cuda")
     sim.eng = OracleEngine()
