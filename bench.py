@@ -19,7 +19,9 @@ configuration the north-star target (>= 20x the CPU path at D = 1024) is quoted 
               bounded sample (one full-bond-dimension site update), extrapolated to sweeps/s by algorithmic flops.
 * N > 1       config 4 is "replicas only" in the reference's semantics (Liouville space is excluded from
               its parallel path; trajectories / initial states are independent): N independent replicas, no
-              data-path collective, weak scaling.
+              data-path collective, weak scaling.  ``--workload c5`` (config 5, 128 sites, D = 512) runs the reference's
+              site-segment-parallel TDVP of ONE chain over NCCL point-to-point instead (strong scaling;
+              ``--parallel replicas|sites`` overrides the choice).
 ``--impl reference`` times the CPU path alone (rank 0), each step being the bounded sample.
 """
 from __future__ import annotations

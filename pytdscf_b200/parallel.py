@@ -1,10 +1,11 @@
 """Multi-GPU plumbing: one process per GPU under ``torch.distributed`` (NCCL on GPUs, gloo in CPU tests).
 
-Round-1 scope: **replicas** -- every rank propagates an independent wavefunction (the
-reference's semantics for Liouville-space / trajectory workloads, which its site-parallel path excludes,
-``pytdscf/_mps_parallel.py:82-87``); there is no data-path collective, only the control-plane reductions below.
-The site-segment-parallel TDVP of ``MPSCoefParallel`` (``_mps_parallel.py:106-470``) is the round-2 item that will
-add NCCL send/recv of boundary environment blocks, bond matrices and centre tensors on top of this module."""
+Two modes use it:
+* **site-segment-parallel TDVP** of one chain (``pytdscf_b200/_mps_parallel.py``, the reference's ``MPSCoefParallel``):
+  nearest-neighbour point-to-point exchange of environment blocks, bond matrices and centre tensors (``Comm`` there);
+* **replicas** -- every rank propagates an independent wavefunction (the reference's semantics for Liouville-space /
+  trajectory workloads, which its site-parallel path excludes, ``pytdscf/_mps_parallel.py:82-87``); no data-path
+  collective, only the control-plane reductions below (MAX of times, SUM of work)."""
 from __future__ import annotations
 
 import os
