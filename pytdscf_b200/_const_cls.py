@@ -20,6 +20,7 @@ class RunConfig:
     display_time_unit: str = "fs"
     time_au_init: float = 0.0
     adaptive: bool = False
+    p_svd: float = 1.0e-07  # adaptive_p_svd: truncation weight of the site-parallel boundary bond (reference const.p_svd)
 
     def __post_init__(self):
         self.space = self.space.lower()

@@ -363,7 +363,7 @@ class MPSCoefParallelCuda(MPSCoefCuda):
         kterms = self.operators_for_superK(op_sys, op_env, H, True, bond=n)
         sigma = self._expm(cfg, +1.0j, dt, sigma, key, 1, kterms=kterms)
         # truncate_sigvec(A, sigma, B, p_svd, regularize=True, keepdim=True)
-        U, S, Vh, _rank = eng.svd_truncate(sigma, P_SVD, keepdim=True, regularize=True)
+        U, S, Vh, _rank = eng.svd_truncate(sigma, getattr(cfg, "p_svd", P_SVD), keepdim=True, regularize=True)
         Asite = SiteCoef(eng.absorb("B", U, pair[0].data), "A", n - 1)
         Bsite = SiteCoef(eng.absorb("A", Vh, pair[1].data), "B", n)
         self.joint_sigvec = S

@@ -203,17 +203,17 @@ class Simulator:
                          backup_interval, autocorr=autocorr, energy=energy, norm=norm, populations=populations,
                          observables=observables, thresh_sil=thresh_sil, integrator=integrator,
                          display_time_unit=display_time_unit, conserve_norm=conserve_norm, write_files=write_files,
-                         record_trace=record_trace, suffix="_prop", adaptive=adaptive,
+                         record_trace=record_trace, suffix="_prop", adaptive=adaptive, p_svd=adaptive_p_svd,
                          per_step=(autocorr_per_step, energy_per_step, norm_per_step, populations_per_step, observables_per_step))
 
     def _run(self, stepsize_fs, maxstep, relax, restart, savefile_ext, loadfile_ext, backup_interval, *, autocorr, energy,
              norm, populations, observables, thresh_sil, integrator, display_time_unit, conserve_norm, write_files,
-             record_trace, suffix, adaptive=False, per_step=(1, 1, 1, 1, 1)):
+             record_trace, suffix, adaptive=False, p_svd=1.0e-07, per_step=(1, 1, 1, 1, 1)):
         autocorr_per_step, energy_per_step, norm_per_step, populations_per_step, observables_per_step = per_step
         stepsize_au = stepsize_fs / units.au_in_fs
         cfg = RunConfig(jobname=self.jobname + suffix, relax=relax, maxstep=maxstep, thresh_exp=thresh_sil,
                         verbose=self.verbose, space=self.model.space, integrator=integrator, conserve_norm=conserve_norm,
-                        display_time_unit=display_time_unit, adaptive=adaptive)
+                        display_time_unit=display_time_unit, adaptive=adaptive, p_svd=p_svd)
         self.cfg = cfg
         split = getattr(self, "_split", None) if not relax else None
         if split is not None:
