@@ -220,8 +220,12 @@ def cpu_baseline(wl, stats: dict, repeats: int = 1) -> dict:
     n_H = max(1, round(stats["avg_matvecs_H"]))
     n_K = max(1, round(stats["avg_matvecs_K"]))
     best = None
-    for _ in range(repeats):
+    nrun = 0
+    while nrun < repeats or (best[0] < 2.0 and nrun < 5):
+        # samples shorter than 2 s (D <= 64 workloads) are repeated and the fastest kept: the first pass pays the
+        # BLAS thread-pool start-up and einsum path search that a long reference run amortises
         sec, flops, info = cpu_site_update_sample(wl, n_H, n_K)
+        nrun += 1
         if best is None or sec < best[0]:
             best = (sec, flops, info)
     sec, flops, info = best
