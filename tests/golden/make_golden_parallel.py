@@ -18,6 +18,7 @@ CASES = {
     "par_exciton_P2": ("exciton", 2, [(0, 1), (2, 3)], 10, 0.05, 6),
     "par_hh8_P2": ("hh8", 2, [(0, 3), (4, 7)], 6, 0.05, 4),
     "par_hh8_P4": ("hh8", 4, [(0, 1), (2, 3), (4, 5), (6, 7)], 6, 0.05, 4),
+    "par_hh8_P3": ("hh8", 3, [(0, 1, 2), (3, 4), (5, 6, 7)], 6, 0.05, 4),     # odd rank count, uneven segments
     # well-conditioned cases: an entangled random initial MPS that saturates every bond (no null space for the
     # boundary pseudo-inverse / regularised SVD to amplify), so independent implementations can agree to 1e-10
     "par_frenkel8_P2": ("frenkel8", 2, [(0, 1, 2, 3), (4, 5, 6, 7)], 4, 0.2, 10),
@@ -143,7 +144,7 @@ def driver():
                 for r, o in enumerate(outs):
                     print(f"--- rank {r} rc={procs[r].returncode}\n{o[-3000:]}")
                 raise SystemExit(f"{case}: a rank failed")
-            merged = {"nranks": np.array(P), "split": np.array(split), "bond_dim": np.array(D), "dt_fs": np.array(dt_fs),
+            merged = {"nranks": np.array(P), "split": np.array([(seg[0], seg[-1]) for seg in split]), "bond_dim": np.array(D), "dt_fs": np.array(dt_fs),
                       "nstep": np.array(nstep), "model": np.array(model_name)}
             for r in range(P):
                 z = np.load(os.path.join(tmp, f"rank{r}.npz"))
