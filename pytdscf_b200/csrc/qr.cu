@@ -343,14 +343,20 @@ __global__ void __launch_bounds__(CT, 1) k_qr_panel_cluster(PanelArgs p) {
     const c128 tau = {s_zl[0], s_zl[1]}, sc = {s_zl[2], s_zl[3]};
     const double hbeta = s_zl[4];
     const bool trivial = (tau.x == 0.0 && tau.y == 0.0);
-    c128 wv = {0.0, 0.0};
+    // a_ij -= conj(tau) v_i w_j with v_i = s a_ic (v = 1 on the diagonal row), w_j = a_cj + conj(s) g_j.  The products
+    // that do not depend on the row are formed once per column and thread: y_j = conj(tau) s w_j (rows below the
+    // diagonal) and yd_j = conj(tau) w_j (diagonal row); the slab pass then costs one complex multiply-add per element
+    // (the panel kernel is bound by the plain FP64 pipe, 2 warp instructions per clock per SM).
+    c128 yj = {0.0, 0.0}, ydj = {0.0, 0.0};
     if (tx > c && tx < jb) {
       const c128 cs = {sc.x, -sc.y};
-      wv = cadd(rowc[tx], cmul(cs, gtot[tx]));               // w_j = a_cj + conj(s) g_j
+      const c128 wv = cadd(rowc[tx], cmul(cs, gtot[tx]));
+      const c128 ctau = {tau.x, -tau.y};
+      ydj = cmul(ctau, wv);
+      yj = cmul(sc, ydj);
     }
-    // apply H^H = I - conj(tau) v v^H to the remaining columns, store v / beta in column c, and in the same pass
-    // accumulate the next column's partial g (lane c+1 holds the freshly updated a_{i,c+1})
-    const c128 ctau = {tau.x, -tau.y};
+    // apply H^H to the remaining columns, store v / beta in column c, and in the same pass accumulate the next column's
+    // partial g (lane c+1 holds the freshly updated a_{i,c+1})
     acc = {0.0, 0.0};
     const int cn = (c + 1 < NB) ? c + 1 : c;
     for (int i = ty; i < nrow; i += CTY) {
@@ -358,15 +364,13 @@ __global__ void __launch_bounds__(CT, 1) k_qr_panel_cluster(PanelArgs p) {
       if (gr < grow) continue;                               // uniform per warp (ty selects the row)
       c128 mine = S[i * NB + tx];
       if (!trivial) {
-        c128 v;
-        if (gr == grow) v = {1.0, 0.0};
-        else v = cmul(S[i * NB + c], sc);
+        const c128 x = S[i * NB + c];
         if (tx > c && tx < jb) {
-          const c128 f = cmul(ctau, cmul(v, wv));
+          const c128 f = (gr == grow) ? ydj : cmul(x, yj);
           mine.x -= f.x;
           mine.y -= f.y;
         }
-        if (tx == c) mine = (gr == grow) ? c128{hbeta, 0.0} : v;
+        if (tx == c) mine = (gr == grow) ? c128{hbeta, 0.0} : cmul(x, sc);
         __syncwarp();                                        // every lane has read S[i][c] before lane c overwrites it
         if (tx >= c) S[i * NB + tx] = mine;
       }
@@ -543,7 +547,8 @@ int qr_factor(Handle* h, c128* A, int m, int n, int lda, c128* Q, int ldq) {
     if (max_cluster >= 1 && mp <= max_cluster * CL_ROWS) {
       // one cluster owns the panel: pick the smallest power-of-two cluster that keeps <= 128 rows per CTA if possible
       int G = 1;
-      while (G < max_cluster && (mp + G - 1) / G > 128) G *= 2;
+      static const int rows_target = getenv("TDVP_QR_ROWS") ? atoi(getenv("TDVP_QR_ROWS")) : 64;    // tuning knob (sweep: scripts/debug/qr_timing.py)
+      while (G < max_cluster && (mp + G - 1) / G > rows_target) G *= 2;
       while ((mp + G - 1) / G > CL_ROWS) G *= 2;
       const int rpc = (mp + G - 1) / G;
       PanelArgs pa{A, lda, m, n, j0, jb, tau, Vall, Tall, gpart, zpart, rpc, qr_dbg};

@@ -32,5 +32,10 @@ if len(sys.argv) > 1:
         print(f"dbg={os.environ.get('TDVP_QR_DEBUG', '0')} shape=({Dl},{d},{Dr}) qr_shift {e0.elapsed_time(e1) / 20 * 1e3:8.1f} us   "
               f"panel kernel {pan['ms'] / pan['launches'] * 1e3:7.1f} us x {pan['launches'] // 20} per shift", flush=True)
 else:
-    for dbg in ("0", "1", "2", "3"):
-        subprocess.run([sys.executable, os.path.abspath(__file__), "run"], env=dict(os.environ, TDVP_QR_DEBUG=dbg), check=False)
+    if os.environ.get("QR_SWEEP_ROWS"):
+        for rows in ("64", "128", "256", "384"):
+            print("TDVP_QR_ROWS =", rows, flush=True)
+            subprocess.run([sys.executable, os.path.abspath(__file__), "run"], env=dict(os.environ, TDVP_QR_ROWS=rows), check=False)
+    else:
+        for dbg in ("0", "1", "2", "3"):
+            subprocess.run([sys.executable, os.path.abspath(__file__), "run"], env=dict(os.environ, TDVP_QR_DEBUG=dbg), check=False)
