@@ -263,3 +263,64 @@ def test_host_kraus_logic(case, tmp_path):
         assert abs(e - row[3]) < 1e-12 and abs(n - row[5]) < 1e-12
     np.testing.assert_allclose(rho, ref, atol=1e-12)
     assert [s.shape for s in wf.ci_coef.sites] == [c.shape for c in g["final"]]
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_identity_channels_on_random_sum_of_products(seed):
+    """Random sum-of-products operators -> sop_to_mpo -> DeviceMPO with channel re-ordering: the flagged channels are the
+    ends of every bond, their environment blocks are unit matrices for a canonical random MPS, and <psi|H|psi> through the
+    (re-ordered) MPO equals the dense value."""
+    import pytdscf_b200 as tb
+    from pytdscf_b200._mps_cuda import DeviceMPO, MPSCoefCuda
+    from pytdscf_b200.mpo_tools import sop_to_dense, sop_to_mpo
+
+    rng = np.random.default_rng(seed)
+    dims = [2, 3, 2, 3, 2]
+    n = len(dims)
+
+    def rop(d):
+        m = rng.standard_normal((d, d)) + 1j * rng.standard_normal((d, d))
+        return m + m.conj().T
+
+    terms = [(rng.standard_normal(), {p: rop(dims[p])}) for p in range(n)]
+    for _ in range(6):
+        a, b = sorted(rng.choice(n, 2, replace=False))
+        terms.append((rng.standard_normal(), {int(a): rop(dims[a]), int(b): rop(dims[b])}))
+    cores = sop_to_mpo(dims, terms)
+    basis = [tb.Exciton(nstate=d) for d in dims]
+    model = tb.Model(basis, {"hamiltonian": cores}, bond_dim=4)
+    eng = OracleEngine()
+    eng.reorder_mpo_channels = True
+    H = DeviceMPO(eng, model.hamiltonian)
+    flagged = 0
+    for terms_p in H.calc_point:
+        for t in terms_p:
+            assert t.core.l_id in (-1, 0) and t.core.r_id in (-1, t.core.wr - 1)
+            flagged += (t.core.l_id >= 0) + (t.core.r_id >= 0)
+    assert flagged >= 2 * (n - 2)
+    # random MPS, right-canonical around site 0
+    from pytdscf_b200._mps_cuda import bond_dims
+
+    tens = []
+    for i in range(n):
+        ml, mr = bond_dims(dims, i, 4)
+        tens.append(eng.to_device(rng.standard_normal((1 if i == 0 else ml, dims[i], 1 if i == n - 1 else mr))
+                                  + 1j * rng.standard_normal((1 if i == 0 else ml, dims[i], 1 if i == n - 1 else mr))))
+    for i in range(n - 1, 0, -1):
+        B, sig = eng.qr_shift("B", tens[i])
+        tens[i] = B
+        tens[i - 1] = eng.absorb("B", sig, tens[i - 1])
+    tens[0] = tens[0] / np.sqrt(eng.inner(tens[0], tens[0], True).real)
+    mps = MPSCoefCuda(eng, tens)
+    right = mps.construct_op_sites(n - 1, 0, H)
+    for p in range(n - 1):
+        for t in H.calc_point[p]:
+            if t.core.r_id >= 0 and t.key in right[n - 1 - p]:
+                E = right[n - 1 - p][t.key].numpy()
+                np.testing.assert_allclose(E[:, t.core.r_id, :], np.eye(E.shape[0]), atol=1e-12)
+    v = np.asarray(tens[0].numpy())[0]
+    for c in tens[1:]:
+        v = np.tensordot(v, c.numpy(), axes=(v.ndim - 1, 0))
+    v = v.reshape(-1)
+    dense = sop_to_dense(dims, terms)
+    assert abs(mps.expectation(H) - np.vdot(v, dense @ v)) < 1e-11 * max(1.0, np.abs(dense).max())
