@@ -102,6 +102,11 @@ int tdvp_env_update(tdvp_handle_t h, int gauge, int Dl, int d, int Dr, const tdv
  * n_warmup, stop on |psi_k - psi_{k-1}| < thresh or beta < 1e-12 or k == size, conserve_norm handling.
  * Exactly one of (hterms, kterms) is non-NULL: H_eff on (Dl,d,Dr) or K_eff on (Dl,Dr) with d ignored.
  * niter receives the number of Krylov vectors used (the reference's _Debug.niter_krylov entry). */
+/* Adaptive bond growth (pytdscf/_contraction.py:479-608 `stack(extend=True)` / `split(truncate=True)`): the next
+ * tdvp_krylov_expm call runs on a zero-extended tensor but sizes its Krylov space (cap min(20, size), warm-up bound,
+ * "space exhausted" test) by `size`, the number of elements of the tensor before extension, as the reference does
+ * (pytdscf/_integrator.py:178-186).  One-shot: reset by the solve; 0 clears it. */
+int tdvp_set_krylov_size(tdvp_handle_t h, long long size);
 int tdvp_krylov_expm(tdvp_handle_t h, int kind, double scale_re, double scale_im, double thresh,
                      int n_warmup, int conserve_norm, const tdvp_heff_term* hterms,
                      const tdvp_keff_term* kterms, int nterms, int Dl, int d, int Dr,

@@ -70,14 +70,15 @@ class OracleEngine:
             return out
         return self._wrap(res)
 
-    def krylov_expm(self, kind, scale, thresh, n_warmup, conserve_norm, psi, *, hterms=None, kterms=None):
+    def krylov_expm(self, kind, scale, thresh, n_warmup, conserve_norm, psi, *, hterms=None, kterms=None, size_override=None):
         last = n_warmup + 2 if n_warmup > 0 else 0
         if hterms is not None:
             mv = lambda x: self.heff_apply(hterms, self._wrap(x)).numpy()  # noqa: E731
         else:
             mv = lambda x: self.keff_apply(kterms, self._wrap(x)).numpy()  # noqa: E731
         solver = orc.sia_reference if kind == "arnoldi" else orc.sil_reference
-        y, n = solver(complex(scale), mv, psi.numpy().copy(), thresh, last_niter=last, conserve_norm=conserve_norm)
+        y, n = solver(complex(scale), mv, psi.numpy().copy(), thresh, last_niter=last, conserve_norm=conserve_norm,
+                      maxsize=size_override)
         psi.copy_(self._wrap(y))
         self._stats["solves"] += 1
         self._stats["matvecs"] += n

@@ -242,12 +242,12 @@ def _rescale(y, b0, conserve_norm):
     return y * b0
 
 
-def sil_reference(scale, matvec, psi, thresh, *, last_niter=0, conserve_norm=True):
+def sil_reference(scale, matvec, psi, thresh, *, last_niter=0, conserve_norm=True, maxsize=None):
     """exp(scale*H) psi by the reference's three-term recurrence (alpha_l = <v0|H v_l>).
 
     ``matvec`` maps an array of ``psi.shape`` to one of the same shape.  Returns (psi_new, niter)."""
     shape = psi.shape
-    maxsize = psi.size
+    maxsize = psi.size if maxsize is None else int(maxsize)   # adaptive runs: size of the tensor before it was extended
     ndim, n_warm = krylov_warmup(maxsize, last_niter)
     v0 = psi.reshape(-1).astype(np.complex128, copy=True)
     if conserve_norm:
@@ -309,10 +309,10 @@ def sil_reference(scale, matvec, psi, thresh, *, last_niter=0, conserve_norm=Tru
     raise ValueError("Short Iterative Lanczos is not converged")
 
 
-def sia_reference(scale, matvec, psi, thresh, *, last_niter=0, conserve_norm=True):
+def sia_reference(scale, matvec, psi, thresh, *, last_niter=0, conserve_norm=True, maxsize=None):
     """Arnoldi variant: one-pass classical Gram-Schmidt, dense eig of the Hessenberg block."""
     shape = psi.shape
-    maxsize = psi.size
+    maxsize = psi.size if maxsize is None else int(maxsize)
     ndim, n_warm = krylov_warmup(maxsize, last_niter)
     hess = np.zeros((ndim + 1, ndim), dtype=np.complex128)
     v0 = psi.reshape(-1).astype(np.complex128, copy=True)

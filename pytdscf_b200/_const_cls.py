@@ -20,6 +20,9 @@ class RunConfig:
     display_time_unit: str = "fs"
     time_au_init: float = 0.0
     adaptive: bool = False
+    Dmax: int = 20       # adaptive_Dmax
+    dD: int = 5          # adaptive_dD
+    p_proj: float = 1.0e-04  # adaptive_p_proj
     p_svd: float = 1.0e-07  # adaptive_p_svd: truncation weight of the site-parallel boundary bond (reference const.p_svd)
 
     def __post_init__(self):
@@ -31,5 +34,5 @@ class RunConfig:
             raise ValueError(f"Invalid integrator: {self.integrator}")
         if self.space == "liouville":  # _const_cls.py:219-224
             self.conserve_norm = False
-        if self.adaptive:
-            raise NotImplementedError("adaptive (A1TDVP) bond dimensions are not implemented in backend='cuda' yet")
+        if self.adaptive and self.relax:
+            raise NotImplementedError("adaptive bond dimensions are implemented for real-time propagation only")

@@ -185,9 +185,12 @@ class Engine:
 
     # -- Krylov ------------------------------------------------------------------------
     def krylov_expm(self, kind: str, scale: complex, thresh: float, n_warmup: int, conserve_norm: bool,
-                    psi: torch.Tensor, *, hterms=None, kterms=None) -> int:
-        """psi <- exp(scale*Op) psi in place; returns the number of Krylov vectors used."""
+                    psi: torch.Tensor, *, hterms=None, kterms=None, size_override: int | None = None) -> int:
+        """psi <- exp(scale*Op) psi in place; returns the number of Krylov vectors used.  ``size_override``: number of
+        elements of the tensor before it was zero-extended (adaptive bond growth, see ``tdvp_set_krylov_size``)."""
         _chk_tensor(psi, "psi")
+        if size_override is not None:
+            check(self.h, self.lib.tdvp_set_krylov_size(self.h, int(size_override)))
         k = _lib.KRYLOV_ARNOLDI if kind == "arnoldi" else _lib.KRYLOV_LANCZOS_REF
         niter = C.c_int(0)
         scale = complex(scale)

@@ -61,6 +61,7 @@ SIGNATURES = {
     "tdvp_keff_apply": (C.c_int, [C.c_void_p, C.POINTER(KeffTerm), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "tdvp_env_update": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]),
+    "tdvp_set_krylov_size": (C.c_int, [C.c_void_p, C.c_longlong]),
     "tdvp_krylov_expm": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
                                    C.POINTER(HeffTerm), C.POINTER(KeffTerm), C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_void_p, C.POINTER(C.c_int)]),

@@ -382,7 +382,16 @@ class MPSCoefCuda:
     def _n_warmup(self, size: int, site: int) -> int:
         return min(size, min(max(0, self.niter_krylov.get(site, 0) - 2), 15))
 
-    def _expm(self, cfg, sign: complex, dt: float, x: torch.Tensor, site: int, kind: int, **terms) -> torch.Tensor:
+    def _expm(self, cfg, sign: complex, dt: float, x: torch.Tensor, site: int, kind: int, shape_out=None, **terms) -> torch.Tensor:
+        """``shape_out`` (adaptive bond growth): the tensor is zero-extended to that shape before the solve and the
+        blocks of ``hterms`` are padded to square, which is the reference's stack(extend) / split(truncate) operator."""
+        size_override = None
+        if shape_out is not None and tuple(shape_out) != tuple(x.shape):
+            from ._adaptive import _square_terms_h, pad_to
+
+            size_override = x.numel()
+            terms = dict(terms, hterms=_square_terms_h(terms["hterms"], shape_out[0], shape_out[2]))
+            x = pad_to(x, tuple(shape_out))
         if cfg.relax == "improved":
             # improved relaxation: eigenvector of H_eff per site, the bond (K) step is skipped (_mps_cls.py:1078-1084, 1159-1160)
             if kind == 1:
@@ -393,8 +402,10 @@ class MPSCoefCuda:
             if self.record_trace:
                 self.trace.append((kind, site, niter))
             return y
-        n_warm = self._n_warmup(x.numel(), site)
+        n_warm = self._n_warmup(x.numel() if size_override is None else size_override, site)
         y = x.clone()
+        if size_override is not None:
+            terms = dict(terms, size_override=size_override)
         if cfg.relax:
             # imaginary time: exp(-H dt/2) on sites, exp(+K dt/2) on bonds, always the Lanczos variant (_mps_cls.py:1086-1094)
             scale = (sign * -1j).real * (dt / 2)
@@ -412,6 +423,7 @@ class MPSCoefCuda:
         eng = self.eng
         A_is_sys = begin_site <= end_site
         step = 1 if A_is_sys else -1
+        to = "->" if A_is_sys else "<-"
         sites = self.sites
         op_sys = self.construct_op_zerosite() if op_sys_initial is None else op_sys_initial
         if self.op_sys_sites is None:
@@ -419,13 +431,34 @@ class MPSCoefCuda:
         else:
             env_sites = self.op_sys_sites[:]
         self.op_sys_sites = [op_sys]
+        adaptive = bool(getattr(cfg, "adaptive", False))
+        if adaptive:
+            from . import _adaptive as ad
+
+            full = ad.get_superblock_full(eng, sites, cfg.dD)      # neighbours with up to dD complement directions
         for p in range(begin_site, end_site + step, step):
             if skip_end_site and p == end_site:
                 return op_sys   # before site_now is touched, as in the reference (_mps_cls.py:878-880)
             self.site_now = p
             op_env = env_sites.pop()
+            shape_out = None
+            grown = False
+            if adaptive and p != end_site:
+                L, C, R = sites[p].shape
+                if A_is_sys:
+                    R = sites[p + 1].shape[0]
+                else:
+                    L = sites[p - 1].shape[2]
+                if not ad.is_max_rank(sites[p], to, cfg.Dmax):
+                    grown = True
+                    newD, _err, op_env, op_env_braket = ad.get_adaptive_rank_and_block(self, p, full, env_sites[-1], H, to, cfg)
+                    if A_is_sys:
+                        R = newD
+                    else:
+                        L = newD
+                shape_out = (L, C, R)
             hterms = self.operators_for_superH(p, op_sys, op_env, H, A_is_sys)
-            psi = self._expm(cfg, -1.0j, dt, sites[p].data, p, 0, hterms=hterms)
+            psi = self._expm(cfg, -1.0j, dt, sites[p].data, p, 0, shape_out=shape_out, hterms=hterms)
             sites[p] = SiteCoef(psi, "Psi", p)
             if p == end_site:
                 break
@@ -433,6 +466,8 @@ class MPSCoefCuda:
             new_site, sigma = eng.qr_shift(gauge, psi)
             sites[p] = SiteCoef(new_site, gauge, p)
             op_sys = self.renormalize_op_psite(p, op_sys, H, A_is_sys)
+            if grown:
+                op_env = op_env_braket
             kterms = self.operators_for_superK(op_sys, op_env, H, A_is_sys, bond=p + 1 if A_is_sys else p)
             sigma = self._expm(cfg, +1.0j, dt, sigma, p, 1, kterms=kterms)
             q = p + step

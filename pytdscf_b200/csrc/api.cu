@@ -161,6 +161,13 @@ int tdvp_env_update(tdvp_handle_t h, int gauge, int Dl, int d, int Dr, const tdv
                          w_kind, w_out, (c128*)out, accumulate != 0);
 }
 
+int tdvp_set_krylov_size(tdvp_handle_t hh, long long size) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || size < 0) return TDVP_ERR_ARG;
+  h->krylov_size_override = size;
+  return 0;
+}
+
 int tdvp_krylov_expm(tdvp_handle_t h, int kind, double scale_re, double scale_im, double thresh, int n_warmup,
                      int conserve_norm, const tdvp_heff_term* hterms, const tdvp_keff_term* kterms, int nterms, int Dl,
                      int d, int Dr, tdvp_c128* psi_inout, int* niter) {

@@ -24,6 +24,7 @@ struct Handle {
   // statistics
   unsigned long long krylov_matvecs = 0;
   unsigned long long krylov_solves = 0;
+  long long krylov_size_override = 0;   // > 0: size of the un-extended tensor (adaptive TDVP), consumed by the next solve
   double heff_flops = 0.0;  // algorithmic flops of H_eff/K_eff/env contractions issued (SURVEY 8(d) formulas)
 };
 

@@ -501,9 +501,14 @@ int krylov_expm_exec(Handle* h, int kind, double scale_re, double scale_im, doub
   const bool isH = hterms != nullptr;
   const long long N = isH ? (long long)Dl * d * Dr : (long long)Dl * Dr;
   if (N <= 0) { set_error(h, "krylov_expm: empty vector"); return TDVP_ERR_SHAPE; }
-  const int ndim = (int)(N < KCAP ? N : KCAP);
+  // The reference sizes the Krylov space (cap, warm-up bound, "space exhausted" test) by the tensor it was GIVEN; with
+  // adaptive bond growth that tensor is smaller than the zero-extended vector the recurrence runs on
+  // (_integrator.py:178-186, 524, 570): tdvp_set_krylov_size passes that size for the next solve.
+  const long long Nref = (h->krylov_size_override > 0 && h->krylov_size_override < N) ? h->krylov_size_override : N;
+  h->krylov_size_override = 0;
+  const int ndim = (int)(Nref < KCAP ? Nref : KCAP);
   int n_warm = n_warmup;
-  if (n_warm > N) n_warm = (int)N;
+  if (n_warm > Nref) n_warm = (int)Nref;
   if (n_warm < 0) n_warm = 0;
 
   // ---- workspace: V[(ndim+1) x N], y, prev, + contraction scratch ----
@@ -574,7 +579,7 @@ int krylov_expm_exec(Handle* h, int kind, double scale_re, double scale_im, doub
     // Warm-up iterations (the reference skips the Ritz step there, _integrator.py:560-575) need nothing on the host:
     // the beta values are read back together with the first convergence scalar, so the stream keeps running ahead.
     // A breakdown (beta < eps) inside the warm-up is detected at that read-back and replayed from the stored basis.
-    if (l < n_warm && (long long)(l + 1) < N) {
+    if (l < n_warm && (long long)(l + 1) < Nref) {
       if (kind == TDVP_KRYLOV_ARNOLDI) ++nvec;    // speculative: beta > eps (checked below)
       continue;
     }
@@ -616,7 +621,7 @@ int krylov_expm_exec(Handle* h, int kind, double scale_re, double scale_im, doub
     }
     synced = l + 1;
     const double beta = h->h_scal[S_BETA + l];
-    const bool conv = beta < EPS_K || (long long)(l + 1) == N;
+    const bool conv = beta < EPS_K || (long long)(l + 1) == Nref;
     if (kind == TDVP_KRYLOV_ARNOLDI && beta > EPS_K) ++nvec;
     const bool done = conv || (have_prev && h->h_scal[S_ERR] < thresh);
     if (done) return finish(y, l + 1);

@@ -196,7 +196,7 @@ class Simulator:
         if parallel_split_indices is not None:
             # reference: one MPI rank per tuple of consecutive sites (simulator_cls.py:243-249, _const_cls.py:236-251);
             # here one torch.distributed rank (= one GPU) per tuple, launched by torchrun
-            if adaptive or restart or self.model.one_gate_to_apply is not None or self.model.kraus_op is not None:
+            if adaptive or restart or self.model.one_gate_to_apply is not None or self.model.kraus_op is not None:  # noqa: SIM102
                 raise NotImplementedError("site-parallel propagation supports neither adaptive bond dimensions, restart nor gates")
             self._split = [tuple(int(i) for i in seg) for seg in parallel_split_indices]
         return self._run(Δt if Δt is not None else stepsize, maxstep, False, restart, savefile_ext, loadfile_ext,
@@ -204,16 +204,18 @@ class Simulator:
                          observables=observables, thresh_sil=thresh_sil, integrator=integrator,
                          display_time_unit=display_time_unit, conserve_norm=conserve_norm, write_files=write_files,
                          record_trace=record_trace, suffix="_prop", adaptive=adaptive, p_svd=adaptive_p_svd,
+                         adaptive_params=(adaptive_Dmax, adaptive_dD, adaptive_p_proj),
                          per_step=(autocorr_per_step, energy_per_step, norm_per_step, populations_per_step, observables_per_step))
 
     def _run(self, stepsize_fs, maxstep, relax, restart, savefile_ext, loadfile_ext, backup_interval, *, autocorr, energy,
              norm, populations, observables, thresh_sil, integrator, display_time_unit, conserve_norm, write_files,
-             record_trace, suffix, adaptive=False, p_svd=1.0e-07, per_step=(1, 1, 1, 1, 1)):
+             record_trace, suffix, adaptive=False, p_svd=1.0e-07, adaptive_params=(20, 5, 1.0e-04), per_step=(1, 1, 1, 1, 1)):
         autocorr_per_step, energy_per_step, norm_per_step, populations_per_step, observables_per_step = per_step
         stepsize_au = stepsize_fs / units.au_in_fs
         cfg = RunConfig(jobname=self.jobname + suffix, relax=relax, maxstep=maxstep, thresh_exp=thresh_sil,
                         verbose=self.verbose, space=self.model.space, integrator=integrator, conserve_norm=conserve_norm,
-                        display_time_unit=display_time_unit, adaptive=adaptive, p_svd=p_svd)
+                        display_time_unit=display_time_unit, adaptive=adaptive, p_svd=p_svd, Dmax=int(adaptive_params[0]),
+                        dD=int(adaptive_params[1]), p_proj=float(adaptive_params[2]))
         self.cfg = cfg
         split = getattr(self, "_split", None) if not relax else None
         if split is not None:

@@ -58,10 +58,11 @@ class CheckedEngine:
         self._rec("env_update", (res.cpu() - ref).abs().max() / max(1e-300, ref.abs().max()), (gauge, tuple(ket.shape)))
         return res
 
-    def krylov_expm(self, kind, scale, thresh, n_warmup, conserve_norm, psi, *, hterms=None, kterms=None):
+    def krylov_expm(self, kind, scale, thresh, n_warmup, conserve_norm, psi, *, hterms=None, kterms=None, size_override=None):
         x0 = _c(psi).clone()
-        n = self.eng.krylov_expm(kind, scale, thresh, n_warmup, conserve_norm, psi, hterms=hterms, kterms=kterms)
-        kw = {}
+        n = self.eng.krylov_expm(kind, scale, thresh, n_warmup, conserve_norm, psi, hterms=hterms, kterms=kterms,
+                                 size_override=size_override)
+        kw = {"size_override": size_override}
         if hterms is not None:
             kw["hterms"] = [(_c(L), _core(c), _c(R), k) for L, c, R, k in hterms]
         else:

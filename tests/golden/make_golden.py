@@ -119,7 +119,7 @@ def _skip(name):
 
 
 def run_reference(name, basis, operators, *, bond_dim, hartree, dt_fs, nstep, space="hilbert",
-                  integrator="lanczos", conserve_norm=True, vibstate=None, thresh_sil=1e-9, relax=None, gates=None):
+                  integrator="lanczos", conserve_norm=True, vibstate=None, thresh_sil=1e-9, relax=None, gates=None, adaptive=None):
     """Run Simulator.propagate and dump inputs + outputs to tests/golden/<name>.npz.
     ``gates``: {site: d x d matrix or length-d diagonal} applied once per step between the half sweeps
     (Model(one_gate_to_apply=...), pytdscf/_mps_cls.py:489-490, 2314-2373)."""
@@ -154,10 +154,12 @@ def run_reference(name, basis, operators, *, bond_dim, hartree, dt_fs, nstep, sp
             init = MPSCoefMPO.alloc_random(model)
             init_cores = [np.array(s.data) for s in init.superblock_states[0]]
             if relax is None:
+                akw = {} if adaptive is None else dict(adaptive=True, adaptive_Dmax=adaptive[0], adaptive_dD=adaptive[1],
+                                                       adaptive_p_proj=adaptive[2], adaptive_p_svd=adaptive[3])
                 ener, wf = sim.propagate(stepsize=dt_fs, maxstep=nstep, thresh_sil=thresh_sil,
                                          integrator=integrator, conserve_norm=conserve_norm,
                                          energy=(space == "hilbert"), autocorr=(space == "hilbert"),
-                                         norm=(space == "hilbert"), populations=False)
+                                         norm=(space == "hilbert"), populations=False, **akw)
             else:
                 import contextlib
                 import io
@@ -197,6 +199,8 @@ def run_reference(name, basis, operators, *, bond_dim, hartree, dt_fs, nstep, sp
             out[f"hartree{i}"] = np.asarray(h, dtype=np.complex128)
     for site, U in (gates or {}).items():
         out[f"gate{site}"] = np.asarray(U, dtype=np.complex128)
+    if adaptive is not None:
+        out["adaptive"] = np.array(adaptive, dtype=float)
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
     print(f"[golden] {name}: E_final={ener!r} steps={nstep} solves={len(RECORD['trace'])}")
 
@@ -488,6 +492,8 @@ def main():
     rot = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]], dtype=complex)   # kick on the exciton site
     phase = np.exp(1j * 0.05 * np.arange(8))                                               # diagonal gate on mode 1
     run_reference("gate_exciton_D6", prim, ops, bond_dim=6, hartree=hartree, dt_fs=0.1, nstep=5, gates={3: rot, 1: phase})
+    prim, ops, hartree = exciton_model()
+    run_reference("adaptive_exciton", prim, ops, bond_dim=1, hartree=hartree, dt_fs=0.1, nstep=6, adaptive=(8, 2, 1.0e-4, 1.0e-7))
     basis, ops, hartree = liouville_model()
     run_reference("liouville_spin3", basis, ops, bond_dim=8, hartree=hartree, dt_fs=2.0, nstep=5,
                   space="liouville", integrator="arnoldi")

@@ -83,8 +83,12 @@ def run_host(name, eps, seed):
             sim = tb.Simulator(name, _build_model(g), backend="cuda", verbose=0)
             sim.eng = eng
             sim.set_initial_mps(g["init"])
+            akw = {}
+            if g.get("adaptive"):
+                Dmax, dD, p_proj, p_svd = g["adaptive"]
+                akw = dict(adaptive=True, adaptive_Dmax=int(Dmax), adaptive_dD=int(dD), adaptive_p_proj=p_proj, adaptive_p_svd=p_svd)
             ener, wf = sim.propagate(stepsize=g["dt_au"] * tb.units.au_in_fs, maxstep=g["nstep"], populations=False,
-                                     write_files=False, record_trace=True)
+                                     write_files=False, record_trace=True, **akw)
         finally:
             os.chdir(cwd)
     return (np.array([r["autocorr"] for r in sim.history]), np.array([r["energy"] for r in sim.history]),
@@ -92,10 +96,10 @@ def run_host(name, eps, seed):
 
 
 def main():
-    from tests.golden_io import GATE_CASES
+    from tests.golden_io import ADAPTIVE_CASES, GATE_CASES
 
     out = {}
-    for name in GATE_CASES:
+    for name in GATE_CASES + ADAPTIVE_CASES:
         a0, e0, s0, t0 = run_host(name, 0.0, 0)
         fa = fe = fs = 0.0
         same_trace = True

@@ -31,7 +31,7 @@ def test_header_is_c_and_all_entry_points_link(tmp_path):
     exe = _build(str(tmp_path))
     out = subprocess.run([exe, "link-only"], capture_output=True, text=True, timeout=60)
     assert out.returncode == 0, out.stderr
-    assert "entry_points=22" in out.stdout
+    assert "entry_points=23" in out.stdout
 
 
 @pytest.mark.gpu

@@ -245,3 +245,20 @@ def test_kraus_map_gpu(case, tmp_path):
     for (e, n), row in zip(obs, g["props"], strict=True):
         assert abs(e - row[3]) <= REL * max(1.0, abs(row[3])) and abs(n - row[5]) <= REL
     np.testing.assert_allclose(rho, ref, atol=1e-10)
+
+
+def test_adaptive_tdvp_gpu(tmp_path):
+    """Rank-adaptive one-site TDVP on the device (square kernels on zero-padded operands, Householder completion for the
+    new bond directions, Krylov size override): same bond growth, Krylov trace and observables as the reference."""
+    from tests.golden_io import ADAPTIVE_CASES
+    from tests.test_host_sweep_cpu import run_adaptive
+
+    g = load_run(ADAPTIVE_CASES[0])
+    sim, ener, wf = run_adaptive(g, None, tmp_path, "_gpu")
+    assert [s.shape for s in wf.ci_coef.sites] == [c.shape for c in g["final"]]
+    assert (np.array(wf.ci_coef.trace) == g["trace"]).all()
+    tol = tolerances(g["name"])
+    for rec, row in zip(sim.history, g["props"], strict=True):
+        assert abs(rec["autocorr"] - complex(row[1], row[2])) <= tol["autocorr"]
+        assert abs(rec["energy"] - row[3]) <= tol["energy"] * abs(row[3]) and abs(rec["norm"] - row[5]) <= REL
+    assert_same_state(wf.ci_coef.to_numpy(), g["final"], tol["state"])

@@ -324,3 +324,36 @@ def test_identity_channels_on_random_sum_of_products(seed):
     v = v.reshape(-1)
     dense = sop_to_dense(dims, terms)
     assert abs(mps.expectation(H) - np.vdot(v, dense @ v)) < 1e-11 * max(1.0, np.abs(dense).max())
+
+
+def run_adaptive(g, eng, tmp_path, tag):
+    import pytdscf_b200 as tb
+
+    os.chdir(tmp_path)
+    sim = tb.Simulator(g["name"] + tag, _build_model(g), backend="cuda")
+    if eng is not None:
+        sim.eng = eng
+    sim.set_initial_mps(g["init"])
+    Dmax, dD, p_proj, p_svd = g["adaptive"]
+    ener, wf = sim.propagate(stepsize=g["dt_au"] * tb.units.au_in_fs, maxstep=g["nstep"], populations=False, record_trace=True,
+                             adaptive=True, adaptive_Dmax=int(Dmax), adaptive_dD=int(dD), adaptive_p_proj=p_proj,
+                             adaptive_p_svd=p_svd)
+    return sim, ener, wf
+
+
+def test_host_adaptive_logic(tmp_path):
+    """Rank-adaptive one-site TDVP (reference adaptive=True, starting from bond dimension 1): the product's host logic
+    with the oracle's kernels reproduces the reference's bond growth, Krylov trace and observables."""
+    from tests.golden_io import ADAPTIVE_CASES
+
+    g = load_run(ADAPTIVE_CASES[0])
+    sim, ener, wf = run_adaptive(g, OracleEngine(), tmp_path, "_cpu")
+    assert [s.shape for s in wf.ci_coef.sites] == [c.shape for c in g["final"]]
+    assert (np.array(wf.ci_coef.trace) == g["trace"]).all()
+    for rec, row in zip(sim.history, g["props"], strict=True):
+        assert abs(rec["autocorr"] - complex(row[1], row[2])) < 1e-11
+        assert abs(rec["energy"] - row[3]) < 1e-12 and abs(rec["norm"] - row[5]) < 1e-12
+    from tests.test_gpu_propagation import dense_state
+
+    a, b = dense_state(wf.ci_coef.to_numpy()), dense_state(g["final"])
+    assert np.abs(a - b).max() < 1e-10
