@@ -494,6 +494,8 @@ def main():
     run_reference("gate_exciton_D6", prim, ops, bond_dim=6, hartree=hartree, dt_fs=0.1, nstep=5, gates={3: rot, 1: phase})
     prim, ops, hartree = exciton_model()
     run_reference("adaptive_exciton", prim, ops, bond_dim=1, hartree=hartree, dt_fs=0.1, nstep=6, adaptive=(8, 2, 1.0e-4, 1.0e-7))
+    prims, ops, vib = henon_heiles_model(2000, 5.0e-2, 6, 5)
+    run_reference("adaptive_hh6", prims, ops, bond_dim=2, hartree=None, vibstate=vib, dt_fs=0.2, nstep=5, adaptive=(5, 3, 1.0e-6, 1.0e-7))
     basis, ops, hartree = liouville_model()
     run_reference("liouville_spin3", basis, ops, bond_dim=8, hartree=hartree, dt_fs=2.0, nstep=5,
                   space="liouville", integrator="arnoldi")

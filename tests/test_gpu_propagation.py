@@ -247,13 +247,13 @@ def test_kraus_map_gpu(case, tmp_path):
     np.testing.assert_allclose(rho, ref, atol=1e-10)
 
 
-def test_adaptive_tdvp_gpu(tmp_path):
+@pytest.mark.parametrize("case", ["adaptive_exciton", "adaptive_hh6"])
+def test_adaptive_tdvp_gpu(case, tmp_path):
     """Rank-adaptive one-site TDVP on the device (square kernels on zero-padded operands, Householder completion for the
     new bond directions, Krylov size override): same bond growth, Krylov trace and observables as the reference."""
-    from tests.golden_io import ADAPTIVE_CASES
     from tests.test_host_sweep_cpu import run_adaptive
 
-    g = load_run(ADAPTIVE_CASES[0])
+    g = load_run(case)
     sim, ener, wf = run_adaptive(g, None, tmp_path, "_gpu")
     assert [s.shape for s in wf.ci_coef.sites] == [c.shape for c in g["final"]]
     assert (np.array(wf.ci_coef.trace) == g["trace"]).all()

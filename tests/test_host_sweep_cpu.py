@@ -341,12 +341,11 @@ def run_adaptive(g, eng, tmp_path, tag):
     return sim, ener, wf
 
 
-def test_host_adaptive_logic(tmp_path):
-    """Rank-adaptive one-site TDVP (reference adaptive=True, starting from bond dimension 1): the product's host logic
-    with the oracle's kernels reproduces the reference's bond growth, Krylov trace and observables."""
-    from tests.golden_io import ADAPTIVE_CASES
-
-    g = load_run(ADAPTIVE_CASES[0])
+@pytest.mark.parametrize("case", ["adaptive_exciton", "adaptive_hh6"])
+def test_host_adaptive_logic(case, tmp_path):
+    """Rank-adaptive one-site TDVP (reference adaptive=True, starting from bond dimension 1 or 2): the product's host
+    logic with the oracle's kernels reproduces the reference's bond growth, Krylov trace and observables."""
+    g = load_run(case)
     sim, ener, wf = run_adaptive(g, OracleEngine(), tmp_path, "_cpu")
     assert [s.shape for s in wf.ci_coef.sites] == [c.shape for c in g["final"]]
     assert (np.array(wf.ci_coef.trace) == g["trace"]).all()
