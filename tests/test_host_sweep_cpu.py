@@ -356,3 +356,31 @@ def test_host_adaptive_logic(case, tmp_path):
 
     a, b = dense_state(wf.ci_coef.to_numpy()), dense_state(g["final"])
     assert np.abs(a - b).max() < 1e-10
+
+
+@pytest.mark.parametrize("gauge", ["A", "B"])
+def test_thin_to_full_matches_scipy_full_qr(gauge):
+    """``thin_to_full`` through the padded-matrix QR equals the reference's construction (scipy full QR, first columns
+    sign-aligned to the isometry, reference _site_cls.py:294-407) including the ORDER of the complement directions."""
+    import scipy.linalg
+
+    from pytdscf_b200._adaptive import thin_to_full
+    from pytdscf_b200._mps_cuda import SiteCoef
+
+    rng = np.random.default_rng(5)
+    eng = OracleEngine()
+    l, c, r, extra = (3, 4, 5, 2) if gauge == "A" else (5, 4, 3, 2)
+    if gauge == "A":
+        mat = np.linalg.qr(rng.standard_normal((l * c, r)) + 1j * rng.standard_normal((l * c, r)))[0]
+        data = mat.reshape(l, c, r)
+    else:
+        mat = np.linalg.qr(rng.standard_normal((c * r, l)) + 1j * rng.standard_normal((c * r, l)))[0]   # (c r) x l
+        data = np.ascontiguousarray(mat.T.reshape(l, c, r))
+    full = thin_to_full(eng, SiteCoef(eng.to_device(data), gauge, 0), extra).data.numpy()
+    Q, _ = scipy.linalg.qr(mat, mode="full")
+    n = mat.shape[1]
+    unflip = np.sign(np.sign(np.diag((mat.T.conj() @ Q)[:n, :n]).real) + 0.5)
+    Q = Q[:, : n + extra].copy()
+    Q[:, :n] *= unflip[None, :]
+    ref = Q.reshape(l, c, r + extra) if gauge == "A" else Q.T.reshape(l + extra, c, r)
+    np.testing.assert_allclose(full, ref, atol=1e-13)
