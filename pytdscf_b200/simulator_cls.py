@@ -247,6 +247,8 @@ class Simulator:
                 rec["pops"] = wf.pop_states()
             if observables and istep % observables_per_step == 0:
                 rec["expectations"] = {k: wf.expectation(op) for k, op in self.model.observables.items()}
+            if cfg.adaptive:
+                rec["bonddim"] = wf.bonddim()
             rd = getattr(self, "_rd", None)
             if rd is not None and not relax and istep % rd[2] == 0:
                 rec["reduced_densities"] = dict(zip(rd[0], wf.get_reduced_densities(rd[1]), strict=True))
@@ -289,7 +291,8 @@ class Simulator:
     def _open_files(self, cfg: RunConfig) -> dict:
         os.makedirs(cfg.jobname, exist_ok=True)
         return {name: _DatFile(os.path.join(cfg.jobname, fn)) for name, fn in
-                (("main", "main.log"), ("auto", "autocorr.dat"), ("pop", "populations.dat"), ("exp", "expectations.dat"))}
+                (("main", "main.log"), ("auto", "autocorr.dat"), ("pop", "populations.dat"), ("exp", "expectations.dat"))
+                + ((("bond", "bonddim.dat"),) if cfg.adaptive else ())}
 
     def _export(self, files: dict, cfg: RunConfig, rec: dict, elapsed: float):
         unit = cfg.display_time_unit
@@ -304,6 +307,10 @@ class Simulator:
             if first:
                 files["pop"].write(f"# time [{unit}]\t" + "\t".join(f"pop_{i}".ljust(11) for i in range(len(rec["pops"]))))
             files["pop"].write(f"{t:6.9f}\t" + "".join(f"{p:6.9f}\t" for p in rec["pops"]))
+        if "bonddim" in rec and "bond" in files:     # adaptive runs: properties.py:344-356
+            if first:
+                files["bond"].write(f"# time [{unit}]\t" + "\t".join(f"{i}" for i in range(len(rec["bonddim"]))))
+            files["bond"].write(f"{t:6.9f}\t" + "".join(f"{b}\t" for b in rec["bonddim"]))
         if rec.get("expectations"):
             if first:
                 files["exp"].write(f"# time [{unit}]\t" + "\t".join(str(k).ljust(11) for k in rec["expectations"]))

@@ -356,6 +356,10 @@ def test_host_adaptive_logic(case, tmp_path):
 
     a, b = dense_state(wf.ci_coef.to_numpy()), dense_state(g["final"])
     assert np.abs(a - b).max() < 1e-10
+    # bonddim.dat in the reference's layout, one row per step
+    lines = open(os.path.join(g["name"] + "_cpu_prop", "bonddim.dat")).read().splitlines()
+    assert lines[0].startswith("# time [fs]") and len(lines) == g["nstep"] + 1
+    assert [int(v) for v in lines[-1].split()[1:]] == sim.history[-1]["bonddim"]
 
 
 @pytest.mark.parametrize("gauge", ["A", "B"])
