@@ -375,6 +375,8 @@ int tdvp_pinv(tdvp_handle_t hh, int m, int n, const tdvp_c128* X, double rcond, 
       return ls(h, "k_pinv_diag");
     }
   }
+  // General (non-diagonal) input: only the very first step of a site-parallel run gets here.  U / Vh cannot live in the
+  // handle's bump workspace because svd_exec re-bases it (ws_reserve), hence the two explicit allocations on this cold path.
   c128 *U = nullptr, *Vh = nullptr;
   TDVP_CUDA(h, cudaMalloc((void**)&U, sizeof(c128) * (size_t)m * n));
   TDVP_CUDA(h, cudaMalloc((void**)&Vh, sizeof(c128) * (size_t)n * n));
