@@ -326,6 +326,12 @@ class Engine:
                                           B.shape[1], b.real, b.imag, _ptr(C_out), C_out.shape[1]))
         return C_out
 
+    GEMM_CFGS = {"auto": 0, "big": 1, "small": 2, "tiny": 3, "tma": 4}
+
+    def set_gemm_config(self, tile: str = "auto", splitk: int = 0, c_stream: int = 0):
+        """Force the GEMM tile configuration / split-K factor / evict-first stores (tests and tuning; see the header)."""
+        check(self.h, self.lib.tdvp_set_gemm_config(self.h, self.GEMM_CFGS[tile], int(splitk), int(c_stream)))
+
     # -- statistics ----------------------------------------------------------------------
     def stats(self) -> dict:
         s, m, f = C.c_ulonglong(0), C.c_ulonglong(0), C.c_double(0.0)

@@ -57,6 +57,7 @@ SIGNATURES = {
     "tdvp_reset_stats": (C.c_int, [C.c_void_p]),
     "tdvp_gemm_profile": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]),
     "tdvp_profile_json": (C.c_size_t, [C.c_char_p, C.c_size_t]),
+    "tdvp_set_gemm_config": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "tdvp_heff_apply": (C.c_int, [C.c_void_p, C.POINTER(HeffTerm), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "tdvp_keff_apply": (C.c_int, [C.c_void_p, C.POINTER(KeffTerm), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "tdvp_env_update": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -13,6 +13,8 @@ int lanczos_eigvec_exec(Handle* h, const tdvp_heff_term* hterms, int nterms, int
 int inner_exec(Handle* h, long long n, const c128* bra, const c128* ket, int conj, c128* host_out);
 int qr_shift_exec(Handle* h, int gauge, int Dl, int d, int Dr, const c128* psi, c128* site, c128* sigma);
 int absorb_exec(Handle* h, int gauge, int Dl, int d, int Dr, int k, const c128* sigma, const c128* site, c128* out);
+int qr_configure(Handle* h);
+int svd_configure(Handle* h);
 
 void set_error(Handle* h, const std::string& msg) {
   if (h) h->err = msg;
@@ -41,6 +43,21 @@ int ws_reserve(Handle* h, size_t bytes) {
   return 0;
 }
 
+int ws_grow_preserve(Handle* h, size_t bytes) {
+  if (bytes <= h->ws_bytes) return 0;
+  void* p = nullptr;
+  TDVP_CUDA(h, cudaMalloc(&p, bytes));
+  if (h->ws) {
+    cudaError_t e = cudaMemcpyAsync(p, h->ws, h->ws_top, cudaMemcpyDeviceToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) { cudaFree(p); return cuda_fail(h, e, "ws_grow_preserve copy", __FILE__, __LINE__); }
+    TDVP_CUDA(h, cudaFree(h->ws));
+  }
+  h->ws = (unsigned char*)p;
+  h->ws_bytes = bytes;
+  return 0;
+}
+
 void* ws_alloc(Handle* h, size_t bytes) {
   const size_t b = align256(bytes);
   if (h->ws_top + b > h->ws_bytes) return nullptr;
@@ -61,9 +78,9 @@ struct tdvp_handle_s : public tdvp::Handle {};
 
 extern "C" {
 
-int tdvp_abi_version(void) { return 1; }
+int tdvp_abi_version(void) { return 2; }
 
-unsigned long long tdvp_launch_count(void) { return tdvp::g_launch_count; }
+unsigned long long tdvp_launch_count(void) { return tdvp::launch_count(); }
 
 int tdvp_create(int device, void* cuda_stream, tdvp_handle_t* out) {
   if (!out) return TDVP_ERR_ARG;
@@ -84,7 +101,26 @@ int tdvp_create(int device, void* cuda_stream, tdvp_handle_t* out) {
   cudaMemsetAsync(h->d_counter, 0, 16 * sizeof(unsigned int), h->stream);
   cudaMemsetAsync(h->d_scal, 0, 4096 * sizeof(double), h->stream);
   memset(h->h_scal, 0, 4096 * sizeof(double));
+  // device limits and kernel attributes are per device: (re)applied for every handle, never cached per process
+  cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
+  h->gemm.stream = h->stream;
+  h->gemm.scratch = h->d_splitk;
+  h->gemm.scratch_elems = tdvp::SPLITK_SCRATCH_ELEMS;
+  h->gemm.num_sms = h->num_sms;
+  int rc = 0;
+  if ((e = tdvp::zgemm_configure_device()) != cudaSuccess) rc = (int)e;
+  if (!rc) rc = tdvp::qr_configure(h);
+  if (!rc) rc = tdvp::svd_configure(h);
+  if (rc) { tdvp_destroy(h); return rc; }
   *out = h;
+  return 0;
+}
+
+int tdvp_set_gemm_config(tdvp_handle_t h, int tile_cfg, int splitk, int c_stream) {
+  if (!h || tile_cfg < 0 || tile_cfg > 4 || splitk < 0 || splitk > 16 || c_stream < 0 || c_stream > 2) return TDVP_ERR_ARG;
+  h->gemm.force_cfg = tile_cfg;
+  h->gemm.force_splitk = splitk;
+  h->gemm.force_cstream = c_stream;
   return 0;
 }
 
@@ -224,7 +260,7 @@ int tdvp_zgemm(tdvp_handle_t h, int transA, int transB, int M, int N, int K, dou
   GemmDesc g = gemm_rowmajor(M, N, K, (const c128*)A, lda, transA != 0, transA == 2, (const c128*)B, ldb, transB != 0,
                              (c128*)C, ldc, c128{alpha_re, alpha_im}, c128{beta_re, beta_im});
   g.b_conj = transB == 2 ? 1 : 0;
-  cudaError_t e = zgemm_auto(g, h->stream, h->d_splitk, tdvp::SPLITK_SCRATCH_ELEMS);
+  cudaError_t e = zgemm_auto(g, h->gemm);
   if (e != cudaSuccess) return cuda_fail(h, e, "zgemm_launch", __FILE__, __LINE__);
   return 0;
 }

@@ -67,15 +67,27 @@ struct GemmDesc {
   int c_stream = 0;   // set by the launcher: outputs larger than half of L2 are stored with evict-first (st.global.cs)
 };
 
-// Launch the DMMA ZGEMM on `stream`.  Returns cudaGetLastError() of the launch.
-cudaError_t zgemm_launch(const GemmDesc& d, cudaStream_t stream);
-// GEMM with automatic split-K for shapes that would leave most of the 148 SMs idle (few output tiles, long K):
-// partial products go to `scratch` (scratch_elems complex128 available, may be null) and are combined in fixed
-// order by a second kernel, so results stay deterministic.
-cudaError_t zgemm_auto(const GemmDesc& d, cudaStream_t stream, c128* scratch, size_t scratch_elems);
+// Per-handle (= per-device) launch context of the GEMM: stream, split-K scratch, device limits and the test /
+// tuning overrides of tdvp_set_gemm_config (0 = automatic choice everywhere).
+struct GemmCtx {
+  cudaStream_t stream = nullptr;
+  c128* scratch = nullptr;       // split-K partial products (may be null: no split-K)
+  size_t scratch_elems = 0;
+  int num_sms = 148;
+  int force_cfg = 0;             // 1 big (128x64), 2 small (64x32), 3 tiny (32x32), 4 tma (persistent TMA-fed 128x64)
+  int force_splitk = 0;          // 1 = never split, S >= 2 = S chunks (where K and the scratch allow it)
+  int force_cstream = 0;         // 1 = evict-first stores of C always, 2 = never
+};
+// Per-device kernel attributes (dynamic shared memory limits): called by tdvp_create for every new handle.
+cudaError_t zgemm_configure_device();
+// GEMM with automatic tile configuration and split-K for shapes that would leave most of the SMs idle (few output
+// tiles, long K): partial products go to ctx.scratch and are combined in fixed order by a second kernel, so results
+// stay deterministic.  Returns cudaGetLastError() of the launch.
+cudaError_t zgemm_auto(const GemmDesc& d, const GemmCtx& ctx);
 constexpr size_t SPLITK_SCRATCH_ELEMS = size_t(18) << 20;  // 288 MiB of partial products
 // Number of kernel launches issued through this library since load (bench.py's gpu_launches claim).
-extern unsigned long long g_launch_count;
+void count_launch(unsigned long long n = 1);
+unsigned long long launch_count();
 // Per-launch CUDA-event timing (off by default; used by bench.py for the roofline and the per-kernel breakdown).
 // Every launch site brackets its kernel with prof_begin/prof_end on the launching stream; totals are kept per label.
 void prof_enable(bool on);

@@ -124,14 +124,14 @@ inline int grid_for(long long n, int threads, int cap = 148 * 8) {
 }
 
 int launch_check(Handle* h, const char* what) {
-  ++g_launch_count;
+  count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(h, e, what, __FILE__, __LINE__);
   return 0;
 }
 
 int gemm(Handle* h, const GemmDesc& g) {
-  cudaError_t e = zgemm_auto(g, h->stream, h->d_splitk, SPLITK_SCRATCH_ELEMS);
+  cudaError_t e = zgemm_auto(g, h->gemm);
   if (e != cudaSuccess) return cuda_fail(h, e, "zgemm_launch", __FILE__, __LINE__);
   return 0;
 }
@@ -163,7 +163,7 @@ int left_apply_skip(Handle* h, const c128* L, int D, int w, int skip, const c128
     cudaError_t e = cudaMemcpy2DAsync(C + (long long)skip * ncols, sizeof(c128) * (size_t)w * ncols, X, sizeof(c128) * (size_t)ncols,
                                       sizeof(c128) * (size_t)ncols, (size_t)D, cudaMemcpyDeviceToDevice, h->stream);
     if (e != cudaSuccess) return cuda_fail(h, e, "cudaMemcpy2DAsync(id channel)", __FILE__, __LINE__); }
-  ++g_launch_count;
+  count_launch();
   return 0;
 }
 

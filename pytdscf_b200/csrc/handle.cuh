@@ -21,6 +21,11 @@ struct Handle {
   double* d_partial = nullptr;  // reduction partials: 1024 blocks x 64 doubles
   unsigned int* d_counter = nullptr;  // "last block done" tickets
   c128* d_splitk = nullptr;           // split-K partial products (SPLITK_SCRATCH_ELEMS)
+  GemmCtx gemm;                       // stream + scratch + overrides handed to every zgemm_auto call
+  // device limits queried once per handle (tdvp_create), never per process
+  int num_sms = 148;
+  int qr_max_cluster = 0;             // largest cluster the device co-schedules for k_qr_panel_cluster (0: none)
+  int svd_max_blocks = 0;             // co-resident CTAs of k_jacobi_svd
   // statistics
   unsigned long long krylov_matvecs = 0;
   unsigned long long krylov_solves = 0;
@@ -30,6 +35,9 @@ struct Handle {
 
 // Make sure the workspace holds at least `bytes`; resets the bump pointer.
 int ws_reserve(Handle* h, size_t bytes);
+// Grow the workspace to at least `bytes` keeping its contents and the bump pointer (pointers into it move by the
+// difference of the base addresses).
+int ws_grow_preserve(Handle* h, size_t bytes);
 // Bump allocation inside the reserved workspace (256-byte aligned). nullptr if it does not fit.
 void* ws_alloc(Handle* h, size_t bytes);
 inline void ws_reset(Handle* h) { h->ws_top = 0; }

@@ -15,6 +15,8 @@
 // The host loop needs three scalars per iteration (beta_l, |y_k - y_{k-1}|, "alpha is real" flag); they are
 // read through a pinned mailbox with one stream synchronisation.  All vector arithmetic stays on device and
 // every reduction is a fixed-order two-level tree (deterministic run to run).
+#include <type_traits>
+
 #include "contract.cuh"
 
 namespace tdvp {
@@ -475,7 +477,7 @@ __global__ void k_store_beta_hess(double* hess, int l, const double* beta) {
 }
 
 int lc(Handle* h, const char* what) {
-  ++g_launch_count;
+  count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(h, e, what, __FILE__, __LINE__);
   return 0;
@@ -641,18 +643,28 @@ int lanczos_eigvec_exec(Handle* h, const tdvp_heff_term* hterms, int nterms, int
                         double thresh, int* niter) {
   const long long N = (long long)Dl * d * Dr;
   if (N <= 0) { set_error(h, "lanczos_eigvec: empty vector"); return TDVP_ERR_SHAPE; }
-  long long kmax = N < 3000 ? N : 3000;
-  const long long mem_cap = (long long)((size_t(8) << 30) / (sizeof(c128) * (size_t)N));  // <= 8 GiB of Lanczos vectors
-  if (kmax > mem_cap) kmax = mem_cap < 4 ? 4 : mem_cap;
+  // Lanczos basis: the reference stores every vector (up to 3000).  The workspace starts with room for 32 and doubles on
+  // demand (contents preserved), bounded by 3000, N and half of the free device memory.
+  const long long kabs = N < 3000 ? N : 3000;
+  size_t free_b = 0, total_b = 0;
+  TDVP_CUDA(h, cudaMemGetInfo(&free_b, &total_b));
+  long long mem_cap = (long long)((free_b / 2 + h->ws_bytes) / (sizeof(c128) * (size_t)N)) - 8;
+  if (mem_cap < 4) mem_cap = 4;
+  const long long klimit = kabs < mem_cap ? kabs : mem_cap;
+  long long kmax = klimit < 32 ? klimit : 32;
   const size_t contr = heff_ws_elems(hterms, nterms, Dl, d, Dr);
-  const size_t need = sizeof(c128) * ((size_t)(kmax + 4) * N + contr) + sizeof(double) * (size_t)(10 * kmax + 64) + 256 * 16;
-  TDVP_TRY(ws_reserve(h, need));
-  c128* V = (c128*)ws_alloc(h, sizeof(c128) * (size_t)(kmax + 2) * N);
+  auto bytes_for = [&](long long k) {
+    return sizeof(c128) * ((size_t)(k + 4) * N + contr) + sizeof(double) * (size_t)(10 * kabs + 64) + 256 * 16;
+  };
+  TDVP_TRY(ws_reserve(h, bytes_for(kmax)));
+  // small arrays first (sized for the absolute cap), the growing basis last
+  double* alpha = (double*)ws_alloc(h, sizeof(double) * (size_t)(kabs + 2));   // real diagonal
+  double* beta = (double*)ws_alloc(h, sizeof(double) * (size_t)(kabs + 2));    // beta[i] = |w_i|, off-diagonal i
+  double* coef = (double*)ws_alloc(h, sizeof(double) * 2 * (size_t)(kabs + 2));
+  double* work = (double*)ws_alloc(h, sizeof(double) * 6 * (size_t)(kabs + 2));
   c128* ybuf[2] = {(c128*)ws_alloc(h, sizeof(c128) * N), (c128*)ws_alloc(h, sizeof(c128) * N)};
-  double* alpha = (double*)ws_alloc(h, sizeof(double) * (size_t)(kmax + 2));   // real diagonal
-  double* beta = (double*)ws_alloc(h, sizeof(double) * (size_t)(kmax + 2));    // beta[i] = |w_i|, off-diagonal i
-  double* coef = (double*)ws_alloc(h, sizeof(double) * 2 * (size_t)(kmax + 2));
-  double* work = (double*)ws_alloc(h, sizeof(double) * 6 * (size_t)(kmax + 2));
+  const size_t top_before_V = h->ws_top;
+  c128* V = (c128*)ws_alloc(h, sizeof(c128) * (size_t)(kmax + 2) * N);
   if (!V || !ybuf[0] || !ybuf[1] || !alpha || !beta || !coef || !work) { set_error(h, "lanczos_eigvec: workspace"); return TDVP_ERR_ARG; }
   double* S = h->d_scal;
   cudaStream_t st = h->stream;
@@ -661,7 +673,19 @@ int lanczos_eigvec_exec(Handle* h, const tdvp_heff_term* hterms, int nterms, int
   ++h->krylov_solves;
   int cur = 0;
   bool have_prev = false;
-  for (long long i = 0; i <= kmax; ++i) {
+  for (long long i = 0; i <= klimit; ++i) {
+    if (i == kmax && kmax < klimit) {
+      // basis full: double it, keeping everything already stored (pointers are rebased onto the new buffer)
+      long long knew = 2 * kmax < klimit ? 2 * kmax : klimit;
+      const unsigned char* old_base = h->ws;
+      TDVP_TRY(ws_grow_preserve(h, bytes_for(knew)));
+      const ptrdiff_t delta = h->ws - old_base;
+      auto rebase = [&](auto*& p) { p = reinterpret_cast<std::remove_reference_t<decltype(p)>>(reinterpret_cast<unsigned char*>(p) + delta); };
+      rebase(alpha); rebase(beta); rebase(coef); rebase(work); rebase(ybuf[0]); rebase(ybuf[1]); rebase(V);
+      h->ws_top = top_before_V;
+      if (!ws_alloc(h, sizeof(c128) * (size_t)(knew + 2) * N)) { set_error(h, "lanczos_eigvec: workspace"); return TDVP_ERR_ARG; }
+      kmax = knew;
+    }
     c128* vi = V + (size_t)i * N;
     c128* w = V + (size_t)(i + 1) * N;
     ++h->krylov_matvecs;
@@ -690,8 +714,13 @@ int lanczos_eigvec_exec(Handle* h, const tdvp_heff_term* hterms, int nterms, int
     if (!(b == b)) { set_error(h, "lanczos_eigvec: NaN in the recurrence"); return TDVP_ERR_NOT_CONVERGED; }
     bool done = b < EPS_K;
     if (!done && i > 0) done = (h->h_scal[S_ERR] < thresh) || (i == N);
-    if (done || i == kmax) {
-      if (!done && kmax < N && kmax >= 3000) break;
+    if (!done && i == klimit) {
+      // the reference raises here as well (3000 vectors); a memory-capped basis must not return an unconverged vector either
+      set_error(h, klimit >= 3000 ? "Lanczos Diagonalization is not converged in 3000 basis"
+                                  : "Lanczos Diagonalization is not converged: the Krylov basis hit the device-memory cap before 3000 vectors");
+      return TDVP_ERR_NOT_CONVERGED;
+    }
+    if (done) {
       { ProfScope _ps(st, "vec.k_scale_dev"); k_scale_dev<<<nb, RED_THREADS, 0, st>>>(y, psi, N, S + S_YNORM, 0, 0.0); }
       TDVP_TRY(lc(h, "k_scale_dev"));
       if (niter) *niter = (int)i + 1;

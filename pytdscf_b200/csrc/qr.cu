@@ -476,57 +476,58 @@ GemmDesc vhc_desc(int jb, int nc, int mp, const c128* V, long long ldv, const c1
 }
 
 int lq(Handle* h, const char* what) {
-  ++g_launch_count;
+  count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(h, e, what, __FILE__, __LINE__);
   return 0;
 }
 
 int gemmq(Handle* h, const GemmDesc& g) {
-  cudaError_t e = zgemm_auto(g, h->stream, h->d_splitk, SPLITK_SCRATCH_ELEMS);
+  cudaError_t e = zgemm_auto(g, h->gemm);
   if (e != cudaSuccess) return cuda_fail(h, e, "zgemm_launch", __FILE__, __LINE__);
   return 0;
 }
 
 }  // namespace
 
+constexpr int CL_ROWS = 384;     // slab rows per CTA in the cluster kernel (384*32*16 B = 192 KiB)
+constexpr int QR_MAX_SMS = 256;  // workspace bound for the per-CTA partials (B200: 148 SMs)
+
 size_t qr_ws_elems(int m, int n) {
   const size_t np = (n + NB - 1) / NB;
-  return 3 * (size_t)m * n + np * NB * NB + 2 * (size_t)NB * n + 4096 + (size_t)148 * NB * NB + 148 * 4 * NB;
+  return 3 * (size_t)m * n + np * NB * NB + 2 * (size_t)NB * n + 4096 + (size_t)QR_MAX_SMS * NB * NB + QR_MAX_SMS * 4 * NB;
+}
+
+// Per-device kernel attributes and co-scheduling limits of the panel kernels (tdvp_create, once per handle).
+int qr_configure(Handle* h) {
+  TDVP_CUDA(h, cudaFuncSetAttribute(k_qr_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, SLAB_ROWS * NB * (int)sizeof(c128)));
+  TDVP_CUDA(h, cudaFuncSetAttribute(k_qr_panel_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, CL_ROWS * NB * (int)sizeof(c128)));
+  TDVP_CUDA(h, cudaFuncSetAttribute(k_qr_panel_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  h->qr_max_cluster = 0;
+  for (int cs : {16, 8, 4, 2, 1}) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cs);
+    cfg.blockDim = dim3(32, CTY);
+    cfg.dynamicSmemBytes = CL_ROWS * NB * sizeof(c128);
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int nclusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&nclusters, k_qr_panel_cluster, &cfg) == cudaSuccess && nclusters >= 1) { h->qr_max_cluster = cs; break; }
+  }
+  cudaGetLastError();
+  if (h->num_sms > QR_MAX_SMS) { set_error(h, "qr: device has more SMs than the workspace bound"); return TDVP_ERR_UNSUPPORTED; }
+  return 0;
 }
 
 // In-place economic QR of the row-major m x n matrix A (m >= n): on return Q (m x n, ld = ldq) and the upper
 // triangle of A hold the factors.  Workspace comes from the handle's bump allocator.
 int qr_factor(Handle* h, c128* A, int m, int n, int lda, c128* Q, int ldq) {
   if (m < n) { set_error(h, "qr_factor: needs m >= n"); return TDVP_ERR_SHAPE; }
-  static bool configured = false;
-  static int max_coop = 0;
-  static int max_cluster = 0;      // largest cluster size the device can co-schedule for the cluster panel kernel
-  constexpr int CL_ROWS = 384;     // slab rows per CTA in the cluster kernel (384*32*16 B = 192 KiB)
-  if (!configured) {
-    cudaFuncSetAttribute(k_qr_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, SLAB_ROWS * NB * (int)sizeof(c128));
-    cudaFuncSetAttribute(k_qr_panel_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, CL_ROWS * NB * (int)sizeof(c128));
-    cudaFuncSetAttribute(k_qr_panel_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    for (int cs : {16, 8, 4, 2, 1}) {
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(cs);
-      cfg.blockDim = dim3(32, CTY);
-      cfg.dynamicSmemBytes = CL_ROWS * NB * sizeof(c128);
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-      cfg.attrs = at; cfg.numAttrs = 1;
-      int nclusters = 0;
-      if (cudaOccupancyMaxActiveClusters(&nclusters, k_qr_panel_cluster, &cfg) == cudaSuccess && nclusters >= 1) { max_cluster = cs; break; }
-    }
-    cudaGetLastError();
-    int nsm = 0, dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    max_coop = nsm;
-    configured = true;
-  }
-  static const int qr_dbg = getenv("TDVP_QR_DEBUG") ? atoi(getenv("TDVP_QR_DEBUG")) : 0;
+  const int max_coop = h->num_sms;
+  const int max_cluster = h->qr_max_cluster;
+  const int qr_dbg = 0;
   const int np = (n + NB - 1) / NB;
   c128* Vall = (c128*)ws_alloc(h, sizeof(c128) * (size_t)m * lda);
   c128* Tall = (c128*)ws_alloc(h, sizeof(c128) * (size_t)np * NB * NB);
@@ -547,7 +548,7 @@ int qr_factor(Handle* h, c128* A, int m, int n, int lda, c128* Q, int ldq) {
     if (max_cluster >= 1 && mp <= max_cluster * CL_ROWS) {
       // one cluster owns the panel: pick the smallest power-of-two cluster that keeps <= 128 rows per CTA if possible
       int G = 1;
-      static const int rows_target = getenv("TDVP_QR_ROWS") ? atoi(getenv("TDVP_QR_ROWS")) : 64;    // tuning knob (sweep: scripts/debug/qr_timing.py)
+      constexpr int rows_target = 64;    // best of the sweep in scripts/debug/qr_timing.py
       while (G < max_cluster && (mp + G - 1) / G > rows_target) G *= 2;
       while ((mp + G - 1) / G > CL_ROWS) G *= 2;
       const int rpc = (mp + G - 1) / G;
@@ -562,7 +563,7 @@ int qr_factor(Handle* h, c128* A, int m, int n, int lda, c128* Q, int ldq) {
       at[0].val.clusterDim.x = G; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
       { ProfScope _ps(h->stream, "qr.k_qr_panel_cluster"); e = cudaLaunchKernelEx(&cfg, k_qr_panel_cluster, pa); }
-      ++g_launch_count;
+      count_launch();
       if (e != cudaSuccess) return cuda_fail(h, e, "cudaLaunchKernelEx(k_qr_panel_cluster)", __FILE__, __LINE__);
     } else {
       int rpc = SLAB_ROWS;
@@ -574,7 +575,7 @@ int qr_factor(Handle* h, c128* A, int m, int n, int lda, c128* Q, int ldq) {
       void* args[] = {&pa};
       const size_t smem = sizeof(c128) * (size_t)(rpc > 2 * NB ? rpc : 2 * NB) * NB;
       { ProfScope _ps(h->stream, "qr.k_qr_panel"); e = cudaLaunchCooperativeKernel((void*)k_qr_panel, dim3(G), dim3(32, PTY), args, smem, h->stream); }
-      ++g_launch_count;
+      count_launch();
       if (e != cudaSuccess) return cuda_fail(h, e, "cudaLaunchCooperativeKernel(k_qr_panel)", __FILE__, __LINE__);
     }
     const int nc = n - j0 - jb;

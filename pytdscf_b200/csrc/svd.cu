@@ -102,7 +102,10 @@ __global__ void __launch_bounds__(JT) k_jacobi_svd(c128* __restrict__ Gt, c128* 
       grid.sync();
     }
     const int nrot = *((volatile int*)&flags[sweep % 3]);
-    if (nrot == 0) break;
+    if (nrot == 0) {
+      if (blockIdx.x == 0 && threadIdx.x == 0) flags[3] = 1;   // converged: a full sweep without a rotation
+      break;
+    }
   }
 }
 
@@ -208,7 +211,7 @@ __global__ void k_pinv_diag(const c128* __restrict__ X, int n, double cut, c128*
 }
 
 int ls(Handle* h, const char* what) {
-  ++g_launch_count;
+  count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(h, e, what, __FILE__, __LINE__);
   return 0;
@@ -233,11 +236,18 @@ int complete_columns(Handle* h, c128* U, int m, int n, int ldu, int r) {
 
 }  // namespace
 
+int svd_configure(Handle* h) {
+  int per = 0;
+  TDVP_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_jacobi_svd, JT, 0));
+  h->svd_max_blocks = h->num_sms * (per > 4 ? 4 : (per < 1 ? 1 : per));
+  return 0;
+}
+
 // Thin SVD sigma(m x n, row-major, m >= n) = U(m x n) diag(s) Vh(n x n); s descending, copied to host_s.
 int svd_exec(Handle* h, int m, int n, const c128* sigma, c128* U, c128* Vh, double* host_s) {
   if (m < n) { set_error(h, "svd: needs m >= n"); return TDVP_ERR_SHAPE; }
   const size_t need = sizeof(c128) * ((size_t)n * m + (size_t)n * n + 2 * (size_t)m * n + qr_ws_elems(m, n)) +
-                      sizeof(double) * 4 * (size_t)n + 4096;
+                      sizeof(double) * 8 * (size_t)n + 8192;   // incl. the n doubles tdvp_svd_truncate / tdvp_pinv add afterwards
   TDVP_TRY(ws_reserve(h, need));
   c128* Gt = (c128*)ws_alloc(h, sizeof(c128) * (size_t)n * m);
   c128* Vt = (c128*)ws_alloc(h, sizeof(c128) * (size_t)n * n);
@@ -262,30 +272,28 @@ int svd_exec(Handle* h, int m, int n, const c128* sigma, c128* U, c128* Vh, doub
   }
   TDVP_CUDA(h, cudaMemsetAsync(flags, 0, sizeof(int) * 4, st));
   {
-    static int max_blocks = 0;
-    if (max_blocks == 0) {
-      int nsm = 0, dev = 0, per = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_jacobi_svd, JT, 0);
-      max_blocks = nsm * (per > 4 ? 4 : (per < 1 ? 1 : per));
-    }
+    const int max_blocks = h->svd_max_blocks;
     int grid = (n + 1) / 2;
     if (grid > max_blocks) grid = max_blocks;
     if (grid < 1) grid = 1;
     int max_sweeps = 40;
-    double tol = 1.0e-15;
+    // LAPACK zgesvj's threshold: sqrt(m) * eps -- the rounding level of an m-term inner product.  A fixed 1e-15 sits
+    // below that noise for m in the hundreds and would keep rotating (and never report convergence).
+    double tol = std::sqrt((double)m) * 2.220446049250313e-16;
     void* args[] = {&Gt, &Vt, &n, &m, &max_sweeps, &tol, &flags};
     cudaError_t e;
     { ProfScope _ps(st, "svd.k_jacobi_svd"); e = cudaLaunchCooperativeKernel((void*)k_jacobi_svd, dim3(grid), dim3(JT), args, 0, st); }
-    ++g_launch_count;
+    count_launch();
     if (e != cudaSuccess) return cuda_fail(h, e, "cudaLaunchCooperativeKernel(k_jacobi_svd)", __FILE__, __LINE__);
   }
   k_row_norms<<<148, JT, 0, st>>>(Gt, n, m, norms);
   TDVP_TRY(ls(h, "k_row_norms"));
   std::vector<double> hn(n);
+  int conv = 0;
   TDVP_CUDA(h, cudaMemcpyAsync(hn.data(), norms, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  TDVP_CUDA(h, cudaMemcpyAsync(&conv, flags + 3, sizeof(int), cudaMemcpyDeviceToHost, st));
   TDVP_CUDA(h, cudaStreamSynchronize(st));
+  if (!conv) { set_error(h, "svd: one-sided Jacobi did not converge in 40 sweeps"); return TDVP_ERR_NOT_CONVERGED; }
   // ordering of the (already computed) singular values is index bookkeeping: descending, stable
   std::vector<int> hp(n);
   for (int i = 0; i < n; ++i) hp[i] = i;
@@ -343,7 +351,7 @@ int tdvp_svd_truncate(tdvp_handle_t hh, int m, int n, const tdvp_c128* sigma, do
   if (!dvals) { set_error(h, "svd_truncate: workspace"); return TDVP_ERR_ARG; }
   TDVP_CUDA(h, cudaMemcpyAsync(dvals, diag.data(), sizeof(double) * k, cudaMemcpyHostToDevice, h->stream));
   k_diag_matrix<<<148, 256, 0, h->stream>>>((c128*)S, k, dvals);
-  ++g_launch_count;
+  count_launch();
   TDVP_CUDA(h, cudaStreamSynchronize(h->stream));
   // without keepdim the caller uses the leading idx columns of U (ld n) and rows of Vh
   *rank = idx;
@@ -391,12 +399,12 @@ int tdvp_pinv(tdvp_handle_t hh, int m, int n, const tdvp_c128* X, double rcond, 
     if (rc == 0) {
       cudaMemcpyAsync(dinv, inv.data(), sizeof(double) * n, cudaMemcpyHostToDevice, h->stream);
       k_scale_rows<<<148, 256, 0, h->stream>>>(Vh, n, n, n, dinv);
-      ++g_launch_count;
+      count_launch();
       // out(n x m) = Vh^H (n x k) . U^H (k x m)
       GemmDesc g = gemm_rowmajor(n, m, n, Vh, n, true, true, U, n, true, (c128*)out, m);
       g.b_conj = 1;
       g.tag = "pinv";
-      cudaError_t e = zgemm_auto(g, h->stream, h->d_splitk, SPLITK_SCRATCH_ELEMS);
+      cudaError_t e = zgemm_auto(g, h->gemm);
       if (e != cudaSuccess) rc = cuda_fail(h, e, "zgemm(pinv)", __FILE__, __LINE__);
       cudaStreamSynchronize(h->stream);
     }

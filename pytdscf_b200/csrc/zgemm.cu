@@ -16,24 +16,28 @@
 //    every fragment LDS.128 is bank-conflict free for both operand majors.
 //  * rows of A/C and columns of B may be two-level indices (GemmDesc) so contractions such as
 //    T2[a,i,t,s] = sum_{c,j} T1[a,c,j,s] W[c,i,j,t] run on their natural layouts (no transposes).
+#include <atomic>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
-#include <cstdlib>
 #include "common.cuh"
 
 namespace tdvp {
 
-unsigned long long g_launch_count = 0;
+namespace { std::atomic<unsigned long long> g_launches{0}; }
+void count_launch(unsigned long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+unsigned long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 // ---- optional per-launch timing (bench.py roofline / breakdown): CUDA events on the launching stream ----
 namespace {
 struct ProfTotals { double ms = 0.0, flops = 0.0; unsigned long long launches = 0; bool is_gemm = false; };
 struct Pending { cudaEvent_t e0, e1; const char* label; };
 struct Profiler {
-  bool enabled = false;
+  std::mutex mu;   // handles on several devices / host threads share the totals
+  std::atomic<bool> enabled{false};
   std::vector<cudaEvent_t> pool;
   std::vector<Pending> pending;
   std::map<std::string, ProfTotals> totals;
@@ -51,7 +55,9 @@ struct Profiler {
 void prof_enable(bool on) { g_prof.enabled = on; }
 bool prof_enabled() { return g_prof.enabled; }
 
+// prof_begin .. prof_end bracket one launch and hold the lock in between (launch sites never nest)
 void prof_begin(cudaStream_t stream, const char* label, double flops, bool is_gemm) {
+  g_prof.mu.lock();
   ProfTotals& t = g_prof.totals[label];
   t.flops += flops;
   t.launches += 1;
@@ -65,9 +71,11 @@ void prof_end(cudaStream_t stream) {
   cudaEvent_t e1 = g_prof.get();
   cudaEventRecord(e1, stream);
   g_prof.pending.push_back({g_prof.open_e0, e1, g_prof.open_label});
+  g_prof.mu.unlock();
 }
 
 void prof_collect(bool reset) {
+  std::lock_guard<std::mutex> lk(g_prof.mu);
   for (auto& pr : g_prof.pending) {
     cudaEventSynchronize(pr.e1);
     float t = 0.f;
@@ -81,6 +89,7 @@ void prof_collect(bool reset) {
 }
 
 void prof_gemm_totals(double* ms, double* flops, unsigned long long* launches) {
+  std::lock_guard<std::mutex> lk(g_prof.mu);
   double m = 0.0, f = 0.0;
   unsigned long long n = 0;
   for (auto& kv : g_prof.totals)
@@ -91,6 +100,7 @@ void prof_gemm_totals(double* ms, double* flops, unsigned long long* launches) {
 }
 
 size_t prof_json(char* out, size_t cap) {
+  std::lock_guard<std::mutex> lk(g_prof.mu);
   std::string js = "{";
   bool first = true;
   for (auto& kv : g_prof.totals) {
@@ -345,15 +355,16 @@ __global__ void __launch_bounds__(C::THREADS, C::THREADS == 256 ? 1 : 4) zgemm_d
 }
 
 template <typename C>
+cudaError_t configure_cfg() {
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(zgemm_dmma_kernel<C, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES))) return e;
+  if ((e = cudaFuncSetAttribute(zgemm_dmma_kernel<C, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES))) return e;
+  if ((e = cudaFuncSetAttribute(zgemm_dmma_kernel<C, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES))) return e;
+  return cudaFuncSetAttribute(zgemm_dmma_kernel<C, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+}
+
+template <typename C>
 cudaError_t launch_cfg(const GemmDesc& d, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(zgemm_dmma_kernel<C, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-    cudaFuncSetAttribute(zgemm_dmma_kernel<C, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-    cudaFuncSetAttribute(zgemm_dmma_kernel<C, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-    cudaFuncSetAttribute(zgemm_dmma_kernel<C, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-    configured = true;
-  }
   dim3 grid((d.N + C::BN - 1) / C::BN, (d.M + C::BM - 1) / C::BM, d.batch * d.splitk);
   const bool ak = (d.a_k == 1), bk = (d.b_k == 1);
   ProfScope scope(stream, d.tag, 8.0 * (double)d.M * (double)d.N * (double)d.K * (double)d.batch, true);
@@ -365,24 +376,12 @@ cudaError_t launch_cfg(const GemmDesc& d, cudaStream_t stream) {
     zgemm_dmma_kernel<C, false, true><<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(d);
   else
     zgemm_dmma_kernel<C, false, false><<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(d);
-  ++g_launch_count;
+  count_launch();
   return cudaGetLastError();
 }
 
 inline long long tiles_of(const GemmDesc& d, int bm, int bn) {
   return (long long)((d.M + bm - 1) / bm) * ((d.N + bn - 1) / bn) * d.batch;
-}
-
-// The small tile is used when the big one would occupy fewer than half of the SMs, the tiny one when even the small
-// tiling leaves SM sub-partitions without a warp (< 2 small CTAs = 4 warps per SM).
-// TDVP_GEMM_CFG=big|small|tiny forces one configuration (tuning experiments, scripts/microbench/zgemm_shapes.py)
-inline int forced_cfg() {
-  static const int f = [] {
-    const char* e = getenv("TDVP_GEMM_CFG");
-    if (!e) return 0;
-    return e[0] == 'b' ? 1 : (e[0] == 's' ? 2 : (e[0] == 't' ? 3 : 0));
-  }();
-  return f;
 }
 
 // Cost model of one launch (measured constants, profiles/r1_zgemm_cfg_sweep.json): a CTA tile of configuration c costs
@@ -396,21 +395,27 @@ constexpr CfgModel MODELS[3] = {
 };
 struct Choice { int cfg = 1, S = 1, chunk = 0; double t = 1e30; };
 
-inline Choice choose(const GemmDesc& d, bool allow_split, size_t scratch_elems) {
+inline Choice choose(const GemmDesc& d, const GemmCtx& ctx) {
   Choice best;
+  const bool allow_split = ctx.scratch != nullptr && ctx.force_splitk != 1;
+  const size_t scratch_elems = ctx.scratch_elems;
+  const int forced = ctx.force_cfg >= 1 && ctx.force_cfg <= 3 ? ctx.force_cfg : 0;
   const double bw = 5.0e12;
   // >= 8 full waves of big tiles with a long K: wave quantisation is < 6 % and the big tiles need the least L2 traffic
   // per flop (short-K GEMMs such as H_eff stage 2 are prologue-bound and keep the free choice)
   const bool large = tiles_of(d, 128, 64) >= 8 * 148 && d.K >= 512;
   for (const CfgModel& m : MODELS) {
-    if (forced_cfg() ? forced_cfg() != m.id : (m.id == 2 || (large && m.id != 1))) continue;
+    if (forced ? forced != m.id : (m.id == 2 || (large && m.id != 1))) continue;
     const long long tiles = tiles_of(d, m.bm, m.bn);
     const int slots = 148 * m.cps;
     int max_s = 1;
-    if (allow_split && d.batch == 1 && d.K >= 2 * m.min_chunk && tiles < 8 * 148) {
+    if (allow_split && d.batch == 1 && d.K >= 2 * m.min_chunk && (tiles < 8 * 148 || ctx.force_splitk >= 2)) {
       max_s = d.K / m.min_chunk < 16 ? d.K / m.min_chunk : 16;
     }
-    for (int S = 1; S <= max_s; ++S) {
+    // tdvp_set_gemm_config(splitk = S >= 2): exactly that factor when the shape allows it (tests of the split-K path)
+    const int min_s = (ctx.force_splitk >= 2 && max_s >= 2) ? (ctx.force_splitk < max_s ? ctx.force_splitk : max_s) : 1;
+    if (min_s > 1) max_s = min_s;
+    for (int S = min_s; S <= max_s; ++S) {
       int chunk = (d.K + S - 1) / S;
       chunk = (chunk + m.bk - 1) / m.bk * m.bk;
       if ((d.K + chunk - 1) / chunk != S) continue;
@@ -439,13 +444,6 @@ inline cudaError_t launch_by_cfg(int cfg, const GemmDesc& d, cudaStream_t stream
 
 }  // namespace
 
-cudaError_t zgemm_launch(const GemmDesc& d0, cudaStream_t stream) {
-  if (d0.M <= 0 || d0.N <= 0 || d0.batch <= 0) return cudaSuccess;
-  GemmDesc d = d0;
-  d.c_stream = (d.splitk == 1 && (double)d.M * d.N * d.batch * 16.0 > 64.0e6) ? 1 : 0;
-  return launch_by_cfg(choose(d, false, 0).cfg, d, stream);
-}
-
 namespace {
 // C[m,n] = alpha * sum_s P[s][m][n] + beta * C[m,n]   (fixed summation order over s; C addressed like GemmDesc)
 __global__ void k_splitk_reduce(const c128* __restrict__ P, int S, int M, int N, long long stride, GemmDesc d) {
@@ -467,14 +465,24 @@ __global__ void k_splitk_reduce(const c128* __restrict__ P, int S, int M, int N,
 }
 }  // namespace
 
-cudaError_t zgemm_auto(const GemmDesc& d, cudaStream_t stream, c128* scratch, size_t scratch_elems) {
+cudaError_t zgemm_configure_device() {
+  cudaError_t e;
+  if ((e = configure_cfg<BigCfg>())) return e;
+  if ((e = configure_cfg<SmallCfg>())) return e;
+  return configure_cfg<TinyCfg>();
+}
+
+cudaError_t zgemm_auto(const GemmDesc& d, const GemmCtx& ctx) {
   if (d.M <= 0 || d.N <= 0 || d.batch <= 0) return cudaSuccess;
+  cudaStream_t stream = ctx.stream;
+  c128* scratch = ctx.scratch;
   // wave-aware choice of the tile configuration AND the split-K factor (see choose())
-  const Choice ch = choose(d, scratch != nullptr, scratch_elems);
+  const Choice ch = choose(d, ctx);
   const int S = ch.S, chunk = ch.chunk;
   if (S < 2) {
     GemmDesc g1 = d;
-    g1.c_stream = ((double)d.M * d.N * d.batch * 16.0 > 64.0e6) ? 1 : 0;
+    // outputs larger than half of L2 are written with evict-first stores
+    g1.c_stream = ctx.force_cstream ? (ctx.force_cstream == 1) : ((double)d.M * d.N * d.batch * 16.0 > 64.0e6);
     return launch_by_cfg(ch.cfg, g1, stream);
   }
   GemmDesc g = d;
@@ -494,7 +502,7 @@ cudaError_t zgemm_auto(const GemmDesc& d, cudaStream_t stream, c128* scratch, si
     ProfScope scope(stream, "aux.k_splitk_reduce");
     k_splitk_reduce<<<blocks, 256, 0, stream>>>(scratch, S, d.M, d.N, (long long)d.M * d.N, d);
   }
-  ++g_launch_count;
+  count_launch();
   return cudaGetLastError();
 }
 

@@ -17,7 +17,7 @@ static const void* const entry_points[] = {
     (const void*)tdvp_profile_json, (const void*)tdvp_heff_apply, (const void*)tdvp_keff_apply, (const void*)tdvp_env_update,
     (const void*)tdvp_set_krylov_size, (const void*)tdvp_krylov_expm, (const void*)tdvp_lanczos_eigvec, (const void*)tdvp_qr_shift, (const void*)tdvp_absorb,
     (const void*)tdvp_svd_truncate, (const void*)tdvp_svd, (const void*)tdvp_pinv, (const void*)tdvp_inner,
-    (const void*)tdvp_overlap_site, (const void*)tdvp_zgemm};
+    (const void*)tdvp_overlap_site, (const void*)tdvp_zgemm, (const void*)tdvp_set_gemm_config};
 
 int main(int argc, char** argv) {
   printf("abi_version=%d entry_points=%d\n", tdvp_abi_version(), (int)(sizeof(entry_points) / sizeof(entry_points[0])));

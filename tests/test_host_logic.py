@@ -147,7 +147,7 @@ def test_abi_library_exports_every_declared_symbol():
     lib = _lib.load_library()
     for name in declared:
         assert hasattr(lib, name), f"{name} missing from libtdvp_b200.so"
-    assert lib.tdvp_abi_version() == 1
+    assert lib.tdvp_abi_version() == 2
     out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r"\bT (tdvp_[a-z_0-9]+)\b", out))
     assert declared <= exported
