@@ -1,8 +1,9 @@
-"""Import the UNMODIFIED reference (PyTDSCF 1.3.3, NumPy backend) from /root/reference.
+"""Import the UNMODIFIED reference (PyTDSCF 1.3.3, NumPy backend).
 
-TEST INFRASTRUCTURE ONLY (see oracle/refshim/README.md).  Used by tests/golden/make_golden.py in
-the build container to pin the oracle; `/root/reference` does not exist on the GPU box, so nothing
-in `-m gpu` tests, `smoke()` or `bench.py` calls this.
+TEST INFRASTRUCTURE ONLY (see oracle/refshim/README.md).  In the build container the package is imported from
+/root/reference (tests/golden/make_golden*.py pin the oracle with it).  /root/reference does not exist on the GPU box;
+there ``bench.py --impl reference`` / the ``cpu_baseline`` leg import the byte-compiled build product ``oracle/_ref``
+(made by oracle/build_ref.py from the sources where they lie; no source travels).  Nothing in ``pytdscf_b200`` imports this.
 """
 from __future__ import annotations
 
@@ -10,19 +11,46 @@ import os
 import sys
 
 REFERENCE_ROOT = "/root/reference"
-_SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "refshim")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SHIM = os.path.join(_HERE, "refshim")
+BUILT_ROOT = os.path.join(_HERE, "_ref")
 
 
-def reference_available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "pytdscf"))
+def _built_ok() -> bool:
+    import importlib.util
+    import json
+
+    info = os.path.join(BUILT_ROOT, "BUILD_INFO.json")
+    if not (os.path.isdir(os.path.join(BUILT_ROOT, "pytdscf")) and os.path.exists(info)):
+        return False
+    try:
+        return json.load(open(info)).get("magic") == importlib.util.MAGIC_NUMBER.hex()
+    except Exception:
+        return False
 
 
-def load_reference():
-    """Return the imported ``pytdscf`` reference package (NumPy backend only)."""
-    if not reference_available():
-        raise RuntimeError(f"{REFERENCE_ROOT} is not present (only available in the build container)")
+def reference_root(allow_built: bool = True) -> str | None:
+    """Directory to put on sys.path: the source tree in the build container, else the byte-compiled oracle/_ref."""
+    if os.path.isdir(os.path.join(REFERENCE_ROOT, "pytdscf")):
+        return REFERENCE_ROOT
+    if allow_built and _built_ok():
+        return BUILT_ROOT
+    return None
+
+
+def reference_available(allow_built: bool = False) -> bool:
+    return reference_root(allow_built) is not None
+
+
+def load_reference(allow_built: bool = False, prefer_built: bool = False):
+    """Return the imported ``pytdscf`` reference package (NumPy backend only).  ``prefer_built`` imports oracle/_ref even
+    when /root/reference exists (used to test the build product in the build container)."""
+    root = BUILT_ROOT if (prefer_built and _built_ok()) else reference_root(allow_built)
+    if root is None:
+        raise RuntimeError(f"{REFERENCE_ROOT} is not present (only available in the build container) and oracle/_ref "
+                           "was not built (python oracle/build_ref.py)")
     sys.dont_write_bytecode = True
-    for p in (REFERENCE_ROOT, _SHIM):
+    for p in (root, _SHIM):
         if p in sys.path:
             sys.path.remove(p)
         sys.path.insert(0, p)
