@@ -245,8 +245,33 @@ def vibronic_chain(nsite: int = 128, N: int = 8, D: int = 512, dt_fs: float = 0.
                                 f"{max(c.shape[-1] for c in pot)} + kinetic MPO w=2, D={D}")
 
 
+def h2co(path: str | None = None) -> Workload:
+    """c1: the H2CO 6-mode grid MPO (diagonal potential cores from the reference's tests/h2co.tensor + kinetic MPO, HO-DVR
+    d = 5, D = 16) exactly as committed in tests/golden/h2co_D16.npz (inputs made by tests/golden/make_golden.py)."""
+    import ast
+    import os
+
+    if path is None:
+        path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "h2co_D16.npz")
+    z = dict(np.load(path))
+    n = len(z["dims"])
+    operators = {}
+    for ik in range(int(z["nkeys"])):
+        key = ast.literal_eval(str(z[f"key{ik}"]))
+        key = tuple(k if isinstance(k, tuple) else (k,) for k in key)
+        cores, ic = [], 0
+        while f"key{ik}_core{ic}" in z:
+            cores.append(z[f"key{ik}_core{ic}"])
+            ic += 1
+        operators[key] = cores
+    hartree = [z[f"init{i}"] for i in range(n)]   # the reference's own right-canonical initial MPS (3-D cores)
+    return Workload("c1_h2co_6mode_D16", [int(d) for d in z["dims"]], operators, hartree, int(z["bond_dim"]),
+                    float(z["dt_au"]) * units.au_in_fs, coupleJ=complex(z["coupleJ"]),
+                    description="H2CO 6-mode grid-based DVR MPO (tests/h2co.tensor), HO-DVR d=5, D=16")
+
+
 def by_name(name: str, **overrides) -> Workload:
-    table = {"c2": henon_heiles, "c3": pyrazine_lvc, "c4": radical_pair, "c5": vibronic_chain}
+    table = {"c1": h2co, "c2": henon_heiles, "c3": pyrazine_lvc, "c4": radical_pair, "c5": vibronic_chain}
     if name not in table:
         raise KeyError(f"unknown workload {name!r}; choose from {sorted(table)}")
     return table[name](**overrides)

@@ -1,14 +1,17 @@
-"""bench.py contract on CPU: the reference arm (CPU oracle port) prints one JSON line with the keys the driver reads."""
+"""bench.py contract on CPU: the reference arm (the unmodified reference from oracle/_ref or /root/reference; the oracle port
+when neither exists) prints one JSON line with the keys the driver reads."""
 import json
 import os
 import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
 
 def test_reference_arm_json_line():
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c2", "--steps", "1",
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c1", "--steps", "1",
                           "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
@@ -16,9 +19,16 @@ def test_reference_arm_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "tdvp_sweeps_per_sec" and d["unit"] == "sweeps/s"
     assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 0
-    assert d["value"] > 0 and d["config"]["workload"].startswith("c2_")
+    assert d["value"] > 0 and d["config"]["workload"].startswith("c1_")
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "site update" in cb["sample"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and len(cb["sample"]) > 20
+    # same config dict as the GPU arm emits for this workload (the driver compares them)
+    import bench
+
+    class A:
+        workload, bond_dim, sites = "c1", None, None
+
+    assert d["config"] == bench.config_dict(bench.make_workload(A), 1, False)
     assert d["e2e"] == {"value": d["value"], "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
