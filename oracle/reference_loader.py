@@ -13,15 +13,16 @@ import sys
 REFERENCE_ROOT = "/root/reference"
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SHIM = os.path.join(_HERE, "refshim")
-BUILT_ROOT = os.path.join(_HERE, "_ref")
+BUILT_DIR = os.path.join(_HERE, "_ref")
+BUILT_ROOT = os.path.join(BUILT_DIR, "pytdscf_ref.zip")   # sys.path entry (zipimport)
 
 
 def _built_ok() -> bool:
     import importlib.util
     import json
 
-    info = os.path.join(BUILT_ROOT, "BUILD_INFO.json")
-    if not (os.path.isdir(os.path.join(BUILT_ROOT, "pytdscf")) and os.path.exists(info)):
+    info = os.path.join(BUILT_DIR, "BUILD_INFO.json")
+    if not (os.path.exists(BUILT_ROOT) and os.path.exists(info)):
         return False
     try:
         return json.load(open(info)).get("magic") == importlib.util.MAGIC_NUMBER.hex()

@@ -48,12 +48,33 @@ __device__ __forceinline__ void block_sum3(double& a, double& b, double& c, doub
 }
 
 // Gt: n x m (row j = column j of sigma), Vt: n x n (row j = column j of V).  n may be odd (a bye is inserted).
+// Columns whose norm falls below NEGLIGIBLE x (largest initial column norm) are numerical zeros: rotating them only
+// reproduces rounding noise one ulp smaller each time (a rank-1 bond matrix of a padded Hartree product would rotate its
+// noise columns until they underflow, ~20 sweeps); they are frozen, and svd_exec takes their left vectors from the
+// orthonormal completion exactly like those of exact zeros.  LAPACK's gesdd resolves singular values only to
+// eps x s_max, so nothing the reference can represent is lost (NEGLIGIBLE = 1e-20 << eps).
+constexpr double NEGLIGIBLE = 1.0e-20;
+
 __global__ void __launch_bounds__(JT) k_jacobi_svd(c128* __restrict__ Gt, c128* __restrict__ Vt, int n, int m, int max_sweeps,
-                                                    double tol, int* __restrict__ flags /* [0]: rotations in this sweep */) {
+                                                    double tol, int* __restrict__ flags /* [0]: rotations in this sweep */,
+                                                    unsigned long long* __restrict__ maxn2 /* zeroed: max |column|^2 as bits */) {
   __shared__ double sm[4 * (JT / 32)];
   cg::grid_group grid = cg::this_grid();
   const int ne = (n + 1) & ~1;           // players (even)
   const int npairs = ne / 2;
+  for (int j = blockIdx.x; j < n; j += gridDim.x) {
+    double a = 0.0, b = 0.0, c = 0.0, d = 0.0;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+      const c128 x = Gt[(size_t)j * m + i];
+      a += x.x * x.x + x.y * x.y;
+    }
+    block_sum3(a, b, c, d, sm);
+    if (threadIdx.x == 0) atomicMax(maxn2, (unsigned long long)__double_as_longlong(a));   // non-negative doubles order like integers
+    __syncthreads();
+  }
+  __threadfence();
+  grid.sync();
+  const double frozen2 = NEGLIGIBLE * NEGLIGIBLE * __longlong_as_double((long long)*((volatile unsigned long long*)maxn2));
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
     if (blockIdx.x == 0 && threadIdx.x == 0) flags[(sweep + 1) % 3] = 0;   // reset the counter of the NEXT sweep (3 slots: no reader of slot sweep-1 is disturbed)
     for (int r = 0; r < ne - 1; ++r) {
@@ -75,7 +96,7 @@ __global__ void __launch_bounds__(JT) k_jacobi_svd(c128* __restrict__ Gt, c128* 
         }
         block_sum3(al, be, gr, gi, sm);
         const double ga = hypot(gr, gi);
-        if (ga > tol * sqrt(al) * sqrt(be) && ga > 0.0) {
+        if (al > frozen2 && be > frozen2 && ga > tol * sqrt(al) * sqrt(be)) {
           if (threadIdx.x == 0) atomicAdd(&flags[sweep % 3], 1);
           const double pr = gr / ga, pi = gi / ga;          // e^{i phi}
           const double zeta = (be - al) / (2.0 * ga);
@@ -254,7 +275,7 @@ int svd_exec(Handle* h, int m, int n, const c128* sigma, c128* U, c128* Vh, doub
   double* norms = (double*)ws_alloc(h, sizeof(double) * n);
   double* svals = (double*)ws_alloc(h, sizeof(double) * n);
   int* perm = (int*)ws_alloc(h, sizeof(int) * n);
-  int* flags = (int*)ws_alloc(h, sizeof(int) * 4);
+  int* flags = (int*)ws_alloc(h, sizeof(int) * 8);   // [0..2] rotation counters, [3] converged, [4..5] max |column|^2
   if (!Gt || !Vt || !norms || !svals || !perm || !flags) { set_error(h, "svd: workspace"); return TDVP_ERR_ARG; }
   cudaStream_t st = h->stream;
   TDVP_TRY(permute_site(h, sigma, Gt, m, 1, n));   // Gt[j, i] = sigma[i, j]
@@ -270,7 +291,8 @@ int svd_exec(Handle* h, int m, int n, const c128* sigma, c128* U, c128* Vh, doub
     k_diag_matrix<<<148, 256, 0, st>>>(Vt, n, ones);
     TDVP_TRY(ls(h, "k_diag_matrix"));
   }
-  TDVP_CUDA(h, cudaMemsetAsync(flags, 0, sizeof(int) * 4, st));
+  TDVP_CUDA(h, cudaMemsetAsync(flags, 0, sizeof(int) * 8, st));
+  unsigned long long* maxn2 = reinterpret_cast<unsigned long long*>(flags + 4);
   {
     const int max_blocks = h->svd_max_blocks;
     int grid = (n + 1) / 2;
@@ -280,7 +302,7 @@ int svd_exec(Handle* h, int m, int n, const c128* sigma, c128* U, c128* Vh, doub
     // LAPACK zgesvj's threshold: sqrt(m) * eps -- the rounding level of an m-term inner product.  A fixed 1e-15 sits
     // below that noise for m in the hundreds and would keep rotating (and never report convergence).
     double tol = std::sqrt((double)m) * 2.220446049250313e-16;
-    void* args[] = {&Gt, &Vt, &n, &m, &max_sweeps, &tol, &flags};
+    void* args[] = {&Gt, &Vt, &n, &m, &max_sweeps, &tol, &flags, &maxn2};
     cudaError_t e;
     { ProfScope _ps(st, "svd.k_jacobi_svd"); e = cudaLaunchCooperativeKernel((void*)k_jacobi_svd, dim3(grid), dim3(JT), args, 0, st); }
     count_launch();
@@ -300,10 +322,10 @@ int svd_exec(Handle* h, int m, int n, const c128* sigma, c128* U, c128* Vh, doub
   std::stable_sort(hp.begin(), hp.end(), [&](int a, int b) { return hn[a] > hn[b]; });
   std::vector<double> hs(n);
   int r = 0;
-  // Columns whose norm is below 1e-140 of the largest cannot be normalised reliably (their squares are denormal in
-  // the plain sums used by the rotations and by k_row_norms); their left vectors come from the orthonormal completion
-  // like those of exactly zero singular values.  The computed value is still reported.
-  for (int i = 0; i < n; ++i) { hs[i] = hn[hp[i]]; if (hs[i] > 0.0 && hs[i] >= 1.0e-140 * hs[0]) r = i + 1; }
+  // Columns the kernel froze as numerical zeros (norm < NEGLIGIBLE x largest initial column norm <= NEGLIGIBLE x s_max)
+  // can never pass this test, so every un-orthogonalised column gets its left vector from the orthonormal completion,
+  // like the columns of exactly zero singular values.  The computed value is still reported.
+  for (int i = 0; i < n; ++i) { hs[i] = hn[hp[i]]; if (hs[i] > 0.0 && hs[i] > 4.0 * NEGLIGIBLE * hs[0]) r = i + 1; }
   TDVP_CUDA(h, cudaMemcpyAsync(perm, hp.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
   TDVP_CUDA(h, cudaMemcpyAsync(svals, hs.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
   k_assemble_uv<<<148 * 2, 256, 0, st>>>(Gt, Vt, perm, svals, n, m, U, n, Vh, n);
