@@ -84,6 +84,10 @@ cudaError_t zgemm_configure_device();
 // tiles, long K): partial products go to ctx.scratch and are combined in fixed order by a second kernel, so results
 // stay deterministic.  Returns cudaGetLastError() of the launch.
 cudaError_t zgemm_auto(const GemmDesc& d, const GemmCtx& ctx);
+// Persistent TMA-fed 128x64 kernel (zgemm_tma.cu).  zgemm_tma_try launches `d` (split-K fields resolved) when its operands
+// can be described by tensor maps and sets *used; otherwise nothing is launched and the caller uses the cp.async kernels.
+cudaError_t zgemm_tma_configure_device();
+cudaError_t zgemm_tma_try(const GemmDesc& d, const GemmCtx& ctx, bool* used);
 constexpr size_t SPLITK_SCRATCH_ELEMS = size_t(18) << 20;  // 288 MiB of partial products
 // Number of kernel launches issued through this library since load (bench.py's gpu_launches claim).
 void count_launch(unsigned long long n = 1);

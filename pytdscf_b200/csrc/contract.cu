@@ -144,18 +144,20 @@ int axpby2d(Handle* h, const c128* x, long long ldx, c128* y, long long ldy, lon
 // Identity-channel shortcuts pay only when the skipped GEMM slice is worth more than the extra copy / add launch.
 constexpr long long ID_CHANNEL_MIN_ELEMS = 1ll << 17;
 
-// C[(a, c), n] = sum_b L[(a, c), b] X[b, n] for every MPO channel c except `skip` (two-level rows: a outer with the
-// full stride, c inner over the remaining channels), and C[(a, skip), :] = X[a, :]  (L[:, skip, :] is the identity).
+// C[(a, c), n] = sum_b L[(a, c), b] X[b, n] for every MPO channel c except `skip` (two-level rows over the remaining
+// channels), and C[(a, skip), :] = X[a, :]  (L[:, skip, :] is the identity).
 int left_apply_skip(Handle* h, const c128* L, int D, int w, int skip, const c128* X, long long ncols, c128* C, const char* tag) {
   int rc = 0;
   for (int part = 0; part < 2; ++part) {
     const int c0 = part == 0 ? 0 : skip + 1, c1 = part == 0 ? skip : w;
     if (c1 <= c0) continue;
+    // GEMM rows ordered (channel outer, a inner): every 128-row tile then lies inside one channel, which is what lets the
+    // TMA kernel describe L[:, c0:c1, :] and the matching rows of C with one box per tile
     GemmDesc g;
     g.M = D * (c1 - c0); g.N = (int)ncols; g.K = D;
-    g.A = L + (long long)c0 * D; g.a_m_inner = c1 - c0; g.a_m1 = (long long)w * D; g.a_m0 = D; g.a_k = 1;
+    g.A = L + (long long)c0 * D; g.a_m_inner = D; g.a_m1 = D; g.a_m0 = (long long)w * D; g.a_k = 1;
     g.B = X; g.b_n_inner = 1; g.b_n1 = 1; g.b_n0 = 0; g.b_k = ncols;
-    g.C = C + (long long)c0 * ncols; g.c_m_inner = c1 - c0; g.c_m1 = (long long)w * ncols; g.c_m0 = ncols; g.c_n = 1;
+    g.C = C + (long long)c0 * ncols; g.c_m_inner = D; g.c_m1 = ncols; g.c_m0 = (long long)w * ncols; g.c_n = 1;
     g.tag = tag;
     if ((rc = gemm(h, g))) return rc;
   }

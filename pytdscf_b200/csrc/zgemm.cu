@@ -399,7 +399,8 @@ inline Choice choose(const GemmDesc& d, const GemmCtx& ctx) {
   Choice best;
   const bool allow_split = ctx.scratch != nullptr && ctx.force_splitk != 1;
   const size_t scratch_elems = ctx.scratch_elems;
-  const int forced = ctx.force_cfg >= 1 && ctx.force_cfg <= 3 ? ctx.force_cfg : 0;
+  // force_cfg 4 (tma) shares the big tile's geometry: the split-K factor is chosen as for the forced big configuration
+  const int forced = ctx.force_cfg == 4 ? 1 : (ctx.force_cfg >= 1 && ctx.force_cfg <= 3 ? ctx.force_cfg : 0);
   const double bw = 5.0e12;
   // >= 8 full waves of big tiles with a long K: wave quantisation is < 6 % and the big tiles need the least L2 traffic
   // per flop (short-K GEMMs such as H_eff stage 2 are prologue-bound and keep the free choice)
@@ -467,6 +468,7 @@ __global__ void k_splitk_reduce(const c128* __restrict__ P, int S, int M, int N,
 
 cudaError_t zgemm_configure_device() {
   cudaError_t e;
+  if ((e = zgemm_tma_configure_device())) return e;
   if ((e = configure_cfg<BigCfg>())) return e;
   if ((e = configure_cfg<SmallCfg>())) return e;
   return configure_cfg<TinyCfg>();
@@ -479,11 +481,21 @@ cudaError_t zgemm_auto(const GemmDesc& d, const GemmCtx& ctx) {
   // wave-aware choice of the tile configuration AND the split-K factor (see choose())
   const Choice ch = choose(d, ctx);
   const int S = ch.S, chunk = ch.chunk;
+  // the big-tile work goes to the persistent TMA kernel whenever tensor maps can describe the operands
+  const bool want_tma = ctx.force_cfg == 4 || (ctx.force_cfg == 0 && ch.cfg == 1);
+  auto launch = [&](const GemmDesc& g) -> cudaError_t {
+    if (want_tma) {
+      bool used = false;
+      cudaError_t e = zgemm_tma_try(g, ctx, &used);
+      if (used || e != cudaSuccess) return e;
+    }
+    return launch_by_cfg(ch.cfg, g, stream);
+  };
   if (S < 2) {
     GemmDesc g1 = d;
     // outputs larger than half of L2 are written with evict-first stores
     g1.c_stream = ctx.force_cstream ? (ctx.force_cstream == 1) : ((double)d.M * d.N * d.batch * 16.0 > 64.0e6);
-    return launch_by_cfg(ch.cfg, g1, stream);
+    return launch(g1);
   }
   GemmDesc g = d;
   g.C = scratch;
@@ -493,7 +505,7 @@ cudaError_t zgemm_auto(const GemmDesc& d, const GemmCtx& ctx) {
   g.splitk = S;
   g.k_chunk = chunk;
   g.c_split = (long long)d.M * d.N;
-  cudaError_t e = launch_by_cfg(ch.cfg, g, stream);
+  cudaError_t e = launch(g);
   if (e != cudaSuccess) return e;
   const long long tot = (long long)d.M * d.N;
   int blocks = (int)((tot + 255) / 256);

@@ -1,0 +1,451 @@
+// Persistent, TMA-fed variant of the complex128 DMMA GEMM (sm_100a): the big-tile path of zgemm.cu rebuilt around
+// cp.async.bulk.tensor + mbarrier, for the GEMMs that carry the D >= 256 work of the sweep
+// (H_eff stages 1-3, K_eff, environment updates; reference: opt_einsum -> ZGEMM at pytdscf/_contraction.py:1162-1174).
+//
+// What changes against zgemm_dmma_kernel<BigCfg> (ncu, profiles/r1_ncu_zgemm_v4_raw.csv: DMMA pipe 90 % busy, the idle
+// 10 % being the eight warps leaving the per-k-tile __syncthreads in lock step and queueing on shared memory together):
+//  * one producer warp issues TMA boxes into a 4-stage ring; full / empty mbarriers replace every block-wide barrier, so
+//    the 8 consumer warps drift apart and their fragment loads interleave with each other's DMMAs;
+//  * persistent CTAs (one per SM) walk the tile list, and the producer runs ahead into the next tile while the consumers
+//    write the epilogue: prologue / epilogue latency is hidden, no per-tile launch tail;
+//  * fragments are double-buffered in registers (loads of step s+1 are issued before the DMMAs of step s);
+//  * the complex product runs as a REAL GEMM with doubled k: A' = [re, im] interleaved along k (exactly the memory
+//    layout), B're = [re; -im], B'im = [im; re] formed on the fly, so a lane holds ONE double per A row and step
+//    (12 fragment doubles per step instead of 20) and conjugation stays a sign-bit flip;
+//  * shared memory is written by TMA with the 128-byte hardware swizzle; the k index a lane handles in step t,
+//    k = 4 (q >> 1) + t, is chosen so that every LDS phase hits 8 distinct 16-byte bank groups for k-contiguous AND
+//    row-contiguous operands (bank arithmetic in DESIGN.md 4.1b).
+// Shapes the tensor maps cannot express (batched, rows not a multiple of 8 on a row-contiguous operand, two-level row
+// indices that do not tile by 128 / 64) fall back to the cp.async kernels of zgemm.cu.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace tdvp {
+
+namespace {
+
+constexpr int BM = 128, BN = 64, BK = 16, STAGES = 4;
+constexpr int CONSUMER_WARPS = 8;
+// Registers are allocated per warpgroup (4 warps): 2 consumer warpgroups + 1 producer warpgroup (one working lane).  The
+// launch gives every thread 168 registers (65536 / 384); the producer group then shrinks to 40 and the consumers grow
+// to 232 with setmaxnreg, as warp-specialised Hopper / Blackwell GEMMs do.
+constexpr int THREADS = 32 * (CONSUMER_WARPS + 4);
+constexpr int PRODUCER_REGS = 40, CONSUMER_REGS = 232;
+constexpr int SLAB_A = BM * 128, SLAB_B = BN * 128;          // bytes of one 8-k slab of the A / B tile
+constexpr int STAGE_BYTES = 2 * (SLAB_A + SLAB_B);            // two slabs (BK = 16) of both operands: 48 KiB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;  // + alignment slack + barriers
+constexpr unsigned BIG_INNER = 1u << 30;                      // "plain" operand: a single row level
+
+struct TmaSide {
+  unsigned inner;      // rows per step of the outer row index (BIG_INNER: plain matrix)
+  short small_inner;   // inner < tile rows: the box spans several outer steps
+  short swapped;       // k-contiguous operand whose two row levels are listed (outer, inner) in the tensor map so that its
+                       // strides ascend (the box has extent 1 in the outer level, the shared-memory image is the same)
+};
+
+struct TmaParams {
+  int M, N, K, tiles_m, tiles_n, splitk, k_chunk;
+  TmaSide a, b;
+  unsigned a_conj, b_conj;
+  c128* C;
+  int c_m_inner;
+  long long c_m1, c_m0, c_n, c_split;
+  c128 alpha, beta;
+  int c_stream;
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.b32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void tma_load_4d(unsigned dst, const CUtensorMap* map, unsigned bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+__device__ __forceinline__ double flip_sign(double x, unsigned mask) {
+  return __hiloint2double(__double2hiint(x) ^ (int)mask, __double2loint(x));
+}
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// Work item w -> (tile_m, tile_n, split): splits outermost, then the grouped rasterisation of zgemm_dmma_kernel (16 M-tiles
+// per N-tile), so the CTAs of one persistent "wave" (consecutive w) share A rows / B columns in L2.
+__device__ __forceinline__ void decode_work(const TmaParams& p, int w, int& tm, int& tn, int& split) {
+  constexpr int GROUP_M = 16;
+  const int per_split = p.tiles_m * p.tiles_n;
+  split = w / per_split;
+  const int pid = w - split * per_split;
+  const int in_group = GROUP_M * p.tiles_n;
+  const int first_m = (pid / in_group) * GROUP_M;
+  const int gsz = (p.tiles_m - first_m) < GROUP_M ? (p.tiles_m - first_m) : GROUP_M;
+  tm = first_m + (pid % in_group) % gsz;
+  tn = (pid % in_group) / gsz;
+}
+
+template <bool KMAJOR>
+__device__ __forceinline__ void issue_box(unsigned dst, const CUtensorMap* map, unsigned bar, const TmaSide& s, int row0, int k0) {
+  const int lo = s.small_inner ? 0 : (int)((unsigned)row0 % s.inner);
+  const int hi = (int)((unsigned)row0 / s.inner);
+  if (KMAJOR) tma_load_4d(dst, map, bar, 2 * k0, s.swapped ? hi : lo, s.swapped ? lo : hi, 0);   // dims (k as f64 pairs, row, outer row, 1)
+  else tma_load_4d(dst, map, bar, 0, k0, lo >> 3, hi);                // dims (8 rows as f64 pairs, k, row / 8, outer row)
+}
+
+struct Frag {
+  double a[4];
+  double2 b[4];
+};
+
+template <bool A_KMAJOR, bool B_KMAJOR>
+__global__ void __launch_bounds__(THREADS, 1)
+    zgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TmaParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  const unsigned raw = smem_u32(smem_raw);
+  const unsigned base = (raw + 1023u) & ~1023u;                  // SWIZZLE_128B pattern repeats every 1024 B of address
+  const unsigned char* sm = smem_raw + (base - raw);
+  const unsigned bars = base + STAGES * STAGE_BYTES;             // full[STAGES], empty[STAGES]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bars + 8 * s, 1);
+      mbar_init(bars + 8 * (STAGES + s), CONSUMER_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  const int total = p.tiles_m * p.tiles_n * p.splitk;
+
+  if (warp >= CONSUMER_WARPS) {
+    // ================= producer: one lane walks the same work list and keeps the ring full =================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(PRODUCER_REGS));
+    if (warp != CONSUMER_WARPS || lane != 0) return;
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(&mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(&mapB) : "memory");
+    int stage = 0;
+    unsigned phase = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      int tm, tn, split;
+      decode_work(p, w, tm, tn, split);
+      const int k_begin = split * p.k_chunk;
+      const int k_end = (p.splitk > 1 && k_begin + p.k_chunk < p.K) ? k_begin + p.k_chunk : p.K;
+      const int KT = (k_end - k_begin + BK - 1) / BK;
+      for (int kt = 0; kt < KT; ++kt) {
+        mbar_wait(bars + 8 * (STAGES + stage), phase ^ 1u);      // slot free (passes at once on a fresh barrier)
+        const unsigned full = bars + 8 * stage;
+        mbar_expect_tx(full, STAGE_BYTES);
+        const unsigned sA = base + stage * STAGE_BYTES, sB = sA + 2 * SLAB_A;
+        const int k0 = k_begin + kt * BK;
+        issue_box<A_KMAJOR>(sA, &mapA, full, p.a, tm * BM, k0);
+        issue_box<B_KMAJOR>(sB, &mapB, full, p.b, tn * BN, k0);
+        issue_box<A_KMAJOR>(sA + SLAB_A, &mapA, full, p.a, tm * BM, k0 + 8);
+        issue_box<B_KMAJOR>(sB + SLAB_B, &mapB, full, p.b, tn * BN, k0 + 8);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+    return;
+  }
+
+  // ================= consumers: 4 x 2 warps of 32 x 32 complex =================
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(CONSUMER_REGS));
+  const int g = lane >> 2, q = lane & 3, hq = q >> 1, odd = q & 1;
+  const int wm = warp & 3, wn = warp >> 2;
+  // 16-byte chunk (after the hardware XOR) of the complex k = 4 hq + t this lane handles in step t, for row (or, on
+  // row-contiguous operands, 8-row group member) g -- the same value serves both operands and both majors
+  int off_t[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) off_t[t] = ((4 * hq + t) ^ g) << 4;
+  const int aBase = A_KMAJOR ? ((wm * 32 + g) * 128 + odd * 8) : (wm * 4 * 1024 + 4 * hq * 128 + odd * 8);
+  const int bBase = B_KMAJOR ? ((wn * 32 + g) * 128) : (wn * 4 * 1024 + 4 * hq * 128);
+  const unsigned maskA = (p.a_conj && odd) ? 0x80000000u : 0u;
+  const unsigned maskB = (p.b_conj ? 0x80000000u : 0u) ^ (odd ? 0x80000000u : 0u);
+
+  auto load_frag = [&](Frag& f, const unsigned char* slabA, const unsigned char* slabB, int t) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      f.a[i] = *reinterpret_cast<const double*>(slabA + aBase + i * 1024 + (A_KMAJOR ? 0 : t * 128) + off_t[t]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      f.b[j] = *reinterpret_cast<const double2*>(slabB + bBase + j * 1024 + (B_KMAJOR ? 0 : t * 128) + off_t[t]);
+  };
+
+  double cre[4][4][2], cim[4][4][2];
+  auto compute = [&](const Frag& f) {
+    double av[4], bre[4], bim[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) av[i] = flip_sign(f.a[i], maskA);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      // real GEMM over the doubled k: even k' multiplies (b.re | b.im), odd k' multiplies (-b.im | b.re)
+      const double y = flip_sign(f.b[j].y, maskB);
+      bre[j] = odd ? y : f.b[j].x;
+      bim[j] = odd ? f.b[j].x : y;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        dmma(cre[i][j][0], cre[i][j][1], av[i], bre[j]);
+        dmma(cim[i][j][0], cim[i][j][1], av[i], bim[j]);
+      }
+  };
+
+  int stage = 0;
+  unsigned phase = 0;
+  const c128 alpha = p.alpha, beta = p.beta;
+  const bool use_beta = (beta.x != 0.0) || (beta.y != 0.0);
+  for (int w = blockIdx.x; w < total; w += gridDim.x) {
+    int tm, tn, split;
+    decode_work(p, w, tm, tn, split);
+    const int k_begin = split * p.k_chunk;
+    const int k_end = (p.splitk > 1 && k_begin + p.k_chunk < p.K) ? k_begin + p.k_chunk : p.K;
+    const int KT = (k_end - k_begin + BK - 1) / BK;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        cre[i][j][0] = cre[i][j][1] = 0.0;
+        cim[i][j][0] = cim[i][j][1] = 0.0;
+      }
+    Frag f0, f1;
+    mbar_wait(bars + 8 * stage, phase);
+    load_frag(f0, sm + stage * STAGE_BYTES, sm + stage * STAGE_BYTES + 2 * SLAB_A, 0);
+    for (int kt = 0; kt < KT; ++kt) {
+      const unsigned char* sA = sm + stage * STAGE_BYTES;
+      const unsigned char* sB = sA + 2 * SLAB_A;
+      int nstage = stage + 1;
+      unsigned nphase = phase;
+      if (nstage == STAGES) { nstage = 0; nphase ^= 1u; }
+#pragma unroll
+      for (int s = 0; s < 8; ++s) {          // s = 4 * slab + t
+        Frag& cur = (s & 1) ? f1 : f0;
+        Frag& nxt = (s & 1) ? f0 : f1;
+        if (s < 7) {
+          load_frag(nxt, sA + ((s + 1) >> 2) * SLAB_A, sB + ((s + 1) >> 2) * SLAB_B, (s + 1) & 3);
+        } else if (kt + 1 < KT) {
+          // first fragments of the next stage are requested before the last DMMAs of this one
+          mbar_wait(bars + 8 * nstage, nphase);
+          load_frag(nxt, sm + nstage * STAGE_BYTES, sm + nstage * STAGE_BYTES + 2 * SLAB_A, 0);
+        }
+        compute(cur);
+      }
+      // every lane's reads of this stage have been consumed by the (warp-synchronous) DMMAs above: hand the slot back
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + 8 * (STAGES + stage));
+      stage = nstage;
+      phase = nphase;
+    }
+
+    // ---- epilogue: C = alpha * acc + beta * C (the producer is already filling the ring for the next tile) ----
+    c128* __restrict__ Cg = p.C + (long long)split * p.c_split;
+    const int tile_m = tm * BM, tile_n = tn * BN;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = tile_m + wm * 32 + 8 * i + g;
+      if (m >= p.M) continue;
+      const long long roff = (long long)(m / p.c_m_inner) * p.c_m1 + (long long)(m % p.c_m_inner) * p.c_m0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int n = tile_n + wn * 32 + 8 * j + 2 * q + e;
+          if (n >= p.N) continue;
+          c128* ptr = Cg + roff + (long long)n * p.c_n;
+          const c128 acc = {cre[i][j][e], cim[i][j][e]};
+          c128 out = cmul(alpha, acc);
+          if (use_beta) out = cadd(out, cmul(beta, *ptr));
+          if (p.c_stream) __stcs(reinterpret_cast<double2*>(ptr), make_double2(out.x, out.y));
+          else *ptr = out;
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side: tensor maps
+// ---------------------------------------------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled encode_fn() {
+  static PFN_cuTensorMapEncodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(ptr);
+    cudaGetLastError();
+  });
+  return fn;
+}
+
+inline cuuint64_t clamp_stride(unsigned long long s) {
+  const unsigned long long cap = (1ull << 40) - 16;
+  return s < 16 ? 16 : (s > cap ? cap : s);
+}
+
+// One operand with `rows` rows (two-level: row = r1 * inner + r0) and K columns, element (row, k) at
+// ptr + r1 * s1 + r0 * s0 + k * sk (complex128 units).  R = tile rows (128 for A, 64 for B).  Returns false when the
+// operand cannot be described (the caller then uses the cp.async kernel).
+bool make_side(CUtensorMap* map, TmaSide* side, bool* kmajor, const c128* ptr, long long rows, int K, int inner, long long s1,
+               long long s0, long long sk, int R) {
+  PFN_cuTensorMapEncodeTiled enc = encode_fn();
+  if (!enc || rows <= 0 || K < BK) return false;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15u) != 0) return false;
+  if (inner <= 0) return false;
+  const bool two = inner > 1 && inner < rows;
+  if (!two) {           // single row level: fold it into (inner = 1, s1)
+    if (inner > 1) { s1 = s0; }   // rows <= inner: only the r0 level is walked
+    inner = 1;
+  } else if (rows % inner != 0) {
+    return false;
+  }
+  cuuint64_t dims[4], strides[3];
+  cuuint32_t box[4], estr[4] = {1, 1, 1, 1};
+  if (sk == 1) {
+    *kmajor = true;
+    if (!two) {
+      dims[0] = 2ull * K; dims[1] = (cuuint64_t)rows; dims[2] = 1; dims[3] = 1;
+      strides[0] = clamp_stride(16ull * s1);
+      strides[1] = clamp_stride(strides[0] * (unsigned long long)rows);
+      strides[2] = strides[1];
+      box[0] = 16; box[1] = R; box[2] = 1; box[3] = 1;
+      side->inner = BIG_INNER; side->small_inner = 0; side->swapped = 0;
+      if (s1 < 1) return false;
+    } else {
+      if (inner % R != 0 && R % inner != 0) return false;
+      if (s0 < 1 || s1 < 1) return false;
+      const long long n1 = rows / inner;
+      const bool small = inner < R;
+      const bool swap = !small && s0 > s1;
+      dims[0] = 2ull * K; dims[3] = 1;
+      if (!swap) {
+        dims[1] = (cuuint64_t)inner; dims[2] = (cuuint64_t)n1;
+        strides[0] = clamp_stride(16ull * s0);
+        strides[1] = clamp_stride(16ull * s1);
+        strides[2] = clamp_stride(strides[1] * (unsigned long long)n1);
+        box[0] = 16; box[1] = small ? inner : R; box[2] = small ? R / inner : 1; box[3] = 1;
+      } else {
+        dims[1] = (cuuint64_t)n1; dims[2] = (cuuint64_t)inner;
+        strides[0] = clamp_stride(16ull * s1);
+        strides[1] = clamp_stride(16ull * s0);
+        strides[2] = clamp_stride(strides[1] * (unsigned long long)inner);
+        box[0] = 16; box[1] = 1; box[2] = R; box[3] = 1;
+      }
+      side->inner = (unsigned)inner; side->small_inner = small ? 1 : 0; side->swapped = swap ? 1 : 0;
+    }
+  } else {
+    *kmajor = false;
+    if (sk < 8) return false;        // k stride must cover the 8-row (128-byte) inner box
+    if (!two) {
+      if (s1 != 1 || rows % 8 != 0) return false;
+      dims[0] = 16; dims[1] = (cuuint64_t)K; dims[2] = (cuuint64_t)(rows / 8); dims[3] = 1;
+      strides[0] = clamp_stride(16ull * sk);
+      strides[1] = 128;
+      strides[2] = clamp_stride(128ull * (unsigned long long)(rows / 8));
+      box[0] = 16; box[1] = 8; box[2] = R / 8; box[3] = 1;
+      side->inner = BIG_INNER; side->small_inner = 0; side->swapped = 0;
+    } else {
+      if (s0 != 1 || inner % 8 != 0) return false;
+      if (inner % R != 0 && R % inner != 0) return false;
+      dims[0] = 16; dims[1] = (cuuint64_t)K; dims[2] = (cuuint64_t)(inner / 8); dims[3] = (cuuint64_t)(rows / inner);
+      strides[0] = clamp_stride(16ull * sk);
+      strides[1] = 128;
+      strides[2] = clamp_stride(16ull * s1);
+      const bool small = inner < R;
+      box[0] = 16; box[1] = 8; box[2] = (small ? inner : R) / 8; box[3] = small ? R / inner : 1;
+      side->inner = (unsigned)inner; side->small_inner = small ? 1 : 0; side->swapped = 0;
+      if (s1 < 1) return false;
+    }
+  }
+  for (int i = 0; i < 3; ++i)
+    if (strides[i] % 16 != 0) return false;
+  const CUresult rc = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<c128*>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return rc == CUDA_SUCCESS;
+}
+
+template <bool AK, bool BK_>
+cudaError_t launch_tma(const CUtensorMap& ma, const CUtensorMap& mb, const TmaParams& p, int grid, cudaStream_t stream) {
+  zgemm_tma_kernel<AK, BK_><<<grid, THREADS, SMEM_BYTES, stream>>>(ma, mb, p);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t zgemm_tma_configure_device() {
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(zgemm_tma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES))) return e;
+  if ((e = cudaFuncSetAttribute(zgemm_tma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES))) return e;
+  if ((e = cudaFuncSetAttribute(zgemm_tma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES))) return e;
+  return cudaFuncSetAttribute(zgemm_tma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+}
+
+// Launch `d` (split-K fields already resolved by zgemm_auto) on the TMA kernel.  *used = false (and cudaSuccess) when the
+// shape is not expressible; nothing has been launched then.
+cudaError_t zgemm_tma_try(const GemmDesc& d, const GemmCtx& ctx, bool* used) {
+  *used = false;
+  if (d.batch != 1 || d.M <= 0 || d.N <= 0 || d.K < BK) return cudaSuccess;
+  if (d.splitk > 1 && (d.k_chunk % BK) != 0) return cudaSuccess;
+  CUtensorMap ma, mb;
+  TmaParams p;
+  bool ak = false, bk = false;
+  if (!make_side(&ma, &p.a, &ak, d.A, d.M, d.K, d.a_m_inner, d.a_m1, d.a_m0, d.a_k, BM)) return cudaSuccess;
+  if (!make_side(&mb, &p.b, &bk, d.B, d.N, d.K, d.b_n_inner, d.b_n1, d.b_n0, d.b_k, BN)) return cudaSuccess;
+  p.M = d.M; p.N = d.N; p.K = d.K;
+  p.tiles_m = (d.M + BM - 1) / BM;
+  p.tiles_n = (d.N + BN - 1) / BN;
+  p.splitk = d.splitk < 1 ? 1 : d.splitk;
+  p.k_chunk = d.k_chunk;
+  p.a_conj = d.a_conj ? 1u : 0u;
+  p.b_conj = d.b_conj ? 1u : 0u;
+  p.C = d.C; p.c_m_inner = d.c_m_inner; p.c_m1 = d.c_m1; p.c_m0 = d.c_m0; p.c_n = d.c_n; p.c_split = d.c_split;
+  p.alpha = d.alpha; p.beta = d.beta; p.c_stream = d.c_stream;
+  const long long total = (long long)p.tiles_m * p.tiles_n * p.splitk;
+  if (total > (1ll << 30)) return cudaSuccess;
+  const int grid = (int)(total < ctx.num_sms ? total : ctx.num_sms);
+  cudaError_t e;
+  {
+    ProfScope scope(ctx.stream, d.tag, 8.0 * (double)d.M * (double)d.N * (double)d.K, true);
+    if (ak && bk) e = launch_tma<true, true>(ma, mb, p, grid, ctx.stream);
+    else if (ak && !bk) e = launch_tma<true, false>(ma, mb, p, grid, ctx.stream);
+    else if (!ak && bk) e = launch_tma<false, true>(ma, mb, p, grid, ctx.stream);
+    else e = launch_tma<false, false>(ma, mb, p, grid, ctx.stream);
+  }
+  count_launch();
+  *used = true;
+  return e;
+}
+
+}  // namespace tdvp

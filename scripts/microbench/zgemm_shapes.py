@@ -37,9 +37,12 @@ SHAPES = [
 
 
 def main():
+    """usage: zgemm_shapes.py [label-filter|-] [auto|big|small|tiny|tma]"""
     eng = Engine(0)
     out = []
-    only = sys.argv[1] if len(sys.argv) > 1 else None
+    only = sys.argv[1] if len(sys.argv) > 1 and sys.argv[1] != "-" else None
+    cfg = sys.argv[2] if len(sys.argv) > 2 else "auto"
+    eng.set_gemm_config(cfg, 0, 0)
     for label, M, N, K, ta, tb in SHAPES:
         if only and only not in label:
             continue
@@ -68,7 +71,7 @@ def main():
         t1.synchronize()
         tf_cublas = 8.0 * M * N * K / (t0.elapsed_time(t1) * 1e-3) / 1e12
         err = float((C - ref).abs().max() / ref.abs().max())
-        rec = {"shape": label, "M": M, "N": N, "K": K, "ms": round(best, 4), "tflops": round(tf, 2),
+        rec = {"cfg": cfg, "shape": label, "M": M, "N": N, "K": K, "ms": round(best, 4), "tflops": round(tf, 2),
                "frac_of_37": round(tf / 37.0, 3), "cublas_tflops": round(tf_cublas, 2), "relerr": err}
         print(json.dumps(rec))
         out.append(rec)
