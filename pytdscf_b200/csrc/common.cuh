@@ -88,6 +88,7 @@ cudaError_t zgemm_auto(const GemmDesc& d, const GemmCtx& ctx);
 // can be described by tensor maps and sets *used; otherwise nothing is launched and the caller uses the cp.async kernels.
 cudaError_t zgemm_tma_configure_device();
 cudaError_t zgemm_tma_try(const GemmDesc& d, const GemmCtx& ctx, bool* used);
+bool zgemm_tma_eligible(const GemmDesc& d);
 constexpr size_t SPLITK_SCRATCH_ELEMS = size_t(18) << 20;  // 288 MiB of partial products
 // Number of kernel launches issued through this library since load (bench.py's gpu_launches claim).
 void count_launch(unsigned long long n = 1);

@@ -236,34 +236,98 @@ __global__ void __launch_bounds__(PT, 1) k_qr_panel(PanelArgs p) {
 }
 
 
-// ---- cluster variant: the whole panel is owned by ONE thread-block cluster (<= 16 CTAs), partial reductions are
-// exchanged through distributed shared memory and ordered by barrier.cluster (~0.2 us) instead of a grid-wide
-// cooperative sync (~3 us).  Same arithmetic and the same fixed CTA-order summation as k_qr_panel. ----
+// ---- cluster variant: the whole panel is owned by ONE thread-block cluster (<= 16 CTAs).  Same arithmetic and the same
+// fixed CTA-order summation as k_qr_panel, but the per-column exchange is a PUSH through distributed shared memory:
+// every CTA stores its 32 partial inner products (and the owner of the diagonal row that row) straight into the inbox of
+// every CTA of the cluster with st.async, which also counts the bytes on the receiver's mbarrier.  A CTA then waits on
+// its OWN barrier and reads its OWN shared memory -- no cluster-wide hardware barrier and no remote-load round trip per
+// column (r1: cluster.sync + DSMEM gather + zlarfg's division chain = ~5 us per column, a third of it barrier wait). ----
 constexpr int CT = 1024;          // threads per CTA, arranged (32, 32)
 constexpr int CTY = CT / 32;
+constexpr int MAXG = 16;          // largest cluster
+
+__device__ __forceinline__ unsigned qr_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned qr_mapa(unsigned local, int cta) {
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(local), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void qr_push(unsigned remote_addr, c128 v, unsigned remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];\n" ::"r"(remote_addr),
+               "d"(v.x), "d"(v.y), "r"(remote_bar)
+               : "memory");
+}
+__device__ __forceinline__ bool qr_try_wait(unsigned bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.b32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+// zlarfg scalars of one column: tau, s = 1 / (alpha - beta), beta, from alpha = (alphr, alphi) and g2 = |x|^2 of the
+// entries below the diagonal.  LAPACK forms the norm with dlapy3's scaled sum (3 divisions + sqrt) and the reciprocal with
+// zladiv; in the range where nothing can overflow or underflow the plain forms give the same values to rounding with one
+// sqrt and two reciprocals (the FP64 division chain was a third of the panel's per-column latency).
+__device__ __forceinline__ void zlarfg_scalars(double alphr, double alphi, double g2, c128& tau, c128& sc, double& hbeta) {
+  // |x|^2 below 1e-200 cannot be formed accurately as a plain sum of squares (the terms are denormal); LAPACK's
+  // dznrm2 rescales, here such a tail (|x| < 1e-100 next to O(1) data) is treated as exactly zero: the reflector
+  // degenerates to a phase on the diagonal and Q stays an isometry to rounding.
+  const bool tiny_tail = g2 < 1.0e-200;
+  if (tiny_tail && alphi == 0.0) { tau = {0.0, 0.0}; sc = {1.0, 0.0}; hbeta = alphr; return; }   // H = I (zlarfg: tau = 0)
+  if (tiny_tail) {
+    const double beta = (alphr >= 0.0) ? -hypot(alphr, alphi) : hypot(alphr, alphi);
+    tau = {(beta - alphr) / beta, -alphi / beta};
+    sc = {0.0, 0.0};                                    // v = e_1: the tail is dropped
+    hbeta = beta;
+    return;
+  }
+  double beta;
+  if (g2 < 1.0e280 && fabs(alphr) < 1.0e140 && fabs(alphi) < 1.0e140) beta = sqrt(alphr * alphr + alphi * alphi + g2);   // g2 >= 1e-200 here
+  else beta = dlapy3(alphr, alphi, sqrt(g2));
+  beta = (alphr >= 0.0) ? -beta : beta;                 // -SIGN(norm, alphr)
+  const double rb = 1.0 / beta;
+  tau = {(beta - alphr) * rb, -alphi * rb};
+  const double dr = alphr - beta, di = alphi;
+  const double rd = 1.0 / (dr * dr + di * di);           // s = 1 / (alpha - beta)
+  sc = {dr * rd, -di * rd};
+  hbeta = beta;
+}
 
 __global__ void __launch_bounds__(CT, 1) k_qr_panel_cluster(PanelArgs p) {
   extern __shared__ __align__(16) unsigned char smraw[];
   c128* S = reinterpret_cast<c128*>(smraw);                 // [rows_per_cta][NB]
   __shared__ c128 red[CTY][NB + 1];
-  __shared__ c128 pbuf[2][NB];   // this CTA's partial g (double-buffered by column parity)
-  __shared__ c128 rbuf[2][NB];   // diagonal row broadcast (valid in the owner CTA)
+  __shared__ __align__(16) c128 inbox[2][MAXG + 1][NB];     // [column parity][source CTA | MAXG: diagonal row][panel column]
+  __shared__ __align__(8) unsigned long long mbar[2];
   __shared__ c128 gtot[NB], rowc[NB];
   __shared__ double s_zl[5];     // zlarfg scalars of the current column: tau, 1/(alpha - beta), beta
   cg::cluster_group cluster = cg::this_cluster();
   const int tx = threadIdx.x, ty = threadIdx.y;
-  const int G = gridDim.x, b = blockIdx.x;
+  const int G = gridDim.x, b = blockIdx.x;                   // the grid is exactly one cluster: rank == blockIdx.x
   const int jb = p.jb, j0 = p.j0;
   const int r0 = j0 + b * p.rows_per_cta;
   int nrow = p.m - r0;
   if (nrow > p.rows_per_cta) nrow = p.rows_per_cta;
   if (nrow < 0) nrow = 0;
 
+  if (tx == 0 && ty == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(qr_smem_u32(&mbar[0])) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(qr_smem_u32(&mbar[1])) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
   for (int i = ty; i < nrow; i += CTY) {
     if (tx < jb) S[i * NB + tx] = p.A[(long long)(r0 + i) * p.lda + j0 + tx];
     else S[i * NB + tx] = {0.0, 0.0};
   }
   __syncthreads();
+  cluster.sync();                                            // every inbox barrier exists before the first remote push
 
   // partial g for column 0; for c > 0 it is accumulated while column c-1 is applied (one pass over the slab per column)
   c128 acc = {0.0, 0.0};
@@ -279,61 +343,46 @@ __global__ void __launch_bounds__(CT, 1) k_qr_panel_cluster(PanelArgs p) {
   for (int c = 0; c < ((p.dbg & 1) ? 0 : jb); ++c) {
     const int grow = j0 + c;
     const int buf = c & 1;
-    const int owner = (grow - j0) / p.rows_per_cta;
+    const unsigned parity = (unsigned)(c >> 1) & 1u;
+    const int owner = c / p.rows_per_cta;
     red[ty][tx] = acc;
     __syncthreads();
     {
-      // warp ty reduces column ty over the 32 row groups (fixed butterfly order), lane 0 publishes it
+      // warp ty reduces column ty over the 32 row groups (fixed butterfly order: every lane ends up with the total) and
+      // lane q pushes it into CTA q's inbox; warps 0..G-1 of the diagonal row's owner also push that row, one CTA each
       c128 t = red[tx][ty];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         t.x += __shfl_xor_sync(0xffffffffu, t.x, o);
         t.y += __shfl_xor_sync(0xffffffffu, t.y, o);
       }
-      if (tx == 0) pbuf[buf][ty] = t;
-      if (ty == 0 && b == owner) rbuf[buf][tx] = S[(grow - r0) * NB + tx];
+      const unsigned bar_local = qr_smem_u32(&mbar[buf]);
+      if (tx < G) qr_push(qr_mapa(qr_smem_u32(&inbox[buf][b][ty]), tx), t, qr_mapa(bar_local, tx));
+      if (b == owner && ty < G) qr_push(qr_mapa(qr_smem_u32(&inbox[buf][MAXG][tx]), ty), S[(grow - r0) * NB + tx], qr_mapa(bar_local, ty));
     }
-    cluster.sync();
     if (ty == 0) {
-      // all remote partials are requested before the first one is consumed (DSMEM latency ~215 cycles each)
-      c128 part[16];
-#pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        part[q] = {0.0, 0.0};
-        if (q < G) part[q] = cluster.map_shared_rank(&pbuf[buf][0], q)[tx];
+      const unsigned bar = qr_smem_u32(&mbar[buf]);
+      if (tx == 0) {
+        const unsigned bytes = (unsigned)((G + 1) * NB * sizeof(c128));
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
       }
-      const c128 rc = cluster.map_shared_rank(&rbuf[buf][0], owner)[tx];
+      __syncwarp();
+      while (!qr_try_wait(bar, parity)) {
+      }
       c128 t = {0.0, 0.0};
 #pragma unroll
-      for (int q = 0; q < 16; ++q) { t.x += part[q].x; t.y += part[q].y; }
+      for (int q = 0; q < MAXG; ++q) {
+        if (q < G) { const c128 v = inbox[buf][q][tx]; t.x += v.x; t.y += v.y; }
+      }
+      const c128 rc = inbox[buf][MAXG][tx];
       gtot[tx] = t;
       rowc[tx] = rc;
       // zlarfg by this warp (every lane the same values), published through shared memory
       const double g2 = __shfl_sync(0xffffffffu, t.x, c);
       const double alphr = __shfl_sync(0xffffffffu, rc.x, c), alphi = __shfl_sync(0xffffffffu, rc.y, c);
-      // |x|^2 below 1e-200 cannot be formed accurately as a plain sum of squares (the terms are denormal); LAPACK's
-      // dznrm2 rescales, here such a tail (|x| < 1e-100 next to O(1) data) is treated as exactly zero: the reflector
-      // degenerates to a phase on the diagonal and Q stays an isometry to rounding.
-      const bool tiny_tail = g2 < 1.0e-200;
-      const double xnorm = tiny_tail ? 0.0 : sqrt(g2);
       c128 tau_, sc_;
       double hb_;
-      if (xnorm == 0.0 && alphi == 0.0) {
-        tau_ = {0.0, 0.0}; sc_ = {1.0, 0.0}; hb_ = alphr;
-      } else if (tiny_tail) {
-        const double beta = (alphr >= 0.0) ? -hypot(alphr, alphi) : hypot(alphr, alphi);
-        tau_ = {(beta - alphr) / beta, -alphi / beta};
-        sc_ = {0.0, 0.0};                                    // v = e_1: the tail is dropped
-        hb_ = beta;
-      } else {
-        double beta = dlapy3(alphr, alphi, xnorm);
-        beta = (alphr >= 0.0) ? -beta : beta;
-        tau_ = {(beta - alphr) / beta, -alphi / beta};
-        const double dr = alphr - beta, di = alphi;
-        const double den = dr * dr + di * di;
-        sc_ = {dr / den, -di / den};
-        hb_ = beta;
-      }
+      zlarfg_scalars(alphr, alphi, g2, tau_, sc_, hb_);
       if (tx == 0) {
         s_zl[0] = tau_.x; s_zl[1] = tau_.y; s_zl[2] = sc_.x; s_zl[3] = sc_.y; s_zl[4] = hb_;
         if (b == 0) { p.tau[2 * (j0 + c)] = tau_.x; p.tau[2 * (j0 + c) + 1] = tau_.y; }
@@ -416,8 +465,12 @@ __global__ void __launch_bounds__(CT, 1) k_qr_panel_cluster(PanelArgs p) {
   __threadfence();
   cluster.sync();
   if (b != 0) return;
+  // ---- T (zlarft, forward / columnwise) by CTA 0.  Row r of T depends only on row r itself:
+  // T[r][c] = -tau_c sum_{q = r}^{c-1} T[r][q] Z[q][c], so lane r of ONE warp builds its row without any barrier
+  // (T is kept transposed in shared memory: lanes read consecutive addresses, Z[q][c] is a broadcast). ----
   c128* Z = S;
-  c128* T = S + NB * NB;
+  c128* Tt = S + NB * NB;        // Tt[q * NB + r] = T[r][q]
+  __shared__ c128 taus[NB];
   {
     const int a = ty;
     c128 z = {0.0, 0.0};
@@ -426,22 +479,35 @@ __global__ void __launch_bounds__(CT, 1) k_qr_panel_cluster(PanelArgs p) {
       z.y += __ldcg(&p.zpart[((size_t)q * NB + a) * NB * 2 + 2 * tx + 1]);
     }
     Z[a * NB + tx] = z;
-    T[a * NB + tx] = {0.0, 0.0};
+    Tt[a * NB + tx] = {0.0, 0.0};
+    if (ty == 0) taus[tx] = (tx < jb) ? c128{__ldcg(&p.tau[2 * (j0 + tx)]), __ldcg(&p.tau[2 * (j0 + tx) + 1])} : c128{0.0, 0.0};
   }
   __syncthreads();
-  for (int c = 0; c < ((p.dbg & 2) ? 0 : jb); ++c) {
-    const c128 tau = {__ldcg(&p.tau[2 * (j0 + c)]), __ldcg(&p.tau[2 * (j0 + c) + 1])};
-    if (ty == 0 && tx < c) {
-      c128 s = {0.0, 0.0};
-      for (int q = tx; q < c; ++q) s = cadd(s, cmul(T[tx * NB + q], Z[q * NB + c]));
-      const c128 r = cmul(tau, s);
-      T[tx * NB + c] = {-r.x, -r.y};
+  if (ty == 0 && !(p.dbg & 2)) {
+    const int r = tx;
+    if (r < jb) {
+      Tt[r * NB + r] = taus[r];
+      for (int c = r + 1; c < jb; ++c) {
+        c128 s0 = {0.0, 0.0}, s1 = {0.0, 0.0};
+        int q = r;
+        for (; q + 1 < c; q += 2) {
+          const c128 a0 = Tt[q * NB + r], z0 = Z[q * NB + c];
+          const c128 a1 = Tt[(q + 1) * NB + r], z1 = Z[(q + 1) * NB + c];
+          s0.x += a0.x * z0.x - a0.y * z0.y; s0.y += a0.x * z0.y + a0.y * z0.x;
+          s1.x += a1.x * z1.x - a1.y * z1.y; s1.y += a1.x * z1.y + a1.y * z1.x;
+        }
+        if (q < c) {
+          const c128 a0 = Tt[q * NB + r], z0 = Z[q * NB + c];
+          s0.x += a0.x * z0.x - a0.y * z0.y; s0.y += a0.x * z0.y + a0.y * z0.x;
+        }
+        const c128 rr = cmul(taus[c], cadd(s0, s1));
+        Tt[c * NB + r] = {-rr.x, -rr.y};
+      }
     }
-    if (ty == 0 && tx == c) T[c * NB + c] = tau;
-    __syncthreads();
   }
+  __syncthreads();
   c128* Tout = p.Tall + (size_t)(j0 / NB) * NB * NB;
-  Tout[ty * NB + tx] = T[ty * NB + tx];
+  Tout[ty * NB + tx] = Tt[tx * NB + ty];
 }
 
 __global__ void k_set_identity(c128* Q, int m, int n, int ld) {
@@ -490,7 +556,7 @@ int gemmq(Handle* h, const GemmDesc& g) {
 
 }  // namespace
 
-constexpr int CL_ROWS = 384;     // slab rows per CTA in the cluster kernel (384*32*16 B = 192 KiB)
+constexpr int CL_ROWS = 352;     // slab rows per CTA in the cluster kernel (352*32*16 B = 176 KiB + 38 KiB of static buffers)
 constexpr int QR_MAX_SMS = 256;  // workspace bound for the per-CTA partials (B200: 148 SMs)
 
 size_t qr_ws_elems(int m, int n) {

@@ -388,7 +388,10 @@ inline long long tiles_of(const GemmDesc& d, int bm, int bn) {
 // `lone` seconds per unit of k when it has an SM to itself and `full` when `cps` of them share the SM; K0 = prologue +
 // epilogue in units of k.  time = waves * (k_chunk + K0) * per_k  (+ the fixed-order reduction for split-K).
 struct CfgModel { int id, bm, bn, bk, cps, min_chunk; double lone, full, K0, bias; };
-constexpr CfgModel MODELS[3] = {
+constexpr CfgModel MODELS[4] = {
+    {4, 128, 64, 16, 1, 128, 0.2606e-6, 0.2606e-6, 40.0, 1.00},  // tma: persistent big tile (7.70 ms on 8192x4096x1024, 0.231 ms on
+                                                                 // 1280x2560x256: profiles/r2_zgemm_shapes_tma.jsonl); replaces "big"
+                                                                 // whenever tensor maps can describe the operands
     {1, 128, 64, 16, 1, 128, 0.282e-6, 0.282e-6, 32.0, 1.00},  // big   (8.33 ms / 28 waves / 1056 k on 8192x4096x1024)
     {2, 64, 32, 8, 4, 64, 0.075e-6, 0.30e-6, 24.0, 1.00},      // small (only when forced: never the best in the sweep)
     {3, 32, 32, 8, 4, 32, 0.040e-6, 0.140e-6, 16.0, 1.00},     // tiny  (832 us / 10.9 waves / 528 k on 1536x4096x512)
@@ -405,8 +408,11 @@ inline Choice choose(const GemmDesc& d, const GemmCtx& ctx) {
   // >= 8 full waves of big tiles with a long K: wave quantisation is < 6 % and the big tiles need the least L2 traffic
   // per flop (short-K GEMMs such as H_eff stage 2 are prologue-bound and keep the free choice)
   const bool large = tiles_of(d, 128, 64) >= 8 * 148 && d.K >= 512;
+  const bool tma_ok = (ctx.force_cfg == 0 || ctx.force_cfg == 4) && zgemm_tma_eligible(d);
   for (const CfgModel& m : MODELS) {
-    if (forced ? forced != m.id : (m.id == 2 || (large && m.id != 1))) continue;
+    if (m.id == 4 ? !tma_ok : (m.id == 1 && tma_ok)) continue;           // the TMA kernel stands in for the big tile
+    const int mid = m.id == 4 ? 1 : m.id;                                 // ... and shares its geometry / forcing rules
+    if (forced ? forced != mid : (mid == 2 || (large && mid != 1))) continue;
     const long long tiles = tiles_of(d, m.bm, m.bn);
     const int slots = 148 * m.cps;
     int max_s = 1;
@@ -431,7 +437,7 @@ inline Choice choose(const GemmDesc& d, const GemmCtx& ctx) {
       if (m.id == 3 && units >= slots) waves = (double)units / slots + 0.5;
       double t = waves * (chunk + m.K0) * per_k * m.bias;
       if (S > 1) t += (double)(S + 2) * d.M * d.N * 16.0 / bw + 4.0e-6;
-      if (t < best.t * (S > 1 && best.cfg == m.id ? 0.97 : 1.0)) { best.t = t; best.cfg = m.id; best.S = S; best.chunk = chunk; }
+      if (t < best.t * (S > 1 && best.cfg == mid ? 0.97 : 1.0)) { best.t = t; best.cfg = mid; best.S = S; best.chunk = chunk; }
     }
   }
   return best;

@@ -317,10 +317,17 @@ inline cuuint64_t clamp_stride(unsigned long long s) {
 // One operand with `rows` rows (two-level: row = r1 * inner + r0) and K columns, element (row, k) at
 // ptr + r1 * s1 + r0 * s0 + k * sk (complex128 units).  R = tile rows (128 for A, 64 for B).  Returns false when the
 // operand cannot be described (the caller then uses the cp.async kernel).
-bool make_side(CUtensorMap* map, TmaSide* side, bool* kmajor, const c128* ptr, long long rows, int K, int inner, long long s1,
+struct SidePlan {
+  cuuint64_t dims[4], strides[3];
+  cuuint32_t box[4];
+};
+
+bool plan_side(SidePlan* pl, TmaSide* side, bool* kmajor, const c128* ptr, long long rows, int K, int inner, long long s1,
                long long s0, long long sk, int R) {
-  PFN_cuTensorMapEncodeTiled enc = encode_fn();
-  if (!enc || rows <= 0 || K < BK) return false;
+  cuuint64_t* dims = pl->dims;
+  cuuint64_t* strides = pl->strides;
+  cuuint32_t* box = pl->box;
+  if (rows <= 0 || K < BK) return false;
   if ((reinterpret_cast<uintptr_t>(ptr) & 15u) != 0) return false;
   if (inner <= 0) return false;
   const bool two = inner > 1 && inner < rows;
@@ -330,8 +337,6 @@ bool make_side(CUtensorMap* map, TmaSide* side, bool* kmajor, const c128* ptr, l
   } else if (rows % inner != 0) {
     return false;
   }
-  cuuint64_t dims[4], strides[3];
-  cuuint32_t box[4], estr[4] = {1, 1, 1, 1};
   if (sk == 1) {
     *kmajor = true;
     if (!two) {
@@ -390,7 +395,16 @@ bool make_side(CUtensorMap* map, TmaSide* side, bool* kmajor, const c128* ptr, l
   }
   for (int i = 0; i < 3; ++i)
     if (strides[i] % 16 != 0) return false;
-  const CUresult rc = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<c128*>(ptr), dims, strides, box, estr,
+  return true;
+}
+
+bool make_side(CUtensorMap* map, TmaSide* side, bool* kmajor, const c128* ptr, long long rows, int K, int inner, long long s1,
+               long long s0, long long sk, int R) {
+  PFN_cuTensorMapEncodeTiled enc = encode_fn();
+  SidePlan pl;
+  if (!enc || !plan_side(&pl, side, kmajor, ptr, rows, K, inner, s1, s0, sk, R)) return false;
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult rc = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<c128*>(ptr), pl.dims, pl.strides, pl.box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return rc == CUDA_SUCCESS;
@@ -410,6 +424,16 @@ cudaError_t zgemm_tma_configure_device() {
   if ((e = cudaFuncSetAttribute(zgemm_tma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES))) return e;
   if ((e = cudaFuncSetAttribute(zgemm_tma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES))) return e;
   return cudaFuncSetAttribute(zgemm_tma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+}
+
+// Shape test only (no driver call): can both operands of `d` be described by tensor maps?  Used by the launch cost model.
+bool zgemm_tma_eligible(const GemmDesc& d) {
+  if (d.batch != 1 || d.M <= 0 || d.N <= 0 || d.K < BK || !encode_fn()) return false;
+  SidePlan pl;
+  TmaSide side;
+  bool km;
+  return plan_side(&pl, &side, &km, d.A, d.M, d.K, d.a_m_inner, d.a_m1, d.a_m0, d.a_k, BM) &&
+         plan_side(&pl, &side, &km, d.B, d.N, d.K, d.b_n_inner, d.b_n1, d.b_n0, d.b_k, BN);
 }
 
 // Launch `d` (split-K fields already resolved by zgemm_auto) on the TMA kernel.  *used = false (and cudaSuccess) when the
