@@ -111,8 +111,15 @@ class DeviceMPO:
         ids = {}      # (key, site) -> (l_id, r_id)
         self.bond_ids: dict = {}   # (key, bond b between sites b-1 and b) -> (prefix channel, suffix channel)
         permuted = {}  # (key, site) -> core with re-ordered MPO bond channels
-        for key, cores in mpo.operators.items():
-            sites = [ind[0] if isinstance(ind, tuple) else int(ind) for ind in key]
+        # per key the cores as the site lists hold them NOW (a Liouville sub-space projection, ``project_subspace``, has
+        # already cut their physical indices there), in site order
+        by_key: dict = {}
+        for cps in mpo.calc_point:
+            for c in cps:
+                by_key.setdefault(c.key, []).append((c.psite, c.data))
+        for key, lst in by_key.items():
+            sites = [s for s, _ in lst]
+            cores = [d for _, d in lst]
             if any(isinstance(c, int) for c in cores):
                 continue
             cores = [np.asarray(c) for c in cores]
@@ -240,6 +247,7 @@ class MPSCoefCuda:
         self.record_trace = False
         self.site_offset = 0   # global index of local site 0 (site-parallel segments share one global MPO)
         self.site_now = 0      # reference: helper._Debug.site_now, the key of the Krylov warm-up history
+        self.subspace: dict[int, tuple[int, tuple[int, ...]]] = {}   # Liouville sub-space sites: site -> (full d, kept indices)
 
     # ------------------------------------------------------------------------------------------
     @classmethod
@@ -249,8 +257,6 @@ class MPSCoefCuda:
         completion of the padded tensors matches the reference (tests/test_gpu_kernels.py)."""
         weights, scale, m = model.initial_core_weights()
         dims = [len(model.get_primbas(0, i)) for i in range(model.get_ndof())]
-        if model.subspace_inds is not None:
-            raise NotImplementedError("Liouville sub-space projection of the initial state is not implemented yet")
         n = len(dims)
         host = []
         for i in range(n):
@@ -280,7 +286,23 @@ class MPSCoefCuda:
             cores[0] = cores[0] * (scale / nrm)
         else:
             cores[0] = cores[0] * scale
-        return cls(eng, cores)
+        subspace = {}
+        if getattr(model, "subspace_inds", None):
+            # Liouville sub-space projection of the finished (right-canonical) MPDO, reference ``project_subspace``
+            # (_mps_mpo.py:196-220): keep the listed physical indices, then cut every bond back to the static rule
+            # for the reduced site dimensions.  Index selection only -- nothing is re-orthogonalised, as in the reference.
+            for isite, P in model.subspace_inds.items():
+                P = tuple(int(i) for i in P)
+                subspace[int(isite)] = (dims[isite], P)
+                idx = torch.as_tensor(P, dtype=torch.long, device=cores[isite].device)
+                cores[isite] = cores[isite].index_select(1, idx)
+                dims[isite] = len(P)
+            for i in range(n):
+                ml, mr = bond_dims(dims, i, m)
+                cores[i] = cores[i][: (1 if i == 0 else ml), :, : (1 if i == n - 1 else mr)].contiguous()
+        me = cls(eng, cores)
+        me.subspace = subspace
+        return me
 
     @property
     def sites(self) -> list[SiteCoef]:
@@ -570,8 +592,65 @@ class MPSCoefCuda:
             self.op_sys_sites = None
 
     # -- observables ---------------------------------------------------------------------------------
-    def expectation(self, H: DeviceMPO) -> complex:
-        """<Psi|Op|Psi> at the centre site 0: full right-environment rebuild + one matvec + inner product."""
+    def _liouville_four(self, isite: int) -> torch.Tensor:
+        """Site tensor of an MPDO as (D_l, q, q, D_r); sub-space sites are embedded back into the full q x q index first
+        (reference ``define_reshape_mat`` / ``_reshape_core``, _mps_mpo.py:135-194)."""
+        t = self.sites[isite].data
+        Dl, dd, Dr = t.shape
+        if isite + self.site_offset in self.subspace:
+            full_d, P = self.subspace[isite + self.site_offset]
+            full = torch.zeros((Dl, full_d, Dr), dtype=t.dtype, device=t.device)
+            full[:, torch.as_tensor(P, dtype=torch.long, device=t.device), :] = t
+            t, dd = full, full_d
+        q = math.isqrt(dd)
+        if q * q != dd:
+            raise ValueError("Liouville-space sites need a square physical dimension")
+        return t.reshape(Dl, q, q, Dr)
+
+    def _exp_liouville(self, H: DeviceMPO) -> complex:
+        """Tr(O rho) of a Liouville-space MPDO for a Hilbert-space operator O given as MPO cores of physical dimension
+        q = sqrt(d) (reference ``_exp_liouville``, _mps_cls.py:3769-3838: per MPO key a left-to-right chain
+        "ab,bcde,adcf->fe"; sites the key does not touch contribute their partial trace "ab,bcce->ae").  Two DMMA GEMMs
+        per site and key; no canonical form is needed.  As in the reference the scalar ``coupleJ`` term is not included."""
+        eng = self.eng
+        by_key: dict = {}
+        for p, terms in enumerate(H.calc_point):
+            for t in terms:
+                by_key.setdefault(t.key, {})[p] = t.core
+        total = 0.0 + 0.0j
+        four = [self._liouville_four(i) for i in range(self.nsite)]
+        for key, cores in by_key.items():
+            left = torch.ones((1, 1), dtype=torch.complex128, device=eng.torch_device)
+            for isite in range(self.nsite):
+                t4 = four[isite]
+                Dl, q, _, Dr = t4.shape
+                core = cores.get(isite + self.site_offset)
+                if core is None:
+                    m = torch.diagonal(t4, dim1=1, dim2=2).sum(-1).contiguous()              # partial trace: (D_l, D_r)
+                    left = eng.zgemm(left, m)
+                    continue
+                w = int(left.shape[0])
+                if core.wl != w or int(core.data.shape[1]) != q:
+                    raise ValueError(f"observable core at site {isite} has shape {tuple(core.data.shape)}; expected MPO bond {w} "
+                                     f"and the Hilbert-space dimension {q} of a Liouville site of dimension {q * q}")
+                X = eng.zgemm(left, t4.reshape(Dl, q * q * Dr).contiguous())                 # [a, (c, d, e)]
+                if core.data.dim() == 4:
+                    perm = core.perm if core.perm is not None else core.data.permute(0, 2, 1, 3).contiguous()
+                    Wm = perm.reshape(w * q * q, core.wr)                                     # perm[a, c, d, f] = W[a, d, c, f]
+                    left = eng.zgemm(Wm, X.reshape(w * q * q, Dr), transA=1)
+                else:                                                                          # diagonal core W[a, c, f]
+                    Xd = torch.diagonal(X.reshape(w, q, q, Dr), dim1=1, dim2=2).permute(0, 2, 1).contiguous()
+                    left = eng.zgemm(core.data.reshape(w * q, core.wr), Xd.reshape(w * q, Dr), transA=1)
+            if tuple(left.shape) != (1, 1):
+                raise ValueError(f"MPO key {key} does not close: final block has shape {tuple(left.shape)}")
+            total += complex(left.cpu().numpy()[0, 0])
+        return total
+
+    def expectation(self, H: DeviceMPO, space: str = "hilbert") -> complex:
+        """<Psi|Op|Psi> at the centre site 0: full right-environment rebuild + one matvec + inner product.
+        ``space="liouville"``: Tr(Op rho) of the vectorised density matrix instead (``_exp_liouville``)."""
+        if space == "liouville":
+            return self._exp_liouville(H)
         assert self.sites[0].gauge == "Psi", "the MPS must be canonical around site 0"
         n = self.nsite
         env = self.construct_op_sites(n - 1, 0, H).pop() if n > 1 else self.construct_op_zerosite()
@@ -648,13 +727,7 @@ class MPSCoefCuda:
         center = max((i for i, n in enumerate(remain_nleg) if n in (1, 2)), default=None)
         if center is None:
             raise ValueError("No site with 2 legs found in remain_nleg")
-        four = []
-        for s in self.sites:
-            Dl, dd, Dr = s.data.shape
-            q = math.isqrt(dd)
-            if q * q != dd:
-                raise ValueError("Liouville-space sites need a square physical dimension")
-            four.append(s.data.reshape(Dl, q, q, Dr))
+        four = [self._liouville_four(i) for i in range(self.nsite)]
         left = torch.ones(1, dtype=torch.complex128, device=four[0].device)
         for isite in range(center):
             t = four[isite]

@@ -38,7 +38,8 @@ class WFunc:
 
     def expectation(self, op) -> float:
         """Real part of <Psi|Op|Psi> (reference ``wavefunction.py:90-114`` also returns ``.real``)."""
-        val = self.ci_coef.expectation(self.device_op(op))
+        val = self.ci_coef.expectation(self.device_op(op), space=self.space) if self.space == "liouville" else \
+            self.ci_coef.expectation(self.device_op(op))
         return None if val is None else val.real   # site-parallel runs: only rank 0 holds the value
 
     def autocorr(self) -> complex:

@@ -262,3 +262,14 @@ def test_adaptive_tdvp_gpu(case, tmp_path):
         assert abs(rec["autocorr"] - complex(row[1], row[2])) <= tol["autocorr"]
         assert abs(rec["energy"] - row[3]) <= tol["energy"] * abs(row[3]) and abs(rec["norm"] - row[5]) <= REL
     assert_same_state(wf.ci_coef.to_numpy(), g["final"], tol["state"])
+
+
+@pytest.mark.parametrize("tag", ["full", "sub"])
+def test_liouville_observables_and_subspace(tag, tmp_path):
+    """Liouville space on the GPU: Tr(O rho) of three Hilbert-space observables per step (reference ``_exp_liouville``,
+    pytdscf/_mps_cls.py:3769-3838), norm / populations, and the sub-space projection of the initial MPDO
+    (``project_subspace``, pytdscf/_mps_mpo.py:196-220), against goldens of the unmodified reference."""
+    from tests.liouville_obs_cases import check_case, run_case
+
+    sim, wf = run_case(tag, tmp_path)
+    check_case(tag, sim, wf, tol_expect=REL, tol_state=1e-9)
