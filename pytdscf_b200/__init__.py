@@ -8,8 +8,9 @@ from .basis import Boson, Exciton, HarmonicOscillator
 from .dvr_operator_cls import TensorOperator, construct_kinetic_mpo
 from .hamiltonian_cls import TensorHamiltonian
 from .model_cls import BasInfo, Model
+from .checkpoint import export_mpo_npz, import_mpo_npz, read_reference_wavefunction, write_reference_wavefunction
 from .simulator_cls import Simulator
 
 __version__ = "0.1.0"
-__all__ = ["units", "Boson", "Exciton", "HarmonicOscillator", "TensorOperator", "construct_kinetic_mpo",
+__all__ = ["export_mpo_npz", "import_mpo_npz", "read_reference_wavefunction", "write_reference_wavefunction", "units", "Boson", "Exciton", "HarmonicOscillator", "TensorOperator", "construct_kinetic_mpo",
            "TensorHamiltonian", "BasInfo", "Model", "Simulator", "__version__"]

@@ -119,16 +119,31 @@ class Simulator:
             self.eng = Engine(self.device)
         return self.eng
 
-    def save_wavefunction(self, wf: WFunc, ext: str = ""):
+    def save_wavefunction(self, wf: WFunc, ext: str = "", reference_format: bool = False):
+        """``wf_<jobname><ext>.pkl``: NumPy site tensors + gauge labels (own format), or -- ``reference_format=True`` -- a
+        pickle that the reference's ``Simulator(...).propagate(restart=True)`` loads as its own ``WFunc``
+        (pytdscf/simulator_cls.py:501-507; see ``pytdscf_b200/checkpoint.py``)."""
         path = f"wf_{self.jobname}{ext}.pkl"
+        cores, gauges = wf.ci_coef.to_numpy(), [s.gauge for s in wf.ci_coef.sites]
+        if reference_format:
+            from .checkpoint import write_reference_wavefunction
+
+            return write_reference_wavefunction(path, cores, gauges)
         with open(path, "wb") as f:
-            pickle.dump({"cores": wf.ci_coef.to_numpy(), "gauges": [s.gauge for s in wf.ci_coef.sites]}, f)
+            pickle.dump({"cores": cores, "gauges": gauges}, f)
         return path
 
     def load_wavefunction(self, ext: str = "") -> WFunc:
+        """Load ``wf_<jobname><ext>.pkl`` written by this package OR by the reference (a ``dill`` dump of its ``WFunc``,
+        pytdscf/simulator_cls.py:577-589; read without importing the reference)."""
+        from .checkpoint import is_reference_pickle, read_reference_wavefunction
+
         path = f"wf_{self.jobname}{ext}.pkl"
-        with open(path, "rb") as f:
-            d = pickle.load(f)
+        if is_reference_pickle(path):
+            d = read_reference_wavefunction(path)
+        else:
+            with open(path, "rb") as f:
+                d = pickle.load(f)
         eng = self._engine()
         return WFunc(MPSCoefCuda(eng, [eng.to_device(c) for c in d["cores"]], d["gauges"]), eng, self.model.space)
 

@@ -273,3 +273,22 @@ def test_liouville_observables_and_subspace(tag, tmp_path):
 
     sim, wf = run_case(tag, tmp_path)
     check_case(tag, sim, wf, tol_expect=REL, tol_state=1e-9)
+
+
+def test_restart_from_reference_checkpoint_on_gpu(tmp_path):
+    """A ``wf_*.pkl`` written by the reference (dill dump of its WFunc) restarts on the GPU and continues with the
+    reference's own energies (tests/golden/make_golden_checkpoint.py), SURVEY 8(f4)."""
+    import shutil
+
+    import pytdscf_b200 as tb
+    from tests.golden_io import GOLDEN_DIR
+
+    g = load_run("exciton_D6")
+    os.chdir(tmp_path)
+    shutil.copy(os.path.join(GOLDEN_DIR, "wf_ref_exciton_D6.pkl"), "wf_ck.pkl")
+    sim = tb.Simulator("ck", build_model(g), backend="cuda", verbose=0)
+    ener, wf = sim.propagate(stepsize=0.1, maxstep=3, restart=True, loadfile_ext="", savefile_ext="_cont", autocorr=False,
+                             norm=False, populations=False)
+    ref = dict(np.load(os.path.join(GOLDEN_DIR, "checkpoint.npz")))["energies_restart_reference_file"]
+    for rec, e in zip(sim.history, ref, strict=True):
+        assert abs(rec["energy"] - e) <= REL * abs(e)
