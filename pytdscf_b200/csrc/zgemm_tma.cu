@@ -28,16 +28,27 @@ namespace tdvp {
 
 namespace {
 
-constexpr int BM = 128, BN = 64, BK = 16, STAGES = 4;
+constexpr int BK = 16;
 constexpr int CONSUMER_WARPS = 8;
+// Two tile geometries, both 8 consumer warps of 32 x 32: 4 x 2 warps (CTA tile 128 x 64, 4 stages) for the bulk of the work and
+// 8 x 1 warps (256 x 32, 3 stages) for GEMMs whose N is at most 32 (H_eff stage 2 at d w <= 32: with a 64-wide tile half of
+// every B fragment would be zero padding).
+template <int WMW_, int WNW_, int STAGES_>
+struct TmaCfg {
+  static constexpr int WMW = WMW_, WNW = WNW_, STAGES = STAGES_;
+  static constexpr int BM = 32 * WMW, BN = 32 * WNW;
+  static constexpr int SLAB_A = BM * 128, SLAB_B = BN * 128;          // bytes of one 8-k slab of the A / B tile
+  static constexpr int STAGE_BYTES = 2 * (SLAB_A + SLAB_B);            // two slabs (BK = 16) of both operands
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;  // + alignment slack + barriers
+  static_assert(WMW * WNW == CONSUMER_WARPS, "8 consumer warps");
+};
+using WideCfg = TmaCfg<4, 2, 4>;     // 128 x 64, 4 x 48 KiB
+using TallCfg = TmaCfg<8, 1, 3>;     // 256 x 32, 3 x 72 KiB
 // Registers are allocated per warpgroup (4 warps): 2 consumer warpgroups + 1 producer warpgroup (one working lane).  The
 // launch gives every thread 168 registers (65536 / 384); the producer group then shrinks to 40 and the consumers grow
 // to 232 with setmaxnreg, as warp-specialised Hopper / Blackwell GEMMs do.
 constexpr int THREADS = 32 * (CONSUMER_WARPS + 4);
 constexpr int PRODUCER_REGS = 40, CONSUMER_REGS = 232;
-constexpr int SLAB_A = BM * 128, SLAB_B = BN * 128;          // bytes of one 8-k slab of the A / B tile
-constexpr int STAGE_BYTES = 2 * (SLAB_A + SLAB_B);            // two slabs (BK = 16) of both operands: 48 KiB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;  // + alignment slack + barriers
 constexpr unsigned BIG_INNER = 1u << 30;                      // "plain" operand: a single row level
 
 struct TmaSide {
@@ -126,9 +137,10 @@ struct Frag {
   double2 b[4];
 };
 
-template <bool A_KMAJOR, bool B_KMAJOR>
+template <typename C, bool A_KMAJOR, bool B_KMAJOR>
 __global__ void __launch_bounds__(THREADS, 1)
     zgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TmaParams p) {
+  constexpr int BM = C::BM, BN = C::BN, STAGES = C::STAGES, SLAB_A = C::SLAB_A, SLAB_B = C::SLAB_B, STAGE_BYTES = C::STAGE_BYTES;
   extern __shared__ unsigned char smem_raw[];
   const unsigned raw = smem_u32(smem_raw);
   const unsigned base = (raw + 1023u) & ~1023u;                  // SWIZZLE_128B pattern repeats every 1024 B of address
@@ -179,7 +191,7 @@ __global__ void __launch_bounds__(THREADS, 1)
   // ================= consumers: 4 x 2 warps of 32 x 32 complex =================
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(CONSUMER_REGS));
   const int g = lane >> 2, q = lane & 3, hq = q >> 1, odd = q & 1;
-  const int wm = warp & 3, wn = warp >> 2;
+  const int wm = warp % C::WMW, wn = warp / C::WMW;
   // 16-byte chunk (after the hardware XOR) of the complex k = 4 hq + t this lane handles in step t, for row (or, on
   // row-contiguous operands, 8-row group member) g -- the same value serves both operands and both majors
   int off_t[4];
@@ -410,20 +422,33 @@ bool make_side(CUtensorMap* map, TmaSide* side, bool* kmajor, const c128* ptr, l
   return rc == CUDA_SUCCESS;
 }
 
-template <bool AK, bool BK_>
-cudaError_t launch_tma(const CUtensorMap& ma, const CUtensorMap& mb, const TmaParams& p, int grid, cudaStream_t stream) {
-  zgemm_tma_kernel<AK, BK_><<<grid, THREADS, SMEM_BYTES, stream>>>(ma, mb, p);
+template <typename C>
+cudaError_t launch_tma(bool ak, bool bk, const CUtensorMap& ma, const CUtensorMap& mb, const TmaParams& p, int grid, cudaStream_t stream) {
+  if (ak && bk) zgemm_tma_kernel<C, true, true><<<grid, THREADS, C::SMEM_BYTES, stream>>>(ma, mb, p);
+  else if (ak && !bk) zgemm_tma_kernel<C, true, false><<<grid, THREADS, C::SMEM_BYTES, stream>>>(ma, mb, p);
+  else if (!ak && bk) zgemm_tma_kernel<C, false, true><<<grid, THREADS, C::SMEM_BYTES, stream>>>(ma, mb, p);
+  else zgemm_tma_kernel<C, false, false><<<grid, THREADS, C::SMEM_BYTES, stream>>>(ma, mb, p);
   return cudaGetLastError();
 }
+
+template <typename C>
+cudaError_t configure_tma() {
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(zgemm_tma_kernel<C, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES))) return e;
+  if ((e = cudaFuncSetAttribute(zgemm_tma_kernel<C, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES))) return e;
+  if ((e = cudaFuncSetAttribute(zgemm_tma_kernel<C, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES))) return e;
+  return cudaFuncSetAttribute(zgemm_tma_kernel<C, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+}
+
+// N <= 32 and enough rows to fill the machine with 256-row tiles: the tall geometry
+inline bool use_tall(const GemmDesc& d) { return d.N <= 32 && d.M >= 256 * 148; }
 
 }  // namespace
 
 cudaError_t zgemm_tma_configure_device() {
   cudaError_t e;
-  if ((e = cudaFuncSetAttribute(zgemm_tma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES))) return e;
-  if ((e = cudaFuncSetAttribute(zgemm_tma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES))) return e;
-  if ((e = cudaFuncSetAttribute(zgemm_tma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES))) return e;
-  return cudaFuncSetAttribute(zgemm_tma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if ((e = configure_tma<WideCfg>())) return e;
+  return configure_tma<TallCfg>();
 }
 
 // Shape test only (no driver call): can both operands of `d` be described by tensor maps?  Used by the launch cost model.
@@ -432,8 +457,9 @@ bool zgemm_tma_eligible(const GemmDesc& d) {
   SidePlan pl;
   TmaSide side;
   bool km;
-  return plan_side(&pl, &side, &km, d.A, d.M, d.K, d.a_m_inner, d.a_m1, d.a_m0, d.a_k, BM) &&
-         plan_side(&pl, &side, &km, d.B, d.N, d.K, d.b_n_inner, d.b_n1, d.b_n0, d.b_k, BN);
+  const int bm = use_tall(d) ? TallCfg::BM : WideCfg::BM, bn = use_tall(d) ? TallCfg::BN : WideCfg::BN;
+  return plan_side(&pl, &side, &km, d.A, d.M, d.K, d.a_m_inner, d.a_m1, d.a_m0, d.a_k, bm) &&
+         plan_side(&pl, &side, &km, d.B, d.N, d.K, d.b_n_inner, d.b_n1, d.b_n0, d.b_k, bn);
 }
 
 // Launch `d` (split-K fields already resolved by zgemm_auto) on the TMA kernel.  *used = false (and cudaSuccess) when the
@@ -445,6 +471,8 @@ cudaError_t zgemm_tma_try(const GemmDesc& d, const GemmCtx& ctx, bool* used) {
   CUtensorMap ma, mb;
   TmaParams p;
   bool ak = false, bk = false;
+  const bool tall = use_tall(d);
+  const int BM = tall ? TallCfg::BM : WideCfg::BM, BN = tall ? TallCfg::BN : WideCfg::BN;
   if (!make_side(&ma, &p.a, &ak, d.A, d.M, d.K, d.a_m_inner, d.a_m1, d.a_m0, d.a_k, BM)) return cudaSuccess;
   if (!make_side(&mb, &p.b, &bk, d.B, d.N, d.K, d.b_n_inner, d.b_n1, d.b_n0, d.b_k, BN)) return cudaSuccess;
   p.M = d.M; p.N = d.N; p.K = d.K;
@@ -462,10 +490,7 @@ cudaError_t zgemm_tma_try(const GemmDesc& d, const GemmCtx& ctx, bool* used) {
   cudaError_t e;
   {
     ProfScope scope(ctx.stream, d.tag, 8.0 * (double)d.M * (double)d.N * (double)d.K, true);
-    if (ak && bk) e = launch_tma<true, true>(ma, mb, p, grid, ctx.stream);
-    else if (ak && !bk) e = launch_tma<true, false>(ma, mb, p, grid, ctx.stream);
-    else if (!ak && bk) e = launch_tma<false, true>(ma, mb, p, grid, ctx.stream);
-    else e = launch_tma<false, false>(ma, mb, p, grid, ctx.stream);
+    e = tall ? launch_tma<TallCfg>(ak, bk, ma, mb, p, grid, ctx.stream) : launch_tma<WideCfg>(ak, bk, ma, mb, p, grid, ctx.stream);
   }
   count_launch();
   *used = true;
