@@ -26,6 +26,7 @@ struct Handle {
   int num_sms = 148;
   int qr_max_cluster = 0;             // largest cluster the device co-schedules for k_qr_panel_cluster (0: none)
   int svd_max_blocks = 0;             // co-resident CTAs of k_jacobi_svd
+  int svd_blocked_max_blocks = 0;     // co-resident CTAs of k_jacobi_svd_blocked (one per SM: it fills the shared memory)
   // statistics
   unsigned long long krylov_matvecs = 0;
   unsigned long long krylov_solves = 0;

@@ -130,6 +130,183 @@ __global__ void __launch_bounds__(JT) k_jacobi_svd(c128* __restrict__ Gt, c128* 
   }
 }
 
+// ---- blocked variant: the columns are grouped into blocks of B; one CTA owns a PAIR of blocks for a tournament round,
+// holds their 2B columns (each of length m) in shared memory and rotates every column pair that meets there -- all B*B cross
+// pairs, plus (in the first round of a sweep) the pairs inside each block -- with one warp per pair and only CTA-level
+// barriers in between.  The unitary accumulated for the 2B columns is applied to the matching 2B columns of V once per
+// task.  A sweep therefore costs n/B - 1 grid-wide barriers instead of n - 1, and a matrix of up to 2B columns needs none
+// at all (r1: 511 grid barriers per sweep at n = 512 made the plain kernel latency-bound at 35 ms).
+constexpr int BJ_THREADS = 256;
+constexpr int BJ_WARPS = BJ_THREADS / 32;
+constexpr int BJ_SMEM_COLS_BYTES = 160 * 1024;     // budget for the 2B resident columns
+
+__device__ __forceinline__ int bj_rotate_pair(c128* __restrict__ xp, c128* __restrict__ xq, int m, c128* __restrict__ wp,
+                                              c128* __restrict__ wq, int w2, double tol, double frozen2, int lane) {
+  double al = 0.0, be = 0.0, gr = 0.0, gi = 0.0;
+  for (int i = lane; i < m; i += 32) {
+    const c128 x = xp[i], y = xq[i];
+    al += x.x * x.x + x.y * x.y;
+    be += y.x * y.x + y.y * y.y;
+    gr += x.x * y.x + x.y * y.y;   // conj(x) * y
+    gi += x.x * y.y - x.y * y.x;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    al += __shfl_xor_sync(0xffffffffu, al, o);
+    be += __shfl_xor_sync(0xffffffffu, be, o);
+    gr += __shfl_xor_sync(0xffffffffu, gr, o);
+    gi += __shfl_xor_sync(0xffffffffu, gi, o);
+  }
+  const double ga = hypot(gr, gi);
+  if (!(al > frozen2 && be > frozen2 && ga > tol * sqrt(al) * sqrt(be))) return 0;
+  const double pr = gr / ga, pi = gi / ga;          // e^{i phi}
+  const double zeta = (be - al) / (2.0 * ga);
+  const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+  const double c = 1.0 / sqrt(1.0 + tt * tt), s = c * tt;
+  for (int i = lane; i < m; i += 32) {
+    const c128 x = xp[i], y = xq[i];
+    const c128 yt = {y.x * pr + y.y * pi, y.y * pr - y.x * pi};   // y * e^{-i phi}
+    xp[i] = {c * x.x - s * yt.x, c * x.y - s * yt.y};
+    xq[i] = {s * x.x + c * yt.x, s * x.y + c * yt.y};
+  }
+  for (int i = lane; i < w2; i += 32) {
+    const c128 x = wp[i], y = wq[i];
+    const c128 yt = {y.x * pr + y.y * pi, y.y * pr - y.x * pi};
+    wp[i] = {c * x.x - s * yt.x, c * x.y - s * yt.y};
+    wq[i] = {s * x.x + c * yt.x, s * x.y + c * yt.y};
+  }
+  return 1;
+}
+
+__global__ void __launch_bounds__(BJ_THREADS, 1)
+    k_jacobi_svd_blocked(c128* __restrict__ Gt, c128* __restrict__ Vt, int n, int m, int B, int max_sweeps, double tol,
+                         int* __restrict__ flags, unsigned long long* __restrict__ maxn2) {
+  extern __shared__ __align__(16) unsigned char bj_smem[];
+  c128* X = reinterpret_cast<c128*>(bj_smem);              // [2B][m]: rows 0..B-1 = block I, B..2B-1 = block J
+  c128* Wt = X + (size_t)2 * B * m;                        // [2B][2B]: accumulated transformation of the 2B rows
+  __shared__ double sm[4 * (BJ_THREADS / 32)];
+  __shared__ int s_rot;
+  cg::grid_group grid = cg::this_grid();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int W2 = 2 * B;
+  const int nblk = (n + B - 1) / B;
+  const int ne = (nblk + 1) & ~1;                          // players (blocks), even
+  const int ntask = ne / 2;
+  // largest initial column norm (see NEGLIGIBLE)
+  for (int j = blockIdx.x; j < n; j += gridDim.x) {
+    double a = 0.0, b2 = 0.0, c2 = 0.0, d2 = 0.0;
+    for (int i = tid; i < m; i += blockDim.x) {
+      const c128 x = Gt[(size_t)j * m + i];
+      a += x.x * x.x + x.y * x.y;
+    }
+    block_sum3(a, b2, c2, d2, sm);
+    if (tid == 0) atomicMax(maxn2, (unsigned long long)__double_as_longlong(a));
+    __syncthreads();
+  }
+  __threadfence();
+  grid.sync();
+  const double frozen2 = NEGLIGIBLE * NEGLIGIBLE * __longlong_as_double((long long)*((volatile unsigned long long*)maxn2));
+
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    if (blockIdx.x == 0 && tid == 0) flags[(sweep + 1) % 3] = 0;
+    const int nrounds = ne > 1 ? ne - 1 : 1;
+    for (int r = 0; r < nrounds; ++r) {
+      for (int t = blockIdx.x; t < ntask; t += gridDim.x) {
+        int bI, bJ;
+        if (ne == 1) { bI = 0; bJ = 1; }
+        else if (t == 0) { bI = ne - 1; bJ = r; }
+        else { bI = (r + t) % (ne - 1); bJ = (r - t + (ne - 1)) % (ne - 1); }
+        if (bI > bJ) { const int x = bI; bI = bJ; bJ = x; }
+        const bool haveJ = bJ < nblk;
+        if (bI >= nblk) continue;                            // both byes (cannot happen for bI < bJ, kept for safety)
+        if (!haveJ && r != 0) continue;                      // bye: only the in-block pairs of round 0 remain to be done
+        // ---- load the 2B columns (rows of Gt), zero rows for columns beyond n / the bye block ----
+        for (int row = 0; row < W2; ++row) {
+          const int gcol = (row < B ? bI * B + row : bJ * B + (row - B));
+          const bool ok = gcol < n && (row < B || haveJ);
+          const c128* src = Gt + (size_t)gcol * m;
+          for (int i = tid; i < m; i += BJ_THREADS) X[(size_t)row * m + i] = ok ? src[i] : c128{0.0, 0.0};
+        }
+        for (int e = tid; e < W2 * W2; e += BJ_THREADS) Wt[e] = {(e / W2 == e % W2) ? 1.0 : 0.0, 0.0};
+        if (tid == 0) s_rot = 0;
+        __syncthreads();
+        int my_rot = 0;
+        // ---- pairs inside the two blocks (first round of the sweep only): round-robin over B players ----
+        if (r == 0 && B > 1) {
+          for (int rr = 0; rr < B - 1; ++rr) {
+            for (int pr_ = warp; pr_ < B; pr_ += BJ_WARPS) {     // B/2 pairs per block, two blocks
+              const int blk = pr_ / (B / 2), tt_ = pr_ % (B / 2);
+              int p, q;
+              if (tt_ == 0) { p = B - 1; q = rr; }
+              else { p = (rr + tt_) % (B - 1); q = (rr - tt_ + (B - 1)) % (B - 1); }
+              if (p > q) { const int x = p; p = q; q = x; }
+              p += blk * B; q += blk * B;
+              my_rot += bj_rotate_pair(X + (size_t)p * m, X + (size_t)q * m, m, Wt + p * W2, Wt + q * W2, W2, tol, frozen2, lane);
+            }
+            __syncthreads();
+          }
+        }
+        // ---- cross pairs: B rounds of B disjoint pairs (i, B + (i + rr) mod B) ----
+        if (haveJ) {
+          for (int rr = 0; rr < B; ++rr) {
+            for (int i = warp; i < B; i += BJ_WARPS) {
+              const int p = i, q = B + (i + rr) % B;
+              my_rot += bj_rotate_pair(X + (size_t)p * m, X + (size_t)q * m, m, Wt + p * W2, Wt + q * W2, W2, tol, frozen2, lane);
+            }
+            __syncthreads();
+          }
+        }
+        if (lane == 0 && my_rot) atomicAdd(&s_rot, my_rot);
+        __syncthreads();
+        const int rot = s_rot;
+        if (rot > 0) {
+          if (tid == 0) atomicAdd(&flags[sweep % 3], rot);
+          // ---- write the columns back and apply the accumulated transformation to the same columns of V ----
+          for (int row = 0; row < W2; ++row) {
+            const int gcol = (row < B ? bI * B + row : bJ * B + (row - B));
+            if (!(gcol < n && (row < B || haveJ))) continue;
+            c128* dst = Gt + (size_t)gcol * m;
+            for (int i = tid; i < m; i += BJ_THREADS) dst[i] = X[(size_t)row * m + i];
+          }
+          for (int col = tid; col < n; col += BJ_THREADS) {
+            c128 vold[32], vnew;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+              if (k < W2) {
+                const int gcol = (k < B ? bI * B + k : bJ * B + (k - B));
+                vold[k] = (gcol < n && (k < B || haveJ)) ? Vt[(size_t)gcol * n + col] : c128{0.0, 0.0};
+              }
+            }
+            for (int j = 0; j < W2; ++j) {
+              const int gcol = (j < B ? bI * B + j : bJ * B + (j - B));
+              if (!(gcol < n && (j < B || haveJ))) continue;
+              vnew = {0.0, 0.0};
+#pragma unroll
+              for (int k = 0; k < 32; ++k) {
+                if (k < W2) {
+                  const c128 w = Wt[j * W2 + k];
+                  vnew.x += w.x * vold[k].x - w.y * vold[k].y;
+                  vnew.y += w.x * vold[k].y + w.y * vold[k].x;
+                }
+              }
+              Vt[(size_t)gcol * n + col] = vnew;
+            }
+          }
+        }
+        __syncthreads();
+      }
+      if (ne > 2) { __threadfence(); grid.sync(); }
+    }
+    if (ne <= 2) { __threadfence(); __syncthreads(); }
+    const int nrot = *((volatile int*)&flags[sweep % 3]);
+    if (nrot == 0) {
+      if (blockIdx.x == 0 && tid == 0) flags[3] = 1;
+      break;
+    }
+    if (ne <= 2) __syncthreads();
+  }
+}
+
 // norms[j] = |Gt[j, :]|
 __global__ void k_row_norms(const c128* __restrict__ Gt, int n, int m, double* __restrict__ norms) {
   __shared__ double sm[4 * (JT / 32)];
@@ -185,6 +362,12 @@ __global__ void k_scale_rows(c128* __restrict__ A, int rows, int cols, int ld, c
     v.x *= f[i];
     v.y *= f[i];
   }
+}
+
+__global__ void k_identity(c128* __restrict__ A, int n) {
+  const long long tot = (long long)n * n;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x)
+    A[e] = {(e / n == e % n) ? 1.0 : 0.0, 0.0};
 }
 
 __global__ void k_diag_matrix(c128* __restrict__ S, int k, const double* __restrict__ vals) {
@@ -261,15 +444,24 @@ int svd_configure(Handle* h) {
   int per = 0;
   TDVP_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_jacobi_svd, JT, 0));
   h->svd_max_blocks = h->num_sms * (per > 4 ? 4 : (per < 1 ? 1 : per));
+  const int smem = BJ_SMEM_COLS_BYTES + 4 * 16 * 16 * (int)sizeof(c128);
+  TDVP_CUDA(h, cudaFuncSetAttribute(k_jacobi_svd_blocked, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  per = 0;
+  TDVP_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_jacobi_svd_blocked, BJ_THREADS, smem));
+  h->svd_blocked_max_blocks = h->num_sms * (per < 1 ? 0 : 1);
   return 0;
 }
 
 // Thin SVD sigma(m x n, row-major, m >= n) = U(m x n) diag(s) Vh(n x n); s descending, copied to host_s.
-int svd_exec(Handle* h, int m, int n, const c128* sigma, c128* U, c128* Vh, double* host_s) {
+size_t svd_ws_bytes(int m, int n) {
+  return sizeof(c128) * ((size_t)n * m + (size_t)n * n + 2 * (size_t)m * n + qr_ws_elems(m, n)) +
+         sizeof(double) * 8 * (size_t)n + 8192;   // incl. the n doubles tdvp_svd_truncate / tdvp_pinv add afterwards
+}
+
+// `reserve` false: the caller has reserved svd_ws_bytes(m, n) beyond what it already took from the bump allocator.
+int svd_exec(Handle* h, int m, int n, const c128* sigma, c128* U, c128* Vh, double* host_s, bool reserve = true) {
   if (m < n) { set_error(h, "svd: needs m >= n"); return TDVP_ERR_SHAPE; }
-  const size_t need = sizeof(c128) * ((size_t)n * m + (size_t)n * n + 2 * (size_t)m * n + qr_ws_elems(m, n)) +
-                      sizeof(double) * 8 * (size_t)n + 8192;   // incl. the n doubles tdvp_svd_truncate / tdvp_pinv add afterwards
-  TDVP_TRY(ws_reserve(h, need));
+  if (reserve) TDVP_TRY(ws_reserve(h, svd_ws_bytes(m, n)));
   c128* Gt = (c128*)ws_alloc(h, sizeof(c128) * (size_t)n * m);
   c128* Vt = (c128*)ws_alloc(h, sizeof(c128) * (size_t)n * n);
   double* norms = (double*)ws_alloc(h, sizeof(double) * n);
@@ -279,34 +471,45 @@ int svd_exec(Handle* h, int m, int n, const c128* sigma, c128* U, c128* Vh, doub
   if (!Gt || !Vt || !norms || !svals || !perm || !flags) { set_error(h, "svd: workspace"); return TDVP_ERR_ARG; }
   cudaStream_t st = h->stream;
   TDVP_TRY(permute_site(h, sigma, Gt, m, 1, n));   // Gt[j, i] = sigma[i, j]
-  TDVP_CUDA(h, cudaMemsetAsync(Vt, 0, sizeof(c128) * (size_t)n * n, st));
-  {
-    std::vector<double> one(1, 1.0);
-    // identity: strided 2D copy of a device scalar would need a kernel; reuse k_diag_matrix with ones
-    double* ones = (double*)ws_alloc(h, sizeof(double) * n);
-    if (!ones) { set_error(h, "svd: workspace"); return TDVP_ERR_ARG; }
-    std::vector<double> hv(n, 1.0);
-    TDVP_CUDA(h, cudaMemcpyAsync(ones, hv.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
-    TDVP_CUDA(h, cudaStreamSynchronize(st));
-    k_diag_matrix<<<148, 256, 0, st>>>(Vt, n, ones);
-    TDVP_TRY(ls(h, "k_diag_matrix"));
-  }
+  { ProfScope _ps(st, "svd.k_identity"); k_identity<<<148, 256, 0, st>>>(Vt, n); }
+  TDVP_TRY(ls(h, "k_identity"));
   TDVP_CUDA(h, cudaMemsetAsync(flags, 0, sizeof(int) * 8, st));
   unsigned long long* maxn2 = reinterpret_cast<unsigned long long*>(flags + 4);
   {
-    const int max_blocks = h->svd_max_blocks;
-    int grid = (n + 1) / 2;
-    if (grid > max_blocks) grid = max_blocks;
-    if (grid < 1) grid = 1;
     int max_sweeps = 40;
     // LAPACK zgesvj's threshold: sqrt(m) * eps -- the rounding level of an m-term inner product.  A fixed 1e-15 sits
     // below that noise for m in the hundreds and would keep rotating (and never report convergence).
     double tol = std::sqrt((double)m) * 2.220446049250313e-16;
-    void* args[] = {&Gt, &Vt, &n, &m, &max_sweeps, &tol, &flags, &maxn2};
     cudaError_t e;
-    { ProfScope _ps(st, "svd.k_jacobi_svd"); e = cudaLaunchCooperativeKernel((void*)k_jacobi_svd, dim3(grid), dim3(JT), args, 0, st); }
-    count_launch();
-    if (e != cudaSuccess) return cuda_fail(h, e, "cudaLaunchCooperativeKernel(k_jacobi_svd)", __FILE__, __LINE__);
+    // columns per block of the blocked kernel: as many as fit the shared-memory budget (two blocks resident), at most 16,
+    // and no more than half of the matrix (two blocks then hold everything and the whole SVD runs without a grid barrier)
+    int Bmax = 0;
+    for (int b = 16; b >= 2; b >>= 1)
+      if ((size_t)2 * b * m * sizeof(c128) <= (size_t)BJ_SMEM_COLS_BYTES) { Bmax = b; break; }
+    if (Bmax >= 2 && h->svd_blocked_max_blocks >= 1) {
+      int B = 2;
+      while (B < Bmax && 2 * B < n) B <<= 1;
+      const int nblk = (n + B - 1) / B;
+      const int ntask = ((nblk + 1) & ~1) / 2;
+      int grid = ntask < h->svd_blocked_max_blocks ? ntask : h->svd_blocked_max_blocks;
+      if (grid < 1) grid = 1;
+      const size_t smem = sizeof(c128) * ((size_t)2 * B * m + (size_t)4 * B * B);
+      void* args[] = {&Gt, &Vt, &n, &m, &B, &max_sweeps, &tol, &flags, &maxn2};
+      { ProfScope _ps(st, "svd.k_jacobi_svd_blocked"); e = cudaLaunchCooperativeKernel((void*)k_jacobi_svd_blocked, dim3(grid), dim3(BJ_THREADS), args, smem, st); }
+      count_launch();
+      if (e != cudaSuccess) return cuda_fail(h, e, "cudaLaunchCooperativeKernel(k_jacobi_svd_blocked)", __FILE__, __LINE__);
+    } else {
+      // very long columns (tall-skinny inputs such as the (D_l D_r) x d matricisation of regularize_site): one CTA per
+      // column pair, streaming from HBM
+      const int max_blocks = h->svd_max_blocks;
+      int grid = (n + 1) / 2;
+      if (grid > max_blocks) grid = max_blocks;
+      if (grid < 1) grid = 1;
+      void* args[] = {&Gt, &Vt, &n, &m, &max_sweeps, &tol, &flags, &maxn2};
+      { ProfScope _ps(st, "svd.k_jacobi_svd"); e = cudaLaunchCooperativeKernel((void*)k_jacobi_svd, dim3(grid), dim3(JT), args, 0, st); }
+      count_launch();
+      if (e != cudaSuccess) return cuda_fail(h, e, "cudaLaunchCooperativeKernel(k_jacobi_svd)", __FILE__, __LINE__);
+    }
   }
   k_row_norms<<<148, JT, 0, st>>>(Gt, n, m, norms);
   TDVP_TRY(ls(h, "k_row_norms"));
@@ -405,35 +608,30 @@ int tdvp_pinv(tdvp_handle_t hh, int m, int n, const tdvp_c128* X, double rcond, 
       return ls(h, "k_pinv_diag");
     }
   }
-  // General (non-diagonal) input: only the very first step of a site-parallel run gets here.  U / Vh cannot live in the
-  // handle's bump workspace because svd_exec re-bases it (ws_reserve), hence the two explicit allocations on this cold path.
-  c128 *U = nullptr, *Vh = nullptr;
-  TDVP_CUDA(h, cudaMalloc((void**)&U, sizeof(c128) * (size_t)m * n));
-  TDVP_CUDA(h, cudaMalloc((void**)&Vh, sizeof(c128) * (size_t)n * n));
+  // General (non-diagonal) input: only the very first step of a site-parallel run gets here.  U / Vh live in the handle's
+  // workspace, reserved together with what the SVD itself needs (no allocation on this path).
+  TDVP_TRY(ws_reserve(h, svd_ws_bytes(m, n) + 2 * align256(sizeof(c128) * (size_t)m * n) + 4096));
+  c128* U = (c128*)ws_alloc(h, sizeof(c128) * (size_t)m * n);
+  c128* Vh = (c128*)ws_alloc(h, sizeof(c128) * (size_t)n * n);
+  if (!U || !Vh) { set_error(h, "pinv: workspace"); return TDVP_ERR_ARG; }
   std::vector<double> s(n);
-  int rc = svd_exec(h, m, n, (const c128*)X, U, Vh, s.data());
-  if (rc == 0) {
-    std::vector<double> inv(n);
-    const double cut = rcond * s[0];
-    for (int i = 0; i < n; ++i) inv[i] = (s[i] > cut) ? 1.0 / s[i] : 0.0;
-    double* dinv = (double*)ws_alloc(h, sizeof(double) * n);
-    if (!dinv) { set_error(h, "pinv: workspace"); rc = TDVP_ERR_ARG; }
-    if (rc == 0) {
-      cudaMemcpyAsync(dinv, inv.data(), sizeof(double) * n, cudaMemcpyHostToDevice, h->stream);
-      k_scale_rows<<<148, 256, 0, h->stream>>>(Vh, n, n, n, dinv);
-      count_launch();
-      // out(n x m) = Vh^H (n x k) . U^H (k x m)
-      GemmDesc g = gemm_rowmajor(n, m, n, Vh, n, true, true, U, n, true, (c128*)out, m);
-      g.b_conj = 1;
-      g.tag = "pinv";
-      cudaError_t e = zgemm_auto(g, h->gemm);
-      if (e != cudaSuccess) rc = cuda_fail(h, e, "zgemm(pinv)", __FILE__, __LINE__);
-      cudaStreamSynchronize(h->stream);
-    }
-  }
-  cudaFree(U);
-  cudaFree(Vh);
-  return rc;
+  TDVP_TRY(svd_exec(h, m, n, (const c128*)X, U, Vh, s.data(), false));
+  std::vector<double> inv(n);
+  const double cut = rcond * s[0];
+  for (int i = 0; i < n; ++i) inv[i] = (s[i] > cut) ? 1.0 / s[i] : 0.0;
+  double* dinv = (double*)ws_alloc(h, sizeof(double) * n);
+  if (!dinv) { set_error(h, "pinv: workspace"); return TDVP_ERR_ARG; }
+  TDVP_CUDA(h, cudaMemcpyAsync(dinv, inv.data(), sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+  k_scale_rows<<<148, 256, 0, h->stream>>>(Vh, n, n, n, dinv);
+  TDVP_TRY(ls(h, "k_scale_rows"));
+  // out(n x m) = Vh^H (n x k) . U^H (k x m)
+  GemmDesc g = gemm_rowmajor(n, m, n, Vh, n, true, true, U, n, true, (c128*)out, m);
+  g.b_conj = 1;
+  g.tag = "pinv";
+  cudaError_t e = zgemm_auto(g, h->gemm);
+  if (e != cudaSuccess) return cuda_fail(h, e, "zgemm(pinv)", __FILE__, __LINE__);
+  TDVP_CUDA(h, cudaStreamSynchronize(h->stream));   // `inv` is a host temporary of the copy above
+  return 0;
 }
 
 }  // extern "C"
