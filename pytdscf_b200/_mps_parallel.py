@@ -43,6 +43,7 @@ class Comm:
         self.size = info.world
         self.device = device
         self.staged = self.dist is not None and self.dist.get_backend() == "gloo"  # gloo moves CPU tensors
+        self._layouts: dict = {}   # (direction, peer, tag) -> container description exchanged at the first use of the tag
 
     # -- (de)serialisation of tensors out of the object tree --
     def _strip(self, obj, out: list):
@@ -88,24 +89,48 @@ class Comm:
                 self._shapes(v, acc)
         return acc
 
-    def send(self, obj, dest: int):
+    # -- point-to-point messages ------------------------------------------------------------------------------
+    # A message is a container of tensors whose layout (keys, shapes) is the same every time step for a given call site
+    # (``tag``): the pickled description of the container travels only the FIRST time a tag is used between two ranks;
+    # afterwards both sides know the shapes and exchange the raw tensors of the message as ONE batch of p2p operations
+    # (one NCCL group launch; r1 sent a pickled header -- host sync + two extra NCCL sends -- before every message and
+    # one blocking send per tensor).  ``tag=None`` keeps the self-describing form (initial scatter, observables).
+    def _tensor_batch(self, op, tensors, peer: int):
+        views = [torch.view_as_real(t.cpu() if self.staged else t) for t in tensors]
+        if not views:
+            return
+        if len(views) == 1:
+            (self.dist.send if op is self.dist.isend else self.dist.recv)(views[0], peer)
+            return
+        for req in self.dist.batch_isend_irecv([self.dist.P2POp(op, v, peer) for v in views]):
+            req.wait()
+
+    def send(self, obj, dest: int, tag: str | None = None):
         tensors: list = []
         tree = self._strip(obj, tensors)
-        self.dist.send_object_list([tree], dst=dest)
-        for t in tensors:
-            t = t.contiguous()
-            self.dist.send(torch.view_as_real(t.cpu() if self.staged else t), dst=dest)
+        key = ("s", dest, tag)
+        if tag is None or key not in self._layouts:
+            self.dist.send_object_list([tree], dst=dest)
+            if tag is not None:
+                self._layouts[key] = tree
+        elif self._layouts[key] != tree:
+            raise RuntimeError(f"message layout of {tag!r} to rank {dest} changed between steps (dynamic shapes need tag=None)")
+        self._tensor_batch(self.dist.isend, [t.contiguous() for t in tensors], dest)
 
-    def recv(self, source: int):
-        box = [None]
-        self.dist.recv_object_list(box, src=source)
-        tree = box[0]
-        tensors = []
-        for shape in self._shapes(tree, []):
-            buf = torch.empty(tuple(shape) + (2,), dtype=torch.float64, device="cpu" if self.staged else self.device)
-            self.dist.recv(buf, src=source)
-            tensors.append(torch.view_as_complex(buf).to(self.device))
-        return self._build(tree, tensors)
+    def recv(self, source: int, tag: str | None = None):
+        key = ("r", source, tag)
+        if tag is None or key not in self._layouts:
+            box = [None]
+            self.dist.recv_object_list(box, src=source)
+            tree = box[0]
+            if tag is not None:
+                self._layouts[key] = tree
+        else:
+            tree = self._layouts[key]
+        bufs = [torch.empty(tuple(shape) + (2,), dtype=torch.float64, device="cpu" if self.staged else self.device)
+                for shape in self._shapes(tree, [])]
+        self._tensor_batch(self.dist.irecv, [torch.view_as_complex(b) for b in bufs], source)
+        return self._build(tree, [torch.view_as_complex(b).to(self.device) for b in bufs])
 
     def bcast_obj(self, obj, root: int = 0):
         box = [obj]
@@ -128,6 +153,44 @@ class Comm:
 
     def barrier(self):
         self.dist.barrier()
+
+
+def balanced_split(dims: list[int], bond_dim: int, nranks: int) -> list[int]:
+    """First site of every rank's segment such that the segments' sweep costs are as equal as possible.  A site update costs
+    ~ d (D_l^2 D_r + D_l D_r^2) (H_eff / environment GEMMs); the sites near the chain ends have small bonds and
+    are nearly free, so equal SITE counts leave the end ranks idle while the interior ranks finish.  The reference takes
+    ``parallel_split_indices`` from the user (pytdscf/simulator_cls.py:178); this is a helper to choose them.  Exact
+    min-max partition by dynamic programming (n is a few hundred at most)."""
+    from ._mps_cuda import bond_dims
+
+    n = len(dims)
+    if nranks < 1 or nranks > n // 2:
+        raise ValueError("need 1 <= nranks <= nsite / 2 (every segment holds at least two sites)")
+    cost = []
+    for i, d in enumerate(dims):
+        dl, dr = bond_dims(dims, i, bond_dim)
+        cost.append(float(d) * (dl * dl * dr + dl * dr * dr))
+    pre = [0.0]
+    for c in cost:
+        pre.append(pre[-1] + c)
+    INF = float("inf")
+    # best[p][i]: min over partitions of sites [0, i) into p segments (>= 2 sites each) of the largest segment cost
+    best = [[INF] * (n + 1) for _ in range(nranks + 1)]
+    cut = [[0] * (n + 1) for _ in range(nranks + 1)]
+    best[0][0] = 0.0
+    for p in range(1, nranks + 1):
+        for i in range(2 * p, n + 1):
+            for j in range(2 * (p - 1), i - 1):
+                if best[p - 1][j] == INF:
+                    continue
+                v = max(best[p - 1][j], pre[i] - pre[j])
+                if v < best[p][i]:
+                    best[p][i], cut[p][i] = v, j
+    starts, i = [], n
+    for p in range(nranks, 0, -1):
+        i = cut[p][i]
+        starts.append(i)
+    return starts[::-1]
 
 
 def _clone_sites(sites):
@@ -227,7 +290,7 @@ class MPSCoefParallelCuda(MPSCoefCuda):
             self.comm.send(blocks[-1], self.rank - 1)
         return blocks
 
-    def send_op_sys_to_left(self, even_rank: bool, H, pop_op_sys: bool):
+    def send_op_sys_to_left(self, even_rank: bool, H, pop_op_sys: bool, tag: str | None = None):
         if (not self._is_update(even_rank)) or self.rank == 0:
             return
         sb = self.sites
@@ -243,14 +306,14 @@ class MPSCoefParallelCuda(MPSCoefCuda):
                 raise ValueError(f"unexpected gauge {sb[0].gauge}")
         else:
             raise ValueError(f"{len(self.op_sys_sites)=} {self.nsite=}")
-        self.comm.send(op_sys, self.rank - 1)
+        self.comm.send(op_sys, self.rank - 1, tag)
 
-    def recv_op_sys_from_right(self, even_rank: bool):
+    def recv_op_sys_from_right(self, even_rank: bool, tag: str | None = None):
         if self._is_update(even_rank) and self.rank != self.size - 1:
-            return self.comm.recv(self.rank + 1)
+            return self.comm.recv(self.rank + 1, tag)
         return None
 
-    def send_joint_sigvec_to_right(self, even_rank: bool):
+    def send_joint_sigvec_to_right(self, even_rank: bool, tag: str | None = None):
         if (not self._is_update(even_rank)) or self.rank == self.size - 1:
             return
         sb = self.sites
@@ -258,63 +321,63 @@ class MPSCoefParallelCuda(MPSCoefCuda):
         x = self.joint_sigvec
         self.joint_sigvec_not_pinv = x
         self.joint_sigvec = self.eng.pinv(x, 1e-15)     # np.linalg.pinv(joint_sigvec), default rcond
-        self.comm.send(x, self.rank + 1)
+        self.comm.send(x, self.rank + 1, tag)
         sb[-1].data = self.eng.absorb("B", x, sb[-1].data)    # A . x
         sb[-1].gauge = "Psi"
 
-    def recv_joint_sigvec_from_left(self, even_rank: bool):
+    def recv_joint_sigvec_from_left(self, even_rank: bool, tag: str | None = None):
         if (not self._is_update(even_rank)) or self.rank == 0:
             return
-        x = self.comm.recv(self.rank - 1)
+        x = self.comm.recv(self.rank - 1, tag)
         sb = self.sites
         assert sb[0].gauge == "B"
         sb[0].data = self.eng.absorb("A", x, sb[0].data)      # x . B
         sb[0].gauge = "Psi"
 
-    def send_op_sys_to_right(self, even_rank: bool):
+    def send_op_sys_to_right(self, even_rank: bool, tag: str | None = None):
         if (not self._is_update(even_rank)) or self.rank == self.size - 1:
             return
-        self.comm.send(self.op_sys_sites.pop(), self.rank + 1)
+        self.comm.send(self.op_sys_sites.pop(), self.rank + 1, tag)
 
-    def recv_op_sys_from_left(self, even_rank: bool):
+    def recv_op_sys_from_left(self, even_rank: bool, tag: str | None = None):
         if self._is_update(even_rank) and self.rank != 0:
-            return self.comm.recv(self.rank - 1)
+            return self.comm.recv(self.rank - 1, tag)
         return None
 
-    def send_op_env_to_right(self, even_rank: bool, op_env_from_left):
+    def send_op_env_to_right(self, even_rank: bool, op_env_from_left, tag: str | None = None):
         if (not self._is_update(even_rank)) or self.rank == self.size - 1:
             return
-        self.comm.send(op_env_from_left, self.rank + 1)
+        self.comm.send(op_env_from_left, self.rank + 1, tag)
 
-    def recv_op_env_from_left(self, even_rank: bool):
+    def recv_op_env_from_left(self, even_rank: bool, tag: str | None = None):
         if self._is_update(even_rank) and self.rank != 0:
-            op_sys = self.comm.recv(self.rank - 1)
+            op_sys = self.comm.recv(self.rank - 1, tag)
             assert len(self.op_sys_sites) == self.nsite
             self.op_sys_sites.append(op_sys)
 
-    def send_Psi_to_left(self, even_rank: bool):
+    def send_Psi_to_left(self, even_rank: bool, tag: str | None = None):
         if self._is_update(even_rank) and self.rank != 0:
             assert self.sites[0].gauge == "Psi"
-            self.comm.send(self.sites[0], self.rank - 1)
+            self.comm.send(self.sites[0], self.rank - 1, tag)
 
-    def recv_Psi_from_right(self, even_rank: bool):
+    def recv_Psi_from_right(self, even_rank: bool, tag: str | None = None):
         if (not self._is_update(even_rank)) or self.rank == self.size - 1:
             return None, None
-        psi_R = self.comm.recv(self.rank + 1)
+        psi_R = self.comm.recv(self.rank + 1, tag)
         psi_L = self.sites[-1]
         assert psi_L.gauge == "Psi" and psi_R.gauge == "Psi"
         return psi_L, psi_R
 
-    def send_B_to_right(self, even_rank: bool, Bsite):
+    def send_B_to_right(self, even_rank: bool, Bsite, tag: str | None = None):
         if (not self._is_update(even_rank)) or self.rank == self.size - 1:
             return
         assert Bsite.gauge == "B"
-        self.comm.send(Bsite, self.rank + 1)
+        self.comm.send(Bsite, self.rank + 1, tag)
 
-    def recv_B_from_left(self, even_rank: bool):
+    def recv_B_from_left(self, even_rank: bool, tag: str | None = None):
         if (not self._is_update(even_rank)) or self.rank == 0:
             return
-        Bsite = self.comm.recv(self.rank - 1)
+        Bsite = self.comm.recv(self.rank - 1, tag)
         assert Bsite.gauge == "B"
         Bsite.isite = 0
         self.sites[0] = Bsite
@@ -384,12 +447,13 @@ class MPSCoefParallelCuda(MPSCoefCuda):
             self.op_sys_sites = right_blocks if self.rank % 2 == 0 else left_blocks
         last = self.size - 1
         # (1) -> (2)
-        self.send_op_sys_to_left(True, H, pop_op_sys=True)
-        op_sys_from_right = self.recv_op_sys_from_right(False)
-        self.send_joint_sigvec_to_right(False)
-        self.recv_joint_sigvec_from_left(True)
-        self.send_op_sys_to_right(False)
-        op_sys_from_left = self.recv_op_sys_from_left(True)
+        # every message of a step carries a tag naming its place in the protocol: its layout is exchanged once (Comm.send)
+        self.send_op_sys_to_left(True, H, pop_op_sys=True, tag="1a")
+        op_sys_from_right = self.recv_op_sys_from_right(False, tag="1a")
+        self.send_joint_sigvec_to_right(False, tag="1b")
+        self.recv_joint_sigvec_from_left(True, tag="1b")
+        self.send_op_sys_to_right(False, tag="1c")
+        op_sys_from_left = self.recv_op_sys_from_left(True, tag="1c")
         # (2) -> (3): all ranks sweep concurrently, even ranks rightwards, odd ranks leftwards
         if self.rank % 2 == 0:
             self.propagate_along_sweep(H, stepsize, cfg, begin_site=0, end_site=self.nsite - 1,
@@ -398,20 +462,20 @@ class MPSCoefParallelCuda(MPSCoefCuda):
             self.propagate_along_sweep(H, stepsize, cfg, begin_site=self.nsite - 1, end_site=0,
                                        op_sys_initial=op_sys_from_right, skip_end_site=True)
         # (3) -> (4)
-        self.send_Psi_to_left(False)
-        psi_L, psi_R = self.recv_Psi_from_right(True)
-        self.send_op_sys_to_left(False, H, pop_op_sys=False)
-        op_env_previous = self.recv_op_sys_from_right(True)
+        self.send_Psi_to_left(False, tag="3a")
+        psi_L, psi_R = self.recv_Psi_from_right(True, tag="3a")
+        self.send_op_sys_to_left(False, H, pop_op_sys=False, tag="3b")
+        op_env_previous = self.recv_op_sys_from_right(True, tag="3b")
         op_sys_from_right, Bsite = self.propagate_joint_two_sites(True, H, stepsize, cfg, op_env_previous, psi_L, psi_R)
-        self.send_B_to_right(True, Bsite)
-        self.recv_B_from_left(False)
+        self.send_B_to_right(True, Bsite, tag="3c")
+        self.recv_B_from_left(False, tag="3c")
         self.save_all_A(True)
         self.save_all_B(False)
         # (4) -> (5)
-        self.send_joint_sigvec_to_right(True)
-        self.recv_joint_sigvec_from_left(False)
-        self.send_op_sys_to_right(True)
-        op_sys_from_left = self.recv_op_sys_from_left(False)
+        self.send_joint_sigvec_to_right(True, tag="4a")
+        self.recv_joint_sigvec_from_left(False, tag="4a")
+        self.send_op_sys_to_right(True, tag="4b")
+        op_sys_from_left = self.recv_op_sys_from_left(False, tag="4b")
         # (5) -> (2): sweep back
         if self.rank % 2 == 0:
             self.propagate_along_sweep(H, stepsize, cfg, begin_site=self.nsite - 1, end_site=0,
@@ -420,15 +484,15 @@ class MPSCoefParallelCuda(MPSCoefCuda):
             self.propagate_along_sweep(H, stepsize, cfg, begin_site=0, end_site=self.nsite - 1,
                                        op_sys_initial=op_sys_from_left, skip_end_site=(self.rank != last))
         # (2) -> (1)
-        self.send_Psi_to_left(True)
-        psi_L, psi_R = self.recv_Psi_from_right(False)
-        self.send_op_sys_to_left(True, H, pop_op_sys=False)
-        op_env_previous = self.recv_op_sys_from_right(False)
+        self.send_Psi_to_left(True, tag="2a")
+        psi_L, psi_R = self.recv_Psi_from_right(False, tag="2a")
+        self.send_op_sys_to_left(True, H, pop_op_sys=False, tag="2b")
+        op_env_previous = self.recv_op_sys_from_right(False, tag="2b")
         op_env_from_left, Bsite = self.propagate_joint_two_sites(False, H, stepsize, cfg, op_env_previous, psi_L, psi_R)
-        self.send_B_to_right(False, Bsite)
-        self.recv_B_from_left(True)
-        self.send_op_env_to_right(False, op_env_from_left)
-        self.recv_op_env_from_left(True)
+        self.send_B_to_right(False, Bsite, tag="2c")
+        self.recv_B_from_left(True, tag="2c")
+        self.send_op_env_to_right(False, op_env_from_left, tag="2d")
+        self.recv_op_env_from_left(True, tag="2d")
         self.save_all_A(False)
         self.save_all_B(True)
 

@@ -486,9 +486,13 @@ int svd_exec(Handle* h, int m, int n, const c128* sigma, c128* U, c128* Vh, doub
     int Bmax = 0;
     for (int b = 16; b >= 2; b >>= 1)
       if ((size_t)2 * b * m * sizeof(c128) <= (size_t)BJ_SMEM_COLS_BYTES) { Bmax = b; break; }
-    if (Bmax >= 2 && h->svd_blocked_max_blocks >= 1) {
-      int B = 2;
-      while (B < Bmax && 2 * B < n) B <<= 1;
+    int B = 2;
+    while (B < Bmax && 2 * B < n) B <<= 1;
+    // Measured (profiles/r2_svd_qr_latency.jsonl): with several block pairs per round the blocked kernel is SLOWER than
+    // the plain one (48 vs 35 ms at 512 x 512: 8 warps per resident block pair cannot hide the ~2 us FP64 sqrt / division
+    // chain of each rotation, and only n / 2B CTAs are busy), so it is used where it needs no grid barrier at all:
+    // matrices whose columns fit one block pair (n <= 2B <= 32 -- the bond matrices of the small-D regime).
+    if (Bmax >= 2 && 2 * B >= n && h->svd_blocked_max_blocks >= 1) {
       const int nblk = (n + B - 1) / B;
       const int ntask = ((nblk + 1) & ~1) / 2;
       int grid = ntask < h->svd_blocked_max_blocks ? ntask : h->svd_blocked_max_blocks;
