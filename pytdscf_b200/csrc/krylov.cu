@@ -182,6 +182,70 @@ __global__ void __launch_bounds__(RED_THREADS) k_lanczos_update(c128* __restrict
   }
 }
 
+// Small vectors (N <= FUSED_MAX_N: the D <= 64 regime, where a sweep is bound by kernel launches, not bandwidth): the
+// three Lanczos vector kernels of one iteration -- alpha = <v0|w>; w -= alpha v_l + beta_{l-1} v_{l-1}, beta = |w|;
+// w /= beta -- as ONE single-CTA kernel.  Same arithmetic, fixed summation order (thread-strided partials, warp
+// butterflies, warp totals in order).
+constexpr int FUSED_THREADS = 1024;
+constexpr long long FUSED_MAX_N = 32768;
+
+__device__ __forceinline__ void cta_sum2(double& a, double& b, double (*sm)[2]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  __syncthreads();
+  if (lane == 0) { sm[warp][0] = a; sm[warp][1] = b; }
+  __syncthreads();
+  double ta = 0.0, tb = 0.0;
+  for (int w = 0; w < nw; ++w) { ta += sm[w][0]; tb += sm[w][1]; }
+  a = ta; b = tb;
+}
+
+__global__ void __launch_bounds__(FUSED_THREADS) k_lanczos_step_small(const c128* __restrict__ v0, c128* __restrict__ w,
+                                                                       const c128* __restrict__ v1, const c128* __restrict__ v2,
+                                                                       int n, double* alpha2, const double* beta_prev,
+                                                                       double* beta_out, double* areal_flag, double min_div) {
+  __shared__ double sm[FUSED_THREADS / 32][2];
+  double ar = 0.0, ai = 0.0;
+  for (int i = threadIdx.x; i < n; i += FUSED_THREADS) {
+    const c128 a = v0[i], b = w[i];
+    ar += a.x * b.x + a.y * b.y;       // conj(v0) * w
+    ai += a.x * b.y - a.y * b.x;
+  }
+  cta_sum2(ar, ai, sm);
+  const double bp = v2 ? *beta_prev : 0.0;
+  double nn = 0.0, dummy = 0.0;
+  for (int i = threadIdx.x; i < n; i += FUSED_THREADS) {
+    c128 x = w[i];
+    const c128 a = v1[i];
+    x.x -= a.x * ar - a.y * ai;
+    x.y -= a.x * ai + a.y * ar;
+    if (v2) {
+      const c128 b = v2[i];
+      x.x -= b.x * bp;
+      x.y -= b.y * bp;
+    }
+    w[i] = x;
+    nn += x.x * x.x + x.y * x.y;
+  }
+  cta_sum2(nn, dummy, sm);
+  const double beta = sqrt(nn);
+  if (threadIdx.x == 0) {
+    alpha2[0] = ar; alpha2[1] = ai;
+    beta_out[0] = beta;
+    if (fabs(ai) > 1e-10) *areal_flag = 0.0;
+  }
+  if (beta < min_div) return;          // Krylov space exhausted: the vector is left untouched (it is never used)
+  for (int i = threadIdx.x; i < n; i += FUSED_THREADS) {
+    c128 x = w[i];
+    x.x /= beta; x.y /= beta;
+    w[i] = x;
+  }
+}
+
 // Arnoldi: h[i] = <V_i | w>, i < k   (one pass over w, k passes over V)
 __global__ void __launch_bounds__(RED_THREADS) k_arnoldi_dots(const c128* __restrict__ V, long long ldv, int k,
                                                                const c128* __restrict__ w, long long n, double* partial,
@@ -557,7 +621,13 @@ int krylov_expm_exec(Handle* h, int kind, double scale_re, double scale_im, doub
       { ProfScope _ps(st, "vec.k_scale_dev"); k_scale_dev<<<vb, RED_THREADS, 0, st>>>(w, w, N, S + S_B0, 0, 0.0); }
       TDVP_TRY(lc(h, "k_scale_dev"));
     }
-    if (kind == TDVP_KRYLOV_LANCZOS_REF) {
+    if (kind == TDVP_KRYLOV_LANCZOS_REF && N <= FUSED_MAX_N) {
+      { ProfScope _ps(st, "vec.k_lanczos_step_small");
+        k_lanczos_step_small<<<1, FUSED_THREADS, 0, st>>>(V, w, V + (size_t)l * N, l > 0 ? V + (size_t)(l - 1) * N : nullptr, (int)N,
+                                                           S + S_ALPHA + 2 * l, S + S_BETA + (l > 0 ? l - 1 : 0), S + S_BETA + l,
+                                                           S + S_AREAL, EPS_K); }
+      TDVP_TRY(lc(h, "k_lanczos_step_small"));
+    } else if (kind == TDVP_KRYLOV_LANCZOS_REF) {
       { ProfScope _ps(st, "vec.k_dot"); k_dot<<<nb, RED_THREADS, 0, st>>>(V, w, N, 1, h->d_partial, h->d_counter, S + S_ALPHA + 2 * l); }
       TDVP_TRY(lc(h, "k_dot"));
       { ProfScope _ps(st, "vec.k_lanczos_update"); k_lanczos_update<<<nb, RED_THREADS, 0, st>>>(w, V + (size_t)l * N, l > 0 ? V + (size_t)(l - 1) * N : nullptr, N,
@@ -576,8 +646,10 @@ int krylov_expm_exec(Handle* h, int kind, double scale_re, double scale_im, doub
       }
     }
     // w /= beta when beta >= EPS (Lanczos) / > EPS (Arnoldi): decided on device, mirrored on host at the next read-back
-    { ProfScope _ps(st, "vec.k_scale_dev"); k_scale_dev<<<vb, RED_THREADS, 0, st>>>(w, w, N, S + S_BETA + l, 0, kind == TDVP_KRYLOV_ARNOLDI ? nextafter(EPS_K, 1.0) : EPS_K); }
-    TDVP_TRY(lc(h, "k_scale_dev"));
+    if (!(kind == TDVP_KRYLOV_LANCZOS_REF && N <= FUSED_MAX_N)) {   // (the fused small-N kernel has done it already)
+      { ProfScope _ps(st, "vec.k_scale_dev"); k_scale_dev<<<vb, RED_THREADS, 0, st>>>(w, w, N, S + S_BETA + l, 0, kind == TDVP_KRYLOV_ARNOLDI ? nextafter(EPS_K, 1.0) : EPS_K); }
+      TDVP_TRY(lc(h, "k_scale_dev"));
+    }
     // Warm-up iterations (the reference skips the Ritz step there, _integrator.py:560-575) need nothing on the host:
     // the beta values are read back together with the first convergence scalar, so the stream keeps running ahead.
     // A breakdown (beta < eps) inside the warm-up is detected at that read-back and replayed from the stored basis.

@@ -436,7 +436,9 @@ inline Choice choose(const GemmDesc& d, const GemmCtx& ctx) {
       double waves = (double)((units + slots - 1) / slots);
       if (m.id == 3 && units >= slots) waves = (double)units / slots + 0.5;
       double t = waves * (chunk + m.K0) * per_k * m.bias;
-      if (S > 1) t += (double)(S + 2) * d.M * d.N * 16.0 / bw + 4.0e-6;
+      // split-K pays a second launch; in the launch-bound small-D regime that launch costs a full ~9 us slot of the stream
+      // (r2 c2 profile: 2300 reduction launches per step), elsewhere ~4 us
+      if (S > 1) t += (double)(S + 2) * d.M * d.N * 16.0 / bw + ((double)d.M * d.N * d.K < 5.0e7 ? 9.0e-6 : 4.0e-6);
       if (t < best.t * (S > 1 && best.cfg == mid ? 0.97 : 1.0)) { best.t = t; best.cfg = mid; best.S = S; best.chunk = chunk; }
     }
   }
