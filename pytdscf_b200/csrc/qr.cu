@@ -242,9 +242,10 @@ __global__ void __launch_bounds__(PT, 1) k_qr_panel(PanelArgs p) {
 // every CTA of the cluster with st.async, which also counts the bytes on the receiver's mbarrier.  A CTA then waits on
 // its OWN barrier and reads its OWN shared memory -- no cluster-wide hardware barrier and no remote-load round trip per
 // column (r1: cluster.sync + DSMEM gather + zlarfg's division chain = ~5 us per column, a third of it barrier wait). ----
-constexpr int CT = 1024;          // threads per CTA, arranged (32, 32)
+constexpr int CT = 512;           // threads per CTA, arranged (32, 16): 128 registers per thread for the resident slab
 constexpr int CTY = CT / 32;
 constexpr int MAXG = 16;          // largest cluster
+constexpr int CL_ROWS = 256;     // slab rows per CTA in the cluster kernel: 16 rows per thread in registers, 128 KiB staged in shared memory
 
 __device__ __forceinline__ unsigned qr_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ unsigned qr_mapa(unsigned local, int cta) {
@@ -306,7 +307,7 @@ __global__ void __launch_bounds__(CT, 1) k_qr_panel_cluster(PanelArgs p) {
   __shared__ c128 red[CTY][NB + 1];
   __shared__ __align__(16) c128 inbox[2][MAXG + 1][NB];     // [column parity][source CTA | MAXG: diagonal row][panel column]
   __shared__ __align__(8) unsigned long long mbar[2];
-  __shared__ c128 gtot[NB], rowc[NB];
+  __shared__ c128 gtot[NB], rowc[NB], rowstage[NB];
   __shared__ double s_zl[5];     // zlarfg scalars of the current column: tau, 1/(alpha - beta), beta
   cg::cluster_group cluster = cg::this_cluster();
   const int tx = threadIdx.x, ty = threadIdx.y;
@@ -329,16 +330,28 @@ __global__ void __launch_bounds__(CT, 1) k_qr_panel_cluster(PanelArgs p) {
   __syncthreads();
   cluster.sync();                                            // every inbox barrier exists before the first remote push
 
+  // The slab lives in REGISTERS during the column loop: thread (tx, ty) owns column tx of the rows ty, ty + 32, ... of this
+  // CTA (at most MAXPER of them).  A warp is one row group, its lanes are the 32 panel columns, so the column-c entries a
+  // thread needs for its own rows sit in lane c of the SAME warp: one shuffle instead of a shared-memory round trip per
+  // row (r2 ncu: the slab pass through shared memory was 44 % of the kernel's samples, MIO-bound).
+  constexpr int MAXPER = (CL_ROWS + CTY - 1) / CTY;
+  c128 mine[MAXPER];
+#pragma unroll
+  for (int k = 0; k < MAXPER; ++k) {
+    const int i = ty + CTY * k;
+    mine[k] = (i < nrow) ? S[i * NB + tx] : c128{0.0, 0.0};
+  }
   // partial g for column 0; for c > 0 it is accumulated while column c-1 is applied (one pass over the slab per column)
   c128 acc = {0.0, 0.0};
-  if (tx < jb) {
-    for (int i = ty; i < nrow; i += CTY) {
-      if (r0 + i > j0) {
-        const c128 x = S[i * NB + 0], y = S[i * NB + tx];
-        acc.x += x.x * y.x + x.y * y.y;
-        acc.y += x.x * y.y - x.y * y.x;
-      }
+#pragma unroll
+  for (int k = 0; k < MAXPER; ++k) {
+    const int i = ty + CTY * k;
+    const double xr = __shfl_sync(0xffffffffu, mine[k].x, 0), xi = __shfl_sync(0xffffffffu, mine[k].y, 0);
+    if (i < nrow && r0 + i > j0 && tx < jb) {
+      acc.x += xr * mine[k].x + xi * mine[k].y;
+      acc.y += xr * mine[k].y - xi * mine[k].x;
     }
+    if (i < nrow && r0 + i == j0) rowstage[tx] = mine[k];     // diagonal row of column 0, staged for its owner's push
   }
   for (int c = 0; c < ((p.dbg & 1) ? 0 : jb); ++c) {
     const int grow = j0 + c;
@@ -346,19 +359,21 @@ __global__ void __launch_bounds__(CT, 1) k_qr_panel_cluster(PanelArgs p) {
     const unsigned parity = (unsigned)(c >> 1) & 1u;
     const int owner = c / p.rows_per_cta;
     red[ty][tx] = acc;
-    __syncthreads();
+    __syncthreads();                                          // (rowstage holds row `grow`: staged by the previous pass)
     {
-      // warp ty reduces column ty over the 32 row groups (fixed butterfly order: every lane ends up with the total) and
-      // lane q pushes it into CTA q's inbox; warps 0..G-1 of the diagonal row's owner also push that row, one CTA each
-      c128 t = red[tx][ty];
+      // warp ty reduces columns ty (lanes 0-15) and ty + 16 (lanes 16-31) over the 16 row groups (fixed butterfly order:
+      // every lane of a half ends up with the total) and lane q of each half pushes it into CTA q's inbox; warps 0..G-1 of
+      // the diagonal row's owner also push that row, one CTA each
+      const int half = tx >> 4, q = tx & 15, col = ty + CTY * half;
+      c128 t = red[q][col];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
+      for (int o = 8; o > 0; o >>= 1) {
         t.x += __shfl_xor_sync(0xffffffffu, t.x, o);
         t.y += __shfl_xor_sync(0xffffffffu, t.y, o);
       }
       const unsigned bar_local = qr_smem_u32(&mbar[buf]);
-      if (tx < G) qr_push(qr_mapa(qr_smem_u32(&inbox[buf][b][ty]), tx), t, qr_mapa(bar_local, tx));
-      if (b == owner && ty < G) qr_push(qr_mapa(qr_smem_u32(&inbox[buf][MAXG][tx]), ty), S[(grow - r0) * NB + tx], qr_mapa(bar_local, ty));
+      if (q < G) qr_push(qr_mapa(qr_smem_u32(&inbox[buf][b][col]), q), t, qr_mapa(bar_local, q));
+      if (b == owner && ty < G) qr_push(qr_mapa(qr_smem_u32(&inbox[buf][MAXG][tx]), ty), rowstage[tx], qr_mapa(bar_local, ty));
     }
     if (ty == 0) {
       const unsigned bar = qr_smem_u32(&mbar[buf]);
@@ -394,8 +409,7 @@ __global__ void __launch_bounds__(CT, 1) k_qr_panel_cluster(PanelArgs p) {
     const bool trivial = (tau.x == 0.0 && tau.y == 0.0);
     // a_ij -= conj(tau) v_i w_j with v_i = s a_ic (v = 1 on the diagonal row), w_j = a_cj + conj(s) g_j.  The products
     // that do not depend on the row are formed once per column and thread: y_j = conj(tau) s w_j (rows below the
-    // diagonal) and yd_j = conj(tau) w_j (diagonal row); the slab pass then costs one complex multiply-add per element
-    // (the panel kernel is bound by the plain FP64 pipe, 2 warp instructions per clock per SM).
+    // diagonal) and yd_j = conj(tau) w_j (diagonal row); the slab pass then costs one complex multiply-add per element.
     c128 yj = {0.0, 0.0}, ydj = {0.0, 0.0};
     if (tx > c && tx < jb) {
       const c128 cs = {sc.x, -sc.y};
@@ -408,28 +422,36 @@ __global__ void __launch_bounds__(CT, 1) k_qr_panel_cluster(PanelArgs p) {
     // partial g (lane c+1 holds the freshly updated a_{i,c+1})
     acc = {0.0, 0.0};
     const int cn = (c + 1 < NB) ? c + 1 : c;
-    for (int i = ty; i < nrow; i += CTY) {
+#pragma unroll
+    for (int k = 0; k < MAXPER; ++k) {
+      const int i = ty + CTY * k;
       const int gr = r0 + i;
-      if (gr < grow) continue;                               // uniform per warp (ty selects the row)
-      c128 mine = S[i * NB + tx];
+      // uniform per warp: ty and k select the row (shuffles below are executed by all lanes of the warp or by none)
+      if (i >= nrow || gr < grow) continue;
       if (!trivial) {
-        const c128 x = S[i * NB + c];
+        const double xr = __shfl_sync(0xffffffffu, mine[k].x, c), xi = __shfl_sync(0xffffffffu, mine[k].y, c);
+        const c128 x = {xr, xi};
         if (tx > c && tx < jb) {
           const c128 f = (gr == grow) ? ydj : cmul(x, yj);
-          mine.x -= f.x;
-          mine.y -= f.y;
+          mine[k].x -= f.x;
+          mine[k].y -= f.y;
         }
-        if (tx == c) mine = (gr == grow) ? c128{hbeta, 0.0} : cmul(x, sc);
-        __syncwarp();                                        // every lane has read S[i][c] before lane c overwrites it
-        if (tx >= c) S[i * NB + tx] = mine;
+        if (tx == c) mine[k] = (gr == grow) ? c128{hbeta, 0.0} : cmul(x, sc);
       }
-      const double xr = __shfl_sync(0xffffffffu, mine.x, cn);
-      const double xi = __shfl_sync(0xffffffffu, mine.y, cn);
+      const double nr = __shfl_sync(0xffffffffu, mine[k].x, cn);
+      const double ni = __shfl_sync(0xffffffffu, mine[k].y, cn);
       if (gr > grow + 1 && tx > c && tx < jb) {
-        acc.x += xr * mine.x + xi * mine.y;
-        acc.y += xr * mine.y - xi * mine.x;
+        acc.x += nr * mine[k].x + ni * mine[k].y;
+        acc.y += nr * mine[k].y - ni * mine[k].x;
       }
+      if (gr == grow + 1) rowstage[tx] = mine[k];             // the next column's diagonal row, now final: staged for its push
     }
+  }
+  // back to shared memory for the write-back, the explicit V and the Gram matrix of the T factor
+#pragma unroll
+  for (int k = 0; k < MAXPER; ++k) {
+    const int i = ty + CTY * k;
+    if (i < nrow) S[i * NB + tx] = mine[k];
   }
   __syncthreads();
 
@@ -448,9 +470,8 @@ __global__ void __launch_bounds__(CT, 1) k_qr_panel_cluster(PanelArgs p) {
     }
   }
   __syncthreads();
-  // partial Gram Z[a, c] = sum_i conj(V[i,a]) V[i,c] (a < c), row a = ty, column c = tx; kept in global scratch
-  {
-    const int a = ty;
+  // partial Gram Z[a, c] = sum_i conj(V[i,a]) V[i,c] (a < c), rows a = ty, ty + 16, column c = tx; kept in global scratch
+  for (int a = ty; a < NB; a += CTY) {
     c128 z = {0.0, 0.0};
     if (tx < jb && a < tx) {
       for (int i = 0; i < nrow; ++i) {
@@ -471,8 +492,7 @@ __global__ void __launch_bounds__(CT, 1) k_qr_panel_cluster(PanelArgs p) {
   c128* Z = S;
   c128* Tt = S + NB * NB;        // Tt[q * NB + r] = T[r][q]
   __shared__ c128 taus[NB];
-  {
-    const int a = ty;
+  for (int a = ty; a < NB; a += CTY) {
     c128 z = {0.0, 0.0};
     for (int q = 0; q < G; ++q) {
       z.x += __ldcg(&p.zpart[((size_t)q * NB + a) * NB * 2 + 2 * tx]);
@@ -480,7 +500,7 @@ __global__ void __launch_bounds__(CT, 1) k_qr_panel_cluster(PanelArgs p) {
     }
     Z[a * NB + tx] = z;
     Tt[a * NB + tx] = {0.0, 0.0};
-    if (ty == 0) taus[tx] = (tx < jb) ? c128{__ldcg(&p.tau[2 * (j0 + tx)]), __ldcg(&p.tau[2 * (j0 + tx) + 1])} : c128{0.0, 0.0};
+    if (a == 0) taus[tx] = (tx < jb) ? c128{__ldcg(&p.tau[2 * (j0 + tx)]), __ldcg(&p.tau[2 * (j0 + tx) + 1])} : c128{0.0, 0.0};
   }
   __syncthreads();
   if (ty == 0 && !(p.dbg & 2)) {
@@ -507,7 +527,7 @@ __global__ void __launch_bounds__(CT, 1) k_qr_panel_cluster(PanelArgs p) {
   }
   __syncthreads();
   c128* Tout = p.Tall + (size_t)(j0 / NB) * NB * NB;
-  Tout[ty * NB + tx] = Tt[tx * NB + ty];
+  for (int a = ty; a < NB; a += CTY) Tout[a * NB + tx] = Tt[tx * NB + a];
 }
 
 __global__ void k_set_identity(c128* Q, int m, int n, int ld) {
@@ -556,7 +576,6 @@ int gemmq(Handle* h, const GemmDesc& g) {
 
 }  // namespace
 
-constexpr int CL_ROWS = 352;     // slab rows per CTA in the cluster kernel (352*32*16 B = 176 KiB + 38 KiB of static buffers)
 constexpr int QR_MAX_SMS = 256;  // workspace bound for the per-CTA partials (B200: 148 SMs)
 
 size_t qr_ws_elems(int m, int n) {
