@@ -409,10 +409,12 @@ class Bench:
         H = DeviceMPO(self.eng, model.hamiltonian)
         cfg = RunConfig(jobname="bench", space=wl.space, integrator=wl.integrator, conserve_norm=wl.conserve_norm)
         if site_parallel:
-            from pytdscf_b200._mps_parallel import Comm, MPSCoefParallelCuda
+            from pytdscf_b200._mps_parallel import Comm, MPSCoefParallelCuda, balanced_split
 
-            n = len(wl.dims)
-            split = [(r * n) // self.world for r in range(self.world)]
+            # contiguous segments of equal SWEEP COST (the end sites of a chain have small bonds and are nearly free); the
+            # reference takes the split from the user (parallel_split_indices), this is the choice a user would make
+            split = balanced_split(wl.dims, wl.bond_dim, self.world)
+            self.last_split = split
             mps = MPSCoefParallelCuda.distribute(self.eng, Comm(self.info, self.eng.torch_device), model, split)
         else:
             mps = MPSCoefCuda.alloc_random(self.eng, model)
@@ -675,6 +677,7 @@ def run_cuda(args):
             if rank == 0:
                 sp["parallel"] = summarize(w5, mp5, world, True)
                 sp["parallel"]["segments"] = world
+                sp["parallel"]["first_site_of_segment"] = list(getattr(b, "last_split", []))
                 sp["strong_scaling_efficiency"] = sp["parallel"]["sweeps_per_s"] / (world * sp["serial_1gpu"]["sweeps_per_s"])
                 sp["speedup_over_1gpu_serial"] = sp["parallel"]["sweeps_per_s"] / sp["serial_1gpu"]["sweeps_per_s"]
                 sp["breakdown_top"] = mp5["breakdown_top"]

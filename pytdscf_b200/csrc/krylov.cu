@@ -15,6 +15,7 @@
 // The host loop needs three scalars per iteration (beta_l, |y_k - y_{k-1}|, "alpha is real" flag); they are
 // read through a pinned mailbox with one stream synchronisation.  All vector arithmetic stays on device and
 // every reduction is a fixed-order two-level tree (deterministic run to run).
+#include <cooperative_groups.h>
 #include <type_traits>
 
 #include "contract.cuh"
@@ -184,10 +185,14 @@ __global__ void __launch_bounds__(RED_THREADS) k_lanczos_update(c128* __restrict
 
 // Small vectors (N <= FUSED_MAX_N: the D <= 64 regime, where a sweep is bound by kernel launches, not bandwidth): the
 // three Lanczos vector kernels of one iteration -- alpha = <v0|w>; w -= alpha v_l + beta_{l-1} v_{l-1}, beta = |w|;
-// w /= beta -- as ONE single-CTA kernel.  Same arithmetic, fixed summation order (thread-strided partials, warp
-// butterflies, warp totals in order).
-constexpr int FUSED_THREADS = 1024;
-constexpr long long FUSED_MAX_N = 32768;
+// w /= beta -- as ONE kernel run by a single 8-CTA cluster.  Every thread keeps its (at most 8) elements of w in
+// registers across the three phases; the two reductions go through distributed shared memory (each CTA publishes its
+// partial, cluster barrier, everybody sums the 8 partials in rank order: deterministic).  One SM alone cannot do this:
+// it pulls ~150 GB/s from L2 and took 27 us for the 4 MB of traffic (first version of this kernel, r2 c2 profile).
+constexpr int FUSED_CLUSTER = 8;    // portable cluster size
+constexpr int FUSED_THREADS = 512;
+constexpr int FUSED_PER_THREAD = 8;
+constexpr long long FUSED_MAX_N = (long long)FUSED_CLUSTER * FUSED_THREADS * FUSED_PER_THREAD;   // 32768
 
 __device__ __forceinline__ void cta_sum2(double& a, double& b, double (*sm)[2]) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -204,46 +209,79 @@ __device__ __forceinline__ void cta_sum2(double& a, double& b, double (*sm)[2]) 
   a = ta; b = tb;
 }
 
-__global__ void __launch_bounds__(FUSED_THREADS) k_lanczos_step_small(const c128* __restrict__ v0, c128* __restrict__ w,
-                                                                       const c128* __restrict__ v1, const c128* __restrict__ v2,
-                                                                       int n, double* alpha2, const double* beta_prev,
-                                                                       double* beta_out, double* areal_flag, double min_div) {
+__global__ void __cluster_dims__(FUSED_CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS)
+    k_lanczos_step_small(const c128* __restrict__ v0, c128* __restrict__ w, const c128* __restrict__ v1,
+                         const c128* __restrict__ v2, int n, double* alpha2, const double* beta_prev, double* beta_out,
+                         double* areal_flag, double min_div) {
+  namespace cgx = cooperative_groups;
+  cgx::cluster_group cluster = cgx::this_cluster();
   __shared__ double sm[FUSED_THREADS / 32][2];
+  __shared__ double part[2][2];                      // this CTA's partial sums: [phase][re | im]
+  const int rank = (int)cluster.block_rank();
+  const int base = rank * FUSED_THREADS + threadIdx.x;
+  constexpr int STRIDE = FUSED_CLUSTER * FUSED_THREADS;
+  c128 x[FUSED_PER_THREAD];
   double ar = 0.0, ai = 0.0;
-  for (int i = threadIdx.x; i < n; i += FUSED_THREADS) {
-    const c128 a = v0[i], b = w[i];
-    ar += a.x * b.x + a.y * b.y;       // conj(v0) * w
-    ai += a.x * b.y - a.y * b.x;
+#pragma unroll
+  for (int k = 0; k < FUSED_PER_THREAD; ++k) {
+    const int i = base + k * STRIDE;
+    x[k] = {0.0, 0.0};
+    if (i < n) {
+      x[k] = w[i];
+      const c128 a = v0[i];
+      ar += a.x * x[k].x + a.y * x[k].y;       // conj(v0) * w
+      ai += a.x * x[k].y - a.y * x[k].x;
+    }
   }
   cta_sum2(ar, ai, sm);
+  if (threadIdx.x == 0) { part[0][0] = ar; part[0][1] = ai; }
+  cluster.sync();
+  ar = 0.0; ai = 0.0;
+#pragma unroll
+  for (int q = 0; q < FUSED_CLUSTER; ++q) {
+    const double* rp = cluster.map_shared_rank(&part[0][0], q);
+    ar += rp[0]; ai += rp[1];
+  }
   const double bp = v2 ? *beta_prev : 0.0;
   double nn = 0.0, dummy = 0.0;
-  for (int i = threadIdx.x; i < n; i += FUSED_THREADS) {
-    c128 x = w[i];
-    const c128 a = v1[i];
-    x.x -= a.x * ar - a.y * ai;
-    x.y -= a.x * ai + a.y * ar;
-    if (v2) {
-      const c128 b = v2[i];
-      x.x -= b.x * bp;
-      x.y -= b.y * bp;
+#pragma unroll
+  for (int k = 0; k < FUSED_PER_THREAD; ++k) {
+    const int i = base + k * STRIDE;
+    if (i < n) {
+      const c128 a = v1[i];
+      x[k].x -= a.x * ar - a.y * ai;
+      x[k].y -= a.x * ai + a.y * ar;
+      if (v2) {
+        const c128 b = v2[i];
+        x[k].x -= b.x * bp;
+        x[k].y -= b.y * bp;
+      }
+      nn += x[k].x * x[k].x + x[k].y * x[k].y;
     }
-    w[i] = x;
-    nn += x.x * x.x + x.y * x.y;
   }
   cta_sum2(nn, dummy, sm);
+  if (threadIdx.x == 0) part[1][0] = nn;
+  cluster.sync();
+  nn = 0.0;
+#pragma unroll
+  for (int q = 0; q < FUSED_CLUSTER; ++q) nn += *cluster.map_shared_rank(&part[1][0], q);
   const double beta = sqrt(nn);
-  if (threadIdx.x == 0) {
+  if (rank == 0 && threadIdx.x == 0) {
     alpha2[0] = ar; alpha2[1] = ai;
     beta_out[0] = beta;
     if (fabs(ai) > 1e-10) *areal_flag = 0.0;
   }
-  if (beta < min_div) return;          // Krylov space exhausted: the vector is left untouched (it is never used)
-  for (int i = threadIdx.x; i < n; i += FUSED_THREADS) {
-    c128 x = w[i];
-    x.x /= beta; x.y /= beta;
-    w[i] = x;
+  const bool scale = beta >= min_div;          // Krylov space exhausted otherwise: the vector is stored unscaled (never used)
+#pragma unroll
+  for (int k = 0; k < FUSED_PER_THREAD; ++k) {
+    const int i = base + k * STRIDE;
+    if (i < n) {
+      c128 y = x[k];
+      if (scale) { y.x /= beta; y.y /= beta; }
+      w[i] = y;
+    }
   }
+  cluster.sync();                              // nobody leaves while a neighbour may still read its partials
 }
 
 // Arnoldi: h[i] = <V_i | w>, i < k   (one pass over w, k passes over V)
@@ -623,7 +661,7 @@ int krylov_expm_exec(Handle* h, int kind, double scale_re, double scale_im, doub
     }
     if (kind == TDVP_KRYLOV_LANCZOS_REF && N <= FUSED_MAX_N) {
       { ProfScope _ps(st, "vec.k_lanczos_step_small");
-        k_lanczos_step_small<<<1, FUSED_THREADS, 0, st>>>(V, w, V + (size_t)l * N, l > 0 ? V + (size_t)(l - 1) * N : nullptr, (int)N,
+        k_lanczos_step_small<<<FUSED_CLUSTER, FUSED_THREADS, 0, st>>>(V, w, V + (size_t)l * N, l > 0 ? V + (size_t)(l - 1) * N : nullptr, (int)N,
                                                            S + S_ALPHA + 2 * l, S + S_BETA + (l > 0 ? l - 1 : 0), S + S_BETA + l,
                                                            S + S_AREAL, EPS_K); }
       TDVP_TRY(lc(h, "k_lanczos_step_small"));
