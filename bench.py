@@ -77,6 +77,7 @@ def parse_args():
     ap.add_argument("--no-extras", action="store_true", help="skip the heff_matvec / d256 / site_parallel / c1 blocks")
     ap.add_argument("--gemm", default="auto", choices=["auto", "big", "small", "tiny", "tma"], help="force a GEMM tile configuration (tuning)")
     ap.add_argument("--no-graphs", action="store_true", help="disable CUDA-graph replay of the small-D site updates (tuning)")
+    ap.add_argument("--no-merge", action="store_true", help="D <= 64 workloads: keep one GEMM chain per MPO key (tuning)")
     return ap.parse_args()
 
 
@@ -406,7 +407,10 @@ class Bench:
         from pytdscf_b200._mps_cuda import DeviceMPO, MPSCoefCuda
 
         model = wl.model()
-        H = DeviceMPO(self.eng, model.hamiltonian)
+        # launch-bound workloads (D <= 64) run the whole-chain MPO keys as one direct-sum MPO (DeviceMPO.merge_terms)
+        merge = wl.bond_dim <= 64 and not site_parallel and not self.args.no_merge
+        H = DeviceMPO(self.eng, model.hamiltonian, merge_terms=merge)
+        self.last_merged = bool(H.merged)
         cfg = RunConfig(jobname="bench", space=wl.space, integrator=wl.integrator, conserve_norm=wl.conserve_norm)
         if site_parallel:
             from pytdscf_b200._mps_parallel import Comm, MPSCoefParallelCuda, balanced_split
@@ -498,7 +502,7 @@ class Bench:
         nK = trace[trace[:, 0] == 1][:, 2] if len(trace) else np.array([0.0])
         gemm_tflops = prof["flops"] / (prof["ms"] * 1e-3) / 1e12 if prof["ms"] > 0 else 0.0
         top = sorted(breakdown.items(), key=lambda kv: -kv[1]["ms"])
-        return {"mps": mps, "H": H, "cfg": cfg, "ms": ms, "ms_prof": ms_prof, "steps": steps, "clocks": clocks, "launches": int(launches),
+        return {"mps": mps, "H": H, "cfg": cfg, "merged": bool(getattr(H, "merged", False)), "ms": ms, "ms_prof": ms_prof, "steps": steps, "clocks": clocks, "launches": int(launches),
                 "graph_replays": int(graph_replays), "trace_len": len(trace), "flops_all": flops_all,
                 "avg_matvecs_H": float(nH.mean()), "avg_matvecs_K": float(nK.mean()) if len(nK) else 0.0,
                 "gemm_tflops": gemm_tflops, "gemm_launches": int(prof["launches"]), "gemm_share": prof["ms"] / ms_prof,
@@ -659,6 +663,7 @@ def run_cuda(args):
             n1 = len(w1.dims)
             extras["c1"] = {"workload": w1.name, "sweeps_per_s": 2 * 10 / (m1["ms"] * 1e-3),
                             "us_per_site_update": m1["ms"] * 1e3 / (10 * 2 * n1), "launches_per_sweep": m1["launches"] / 20,
+                            "mpo_direct_sum": m1["merged"],
                             "graph_replays_per_sweep": m1["graph_replays"] / 20}
             del m1
             torch.cuda.empty_cache()
@@ -711,6 +716,7 @@ def run_cuda(args):
         "krylov": {"avg_matvecs_H": m["avg_matvecs_H"], "avg_matvecs_K": m["avg_matvecs_K"],
                    "solves_per_step": m["trace_len"] / args.steps, "tflop_per_sweep": flops_per_sweep / 1e12},
         "gpu_launches": m["launches"],
+        "mpo_direct_sum": bool(m.get("merged", False)),
         "roofline": {"kernel": "zgemm (DMMA)", "bound": "tensor", "achieved": m["gemm_tflops"], "peak": FP64_DMMA_PEAK_TFLOPS,
                      "unit": "TFLOP/s", "frac": m["gemm_tflops"] / FP64_DMMA_PEAK_TFLOPS,
                      "traffic": None if ncu is None else ncu.get("dram_bytes_per_launch"),

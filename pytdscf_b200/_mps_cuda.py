@@ -100,29 +100,77 @@ def identity_channels(cores: list[np.ndarray]) -> tuple[list[int], list[int]]:
     return bond[:n], dnob[1:]
 
 
-class DeviceMPO:
-    """MPO cores of a ``TensorHamiltonian`` uploaded to HBM once (complex128; float cores are widened)."""
+def direct_sum_mpo(core_lists: list[list[np.ndarray]]) -> list[np.ndarray]:
+    """Direct sum of full-length MPOs: ONE MPO whose bond space is the disjoint union of the inputs' bond spaces
+    (block-diagonal cores, a row of blocks on the first site and a column on the last), i.e. the operator sum.  Diagonal
+    (3-index) cores are expanded to 4-index ones."""
+    n = len(core_lists[0])
+    full = []
+    for cores in core_lists:
+        row = []
+        for W in cores:
+            W = np.asarray(W, dtype=np.complex128)
+            if W.ndim == 3:
+                d = W.shape[1]
+                F = np.zeros((W.shape[0], d, d, W.shape[2]), dtype=np.complex128)
+                idx = np.arange(d)
+                F[:, idx, idx, :] = W
+                W = F
+            row.append(W)
+        full.append(row)
+    out = []
+    for k in range(n):
+        blocks = [row[k] for row in full]
+        d = blocks[0].shape[1]
+        wl = 1 if k == 0 else sum(b.shape[0] for b in blocks)
+        wr = 1 if k == n - 1 else sum(b.shape[3] for b in blocks)
+        W = np.zeros((wl, d, d, wr), dtype=np.complex128)
+        a = c = 0
+        for b in blocks:
+            la, lc = (0 if k == 0 else a), (0 if k == n - 1 else c)
+            W[la:la + b.shape[0], :, :, lc:lc + b.shape[3]] += b
+            a += b.shape[0]
+            c += b.shape[3]
+        out.append(W)
+    return out
 
-    def __init__(self, eng: Engine, ham: TensorHamiltonian):
+
+class DeviceMPO:
+    """MPO cores of a ``TensorHamiltonian`` uploaded to HBM once (complex128; float cores are widened).
+
+    ``merge_terms``: combine all MPO keys that span the whole chain into one direct-sum MPO.  The operator is the same sum;
+    H_eff / K_eff / the environment updates then issue one GEMM chain instead of one per key.  Worth it only where a sweep
+    is bound by kernel LAUNCHES (D <= 64: BASELINE configs 1 and 2 carry a potential and a kinetic MPO): the block-diagonal
+    cores make stage 2 do (w_1 + w_2)^2 d^2 work instead of w_1^2 d + w_2^2 d^2, which would cost 10-15 % of a step at
+    D >= 256, and the order of the term sum (hence rounding) differs from the reference's."""
+
+    def __init__(self, eng: Engine, ham: TensorHamiltonian, merge_terms: bool = False):
         mpo = ham.mpo[0][0]
         self.coupleJ = complex(ham.coupleJ[0][0])
         self.nsite = mpo.nsite
-        self.calc_point: list[list[DeviceTerm]] = []
-        ids = {}      # (key, site) -> (l_id, r_id)
+        self.calc_point: list[list[DeviceTerm]] = [[] for _ in range(mpo.nsite)]
         self.bond_ids: dict = {}   # (key, bond b between sites b-1 and b) -> (prefix channel, suffix channel)
-        permuted = {}  # (key, site) -> core with re-ordered MPO bond channels
         # per key the cores as the site lists hold them NOW (a Liouville sub-space projection, ``project_subspace``, has
         # already cut their physical indices there), in site order
         by_key: dict = {}
         for cps in mpo.calc_point:
             for c in cps:
                 by_key.setdefault(c.key, []).append((c.psite, c.data))
+        term_list = []          # (key, sites, cores)
         for key, lst in by_key.items():
-            sites = [s for s, _ in lst]
-            cores = [d for _, d in lst]
-            if any(isinstance(c, int) for c in cores):
-                continue
-            cores = [np.asarray(c) for c in cores]
+            if any(isinstance(d, int) for _, d in lst):
+                raise NotImplementedError(
+                    f"MPO key {key} skips a site: identity gap cores fail in the reference's H_eff apply "
+                    "as well (pytdscf/_contraction.py:1067); give full-length cores instead")
+            term_list.append((key, [s for s, _ in lst], [np.asarray(d) for _, d in lst]))
+        if merge_terms:
+            whole = [t for t in term_list if t[1] == list(range(mpo.nsite))]
+            if len(whole) >= 2 and mpo.nsite >= 2:
+                merged_key = ("direct_sum",) + tuple(t[0] for t in whole)
+                rest = [t for t in term_list if t[1] != list(range(mpo.nsite))]
+                term_list = [(merged_key, list(range(mpo.nsite)), direct_sum_mpo([t[2] for t in whole]))] + rest
+        self.merged = merge_terms and any(isinstance(t[0], tuple) and t[0][:1] == ("direct_sum",) for t in term_list)
+        for key, sites, cores in term_list:
             pre, suf = identity_channels(cores)
             # Re-order the channels of every internal bond so that the identity-prefix channel comes first and the
             # identity-suffix channel last (the same permutation on the right index of core k-1 and the left index of
@@ -139,22 +187,13 @@ class DeviceMPO:
                     cores[k - 1] = np.ascontiguousarray(np.take(cores[k - 1], order, axis=-1))
                     cores[k] = np.ascontiguousarray(np.take(cores[k], order, axis=0))
             pre, suf = identity_channels(cores)
-            for k, s in enumerate(sites):
-                ids[(key, s)] = (pre[k], suf[k])
-                permuted[(key, s)] = cores[k]
-                if k > 0 and sites[k - 1] == s - 1:
-                    self.bond_ids[(key, s)] = (pre[k], suf[k - 1])
-        for cores in mpo.calc_point:
-            terms = []
-            for c in cores:
-                if isinstance(c.data, int):
-                    raise NotImplementedError(
-                        f"MPO key {c.key} skips site {c.psite}: identity gap cores fail in the reference's H_eff apply "
-                        "as well (pytdscf/_contraction.py:1067); give full-length cores instead")
-                dc = eng.upload_core(permuted.get((c.key, c.psite), c.data))
-                dc.l_id, dc.r_id = ids.get((c.key, c.psite), (-1, -1))
-                terms.append(DeviceTerm(c.key, dc, c.is_left_side, c.is_right_side))
-            self.calc_point.append(terms)
+            lo, hi = min(sites), max(sites)
+            for k, site in enumerate(sites):
+                dc = eng.upload_core(cores[k])
+                dc.l_id, dc.r_id = pre[k], suf[k]
+                self.calc_point[site].append(DeviceTerm(key, dc, site == lo, site == hi))
+                if k > 0 and sites[k - 1] == site - 1:
+                    self.bond_ids[(key, site)] = (pre[k], suf[k - 1])
 
 
 def bond_dims(dims: list[int], isite: int, m: int) -> tuple[int, int]:

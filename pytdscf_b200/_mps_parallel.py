@@ -99,9 +99,6 @@ class Comm:
         views = [torch.view_as_real(t.cpu() if self.staged else t) for t in tensors]
         if not views:
             return
-        if len(views) == 1:
-            (self.dist.send if op is self.dist.isend else self.dist.recv)(views[0], peer)
-            return
         for req in self.dist.batch_isend_irecv([self.dist.P2POp(op, v, peer) for v in views]):
             req.wait()
 

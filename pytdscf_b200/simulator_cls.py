@@ -29,11 +29,12 @@ class WFunc:
         self.eng = eng
         self.space = space
         self._dev_ops: dict[int, DeviceMPO] = {}
+        self.merge_mpo_terms = False   # set by Simulator: direct-sum the whole-chain MPO keys (launch-bound small-D runs)
 
     def device_op(self, op) -> DeviceMPO:
         key = id(op)
         if key not in self._dev_ops:
-            self._dev_ops[key] = DeviceMPO(self.eng, op)
+            self._dev_ops[key] = DeviceMPO(self.eng, op, merge_terms=self.merge_mpo_terms)
         return self._dev_ops[key]
 
     def expectation(self, op) -> float:
@@ -241,6 +242,11 @@ class Simulator:
         else:
             wf = self.get_initial_wavefunction(restart, loadfile_ext)
         wf.ci_coef.record_trace = record_trace
+        # opt-in for the launch-bound regime (D <= 64, several whole-chain MPO keys): ``sim.merge_mpo_terms = True`` makes
+        # DeviceMPO build one direct-sum MPO, i.e. one GEMM chain per apply instead of one per key.  Off by default because
+        # the order of the term sum then differs from the reference's (results agree to ~1e-11 instead of ~1e-14); not
+        # available for adaptive / site-parallel runs, whose bookkeeping addresses the keys individually.
+        wf.merge_mpo_terms = bool(getattr(self, "merge_mpo_terms", False)) and split is None and not adaptive
         self.history = []
         files = self._open_files(cfg) if write_files else None
         if write_files:
