@@ -169,14 +169,16 @@ def test_site_update_replay_at_bench_shape(eng, name, d, cfg):
 
 
 # -------------------------------------------------------------------------------------------------------------
-def test_c2_full_step_matches_oracle(eng):
+@pytest.mark.parametrize("merge", [False, True], ids=["per-key", "direct-sum"])
+def test_c2_full_step_matches_oracle(eng, merge):
     """One full time step (2 half sweeps, 64 sites, D = 64, 254 Krylov solves) of BASELINE config 2 -- the launch-bound
     regime that uses the tiny GEMM tiles and, from round 2 on, captured CUDA graphs -- against ``TDVPOracle`` on the host.
 
     The oracle's own Krylov trace is not stable under one-ulp perturbations at this size (tests/golden/noise_floor_c2.json:
     2 of 3 seeded 2e-16 perturbations of the H_eff outputs move one stop decision by +-1 and the autocorrelation by
     5e-12), so the trace may differ from the oracle's in at most 3 solves by at most one vector; energy and
-    autocorrelation must agree to 1e-10."""
+    autocorrelation must agree to 1e-10.  ``merge``: the opt-in direct-sum MPO (one GEMM chain for potential + kinetic
+    terms, ``DeviceMPO(merge_terms=True)``), which bench.py uses for the D <= 64 workloads."""
     from pytdscf_b200._const_cls import RunConfig
     from pytdscf_b200._mps_cuda import DeviceMPO, MPSCoefCuda
 
@@ -185,7 +187,8 @@ def test_c2_full_step_matches_oracle(eng):
     o = orc.TDVPOracle(Ho, orc.initial_mps(wl.dims, wl.bond_dim, wl.hartree, space=wl.space), integrator=wl.integrator,
                        conserve_norm=wl.conserve_norm, space=wl.space)
     model = wl.model()
-    H = DeviceMPO(eng, model.hamiltonian)
+    H = DeviceMPO(eng, model.hamiltonian, merge_terms=merge)
+    assert H.merged == merge
     mps = MPSCoefCuda.alloc_random(eng, model)
     for c, r in zip(mps.to_numpy(), o.mps, strict=True):
         np.testing.assert_allclose(c, r, rtol=0, atol=1e-13)
