@@ -387,10 +387,13 @@ class Bench:
 
         self.torch = torch
         self.args = args
-        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
-        self.info = parallel.init_from_env("nccl")
-        self.rank, self.world, self.local_rank, self.dist = self.info.rank, self.info.world, self.info.local_rank, self.info.dist
-        self.eng = Engine(self.local_rank)
+        # TDVP_BENCH_BACKEND=gloo (debugging only, never a bench line): lets more ranks than GPUs share the devices
+        backend = os.environ.get("TDVP_BENCH_BACKEND", "nccl")
+        dev = int(os.environ.get("LOCAL_RANK", "0")) % max(1, torch.cuda.device_count())
+        torch.cuda.set_device(dev)
+        self.info = parallel.init_from_env(backend)
+        self.rank, self.world, self.local_rank, self.dist = self.info.rank, self.info.world, dev, self.info.dist
+        self.eng = Engine(dev)
         if args.gemm != "auto":
             self.eng.set_gemm_config(args.gemm, 0, 0)
         if args.no_graphs and hasattr(self.eng, "use_graphs"):
