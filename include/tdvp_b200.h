@@ -79,8 +79,8 @@ int tdvp_gemm_profile(int enable, int reset, double* ms, double* flops, unsigned
 size_t tdvp_profile_json(char* out, size_t cap);
 
 /* Test / tuning override of the GEMM launch choice for every later call on this handle (0 = automatic everywhere):
- * tile_cfg 1 = big (128x64 CTA tile), 2 = small (64x32), 3 = tiny (32x32), 4 = tma (persistent TMA-fed 128x64; shapes it
- * cannot serve fall back to the automatic choice); splitk 1 = never split K, S >= 2 = S chunks where K allows;
+ * tile_cfg 1 = big (128x64 CTA tile), 2 = small (64x32), 3 = tiny (32x32), 4 = tma (persistent TMA-fed 128x64 with stream-K
+ * balancing; shapes it cannot serve fall back to the automatic choice), 5 = tma with whole tiles only; splitk 1 = never split K, S >= 2 = S chunks where K allows;
  * c_stream 1 = always store C with evict-first, 2 = never.  The parity tests use it to pin EVERY configuration on the
  * benchmarked shapes (tests/test_gpu_bench_shapes.py); production code leaves it at 0. */
 int tdvp_set_gemm_config(tdvp_handle_t h, int tile_cfg, int splitk, int c_stream);

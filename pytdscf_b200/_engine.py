@@ -326,7 +326,7 @@ class Engine:
                                           B.shape[1], b.real, b.imag, _ptr(C_out), C_out.shape[1]))
         return C_out
 
-    GEMM_CFGS = {"auto": 0, "big": 1, "small": 2, "tiny": 3, "tma": 4}
+    GEMM_CFGS = {"auto": 0, "big": 1, "small": 2, "tiny": 3, "tma": 4, "tma_tiles": 5}
 
     def set_gemm_config(self, tile: str = "auto", splitk: int = 0, c_stream: int = 0):
         """Force the GEMM tile configuration / split-K factor / evict-first stores (tests and tuning; see the header)."""

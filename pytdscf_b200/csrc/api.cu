@@ -107,6 +107,10 @@ int tdvp_create(int device, void* cuda_stream, tdvp_handle_t* out) {
   h->gemm.scratch = h->d_splitk;
   h->gemm.scratch_elems = tdvp::SPLITK_SCRATCH_ELEMS;
   h->gemm.num_sms = h->num_sms;
+  h->gemm.sk_slots = h->num_sms;
+  if ((e = cudaMalloc((void**)&h->gemm.sk_ws, sizeof(c128) * tdvp::STREAMK_TILE_ELEMS * (size_t)h->num_sms)) != cudaSuccess ||
+      (e = cudaMalloc((void**)&h->gemm.sk_flags, sizeof(int) * (size_t)h->num_sms)) != cudaSuccess) { tdvp_destroy(h); return (int)e; }
+  cudaMemsetAsync(h->gemm.sk_flags, 0, sizeof(int) * (size_t)h->num_sms, h->stream);
   int rc = 0;
   if ((e = tdvp::zgemm_configure_device()) != cudaSuccess) rc = (int)e;
   if (!rc) rc = tdvp::qr_configure(h);
@@ -117,7 +121,7 @@ int tdvp_create(int device, void* cuda_stream, tdvp_handle_t* out) {
 }
 
 int tdvp_set_gemm_config(tdvp_handle_t h, int tile_cfg, int splitk, int c_stream) {
-  if (!h || tile_cfg < 0 || tile_cfg > 4 || splitk < 0 || splitk > 16 || c_stream < 0 || c_stream > 2) return TDVP_ERR_ARG;
+  if (!h || tile_cfg < 0 || tile_cfg > 5 || splitk < 0 || splitk > 16 || c_stream < 0 || c_stream > 2) return TDVP_ERR_ARG;
   h->gemm.force_cfg = tile_cfg;
   h->gemm.force_splitk = splitk;
   h->gemm.force_cstream = c_stream;
@@ -134,6 +138,8 @@ int tdvp_destroy(tdvp_handle_t h) {
   if (h->d_partial) cudaFree(h->d_partial);
   if (h->d_counter) cudaFree(h->d_counter);
   if (h->d_splitk) cudaFree(h->d_splitk);
+  if (h->gemm.sk_ws) cudaFree(h->gemm.sk_ws);
+  if (h->gemm.sk_flags) cudaFree(h->gemm.sk_flags);
   delete h;
   return 0;
 }

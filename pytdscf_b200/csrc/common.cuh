@@ -74,10 +74,16 @@ struct GemmCtx {
   c128* scratch = nullptr;       // split-K partial products (may be null: no split-K)
   size_t scratch_elems = 0;
   int num_sms = 148;
-  int force_cfg = 0;             // 1 big (128x64), 2 small (64x32), 3 tiny (32x32), 4 tma (persistent TMA-fed 128x64)
+  int force_cfg = 0;             // 1 big (128x64), 2 small (64x32), 3 tiny (32x32), 4 tma (persistent TMA-fed 128x64), 5 tma without stream-K
   int force_splitk = 0;          // 1 = never split, S >= 2 = S chunks (where K and the scratch allow it)
   int force_cstream = 0;         // 1 = evict-first stores of C always, 2 = never
+  // stream-K fix-up buffers of the TMA kernel (one 128 x 64 accumulator image and one flag per CTA) and the launch epoch
+  c128* sk_ws = nullptr;
+  int* sk_flags = nullptr;
+  int sk_slots = 0;
+  mutable int sk_epoch = 0;
 };
+constexpr size_t STREAMK_TILE_ELEMS = 128 * 64;
 // Per-device kernel attributes (dynamic shared memory limits): called by tdvp_create for every new handle.
 cudaError_t zgemm_configure_device();
 // GEMM with automatic tile configuration and split-K for shapes that would leave most of the SMs idle (few output

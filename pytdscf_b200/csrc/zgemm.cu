@@ -403,12 +403,12 @@ inline Choice choose(const GemmDesc& d, const GemmCtx& ctx) {
   const bool allow_split = ctx.scratch != nullptr && ctx.force_splitk != 1;
   const size_t scratch_elems = ctx.scratch_elems;
   // force_cfg 4 (tma) shares the big tile's geometry: the split-K factor is chosen as for the forced big configuration
-  const int forced = ctx.force_cfg == 4 ? 1 : (ctx.force_cfg >= 1 && ctx.force_cfg <= 3 ? ctx.force_cfg : 0);
+  const int forced = ctx.force_cfg >= 4 ? 1 : (ctx.force_cfg >= 1 && ctx.force_cfg <= 3 ? ctx.force_cfg : 0);
   const double bw = 5.0e12;
   // >= 8 full waves of big tiles with a long K: wave quantisation is < 6 % and the big tiles need the least L2 traffic
   // per flop (short-K GEMMs such as H_eff stage 2 are prologue-bound and keep the free choice)
   const bool large = tiles_of(d, 128, 64) >= 8 * 148 && d.K >= 512;
-  const bool tma_ok = (ctx.force_cfg == 0 || ctx.force_cfg == 4) && zgemm_tma_eligible(d);
+  const bool tma_ok = (ctx.force_cfg == 0 || ctx.force_cfg >= 4) && zgemm_tma_eligible(d);
   for (const CfgModel& m : MODELS) {
     if (m.id == 4 ? !tma_ok : (m.id == 1 && tma_ok)) continue;           // the TMA kernel stands in for the big tile
     const int mid = m.id == 4 ? 1 : m.id;                                 // ... and shares its geometry / forcing rules
@@ -435,6 +435,8 @@ inline Choice choose(const GemmDesc& d, const GemmCtx& ctx) {
       // sweep fits as fractional waves + half a wave of tail
       double waves = (double)((units + slots - 1) / slots);
       if (m.id == 3 && units >= slots) waves = (double)units / slots + 0.5;
+      // the TMA kernel cuts the tiles x k-tiles space evenly over the SMs (stream-K): fractional waves + the fix-up
+      if (m.id == 4 && S == 1 && units >= slots && ctx.force_cfg != 5 && ctx.sk_ws) waves = (double)units / slots + 0.1;
       double t = waves * (chunk + m.K0) * per_k * m.bias;
       // split-K pays a second launch; in the launch-bound small-D regime that launch costs a full ~9 us slot of the stream
       // (r2 c2 profile: 2300 reduction launches per step), elsewhere ~4 us
@@ -490,7 +492,7 @@ cudaError_t zgemm_auto(const GemmDesc& d, const GemmCtx& ctx) {
   const Choice ch = choose(d, ctx);
   const int S = ch.S, chunk = ch.chunk;
   // the big-tile work goes to the persistent TMA kernel whenever tensor maps can describe the operands
-  const bool want_tma = ctx.force_cfg == 4 || (ctx.force_cfg == 0 && ch.cfg == 1);
+  const bool want_tma = ctx.force_cfg >= 4 || (ctx.force_cfg == 0 && ch.cfg == 1);
   auto launch = [&](const GemmDesc& g) -> cudaError_t {
     if (want_tma) {
       bool used = false;

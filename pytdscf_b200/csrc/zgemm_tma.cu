@@ -68,6 +68,16 @@ struct TmaParams {
   long long c_m1, c_m0, c_n, c_split;
   c128 alpha, beta;
   int c_stream;
+  // stream-K (splitk == 1, at least one tile per CTA): the tiles x k-tiles iteration space is cut into gridDim.x equal
+  // contiguous ranges; a tile that straddles two ranges is finished by the second CTA from the first one's partial sums
+  int streamk;         // 0: whole tiles round-robin (and split-K work items)
+  int epoch;           // value the head writer stores into sk_flags[cta] (grows with every launch: no reset needed)
+  int* sk_flags;       // one per CTA
+  c128* sk_ws;         // one BM x BN accumulator image per CTA, in fragment order
+};
+
+struct Seg {
+  int tm, tn, split, kt0, kt1, role;   // role 0: whole tile (or split-K item), 1: head part -> publish, 2: tail part -> finish
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -125,6 +135,50 @@ __device__ __forceinline__ void decode_work(const TmaParams& p, int w, int& tm, 
   tn = (pid % in_group) / gsz;
 }
 
+// Number of segments of this CTA and the si-th of them.  Stream-K order inside a CTA: the trailing partial tile (the HEAD
+// part of a tile the next CTA finishes) first, then the whole tiles, the leading partial tile (TAIL part, finished here from
+// the previous CTA's partial) last -- so a finisher never waits for work its neighbour has not started with.
+__device__ __forceinline__ int seg_count(const TmaParams& p, int KT) {
+  const int total = p.tiles_m * p.tiles_n * p.splitk;
+  if (!p.streamk) return (int)blockIdx.x < total ? (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const long long I = (long long)total * KT;
+  const long long a = I * blockIdx.x / gridDim.x, b = I * (blockIdx.x + 1) / gridDim.x;
+  if (b <= a) return 0;
+  const int first = (int)(a / KT), last = (int)((b - 1) / KT);
+  return last - first + 1;       // lead (partial or whole) + middle tiles + trail (partial or whole)
+}
+
+__device__ __forceinline__ Seg get_seg(const TmaParams& p, int si, int KT) {
+  Seg sg;
+  const int total = p.tiles_m * p.tiles_n * p.splitk;
+  if (!p.streamk) {
+    const int w = blockIdx.x + si * gridDim.x;
+    decode_work(p, w, sg.tm, sg.tn, sg.split);
+    const int k_begin = sg.split * p.k_chunk;
+    const int k_end = (p.splitk > 1 && k_begin + p.k_chunk < p.K) ? k_begin + p.k_chunk : p.K;
+    sg.kt0 = 0;
+    sg.kt1 = (k_end - k_begin + BK - 1) / BK;
+    sg.role = 0;
+    return sg;
+  }
+  const long long I = (long long)total * KT;
+  const long long a = I * blockIdx.x / gridDim.x, b = I * (blockIdx.x + 1) / gridDim.x;
+  const int first = (int)(a / KT), a_off = (int)(a % KT), last = (int)((b - 1) / KT), b_off = (int)(b - (long long)last * KT);
+  int tile;
+  if (first == last) {                       // the whole range lies in one tile (a whole tile when ranges are >= KT long)
+    tile = first; sg.kt0 = a_off; sg.kt1 = b_off;
+    sg.role = (a_off == 0 && b_off == KT) ? 0 : (a_off == 0 ? 1 : 2);
+  } else {
+    const int n = last - first + 1;
+    // order: [trail, middle..., lead]
+    if (si == 0) { tile = last; sg.kt0 = 0; sg.kt1 = b_off; sg.role = b_off == KT ? 0 : 1; }
+    else if (si == n - 1) { tile = first; sg.kt0 = a_off; sg.kt1 = KT; sg.role = a_off == 0 ? 0 : 2; }
+    else { tile = first + si; sg.kt0 = 0; sg.kt1 = KT; sg.role = 0; }
+  }
+  decode_work(p, tile, sg.tm, sg.tn, sg.split);
+  return sg;
+}
+
 template <bool KMAJOR>
 __device__ __forceinline__ void issue_box(unsigned dst, const CUtensorMap* map, unsigned bar, const TmaSide& s, int row0, int k0) {
   const int lo = s.small_inner ? 0 : (int)((unsigned)row0 % s.inner);
@@ -157,7 +211,8 @@ __global__ void __launch_bounds__(THREADS, 1)
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
-  const int total = p.tiles_m * p.tiles_n * p.splitk;
+  const int KT_full = (p.K + BK - 1) / BK;
+  const int nseg = seg_count(p, KT_full);
 
   if (warp >= CONSUMER_WARPS) {
     // ================= producer: one lane walks the same work list and keeps the ring full =================
@@ -167,13 +222,11 @@ __global__ void __launch_bounds__(THREADS, 1)
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(&mapB) : "memory");
     int stage = 0;
     unsigned phase = 0;
-    for (int w = blockIdx.x; w < total; w += gridDim.x) {
-      int tm, tn, split;
-      decode_work(p, w, tm, tn, split);
-      const int k_begin = split * p.k_chunk;
-      const int k_end = (p.splitk > 1 && k_begin + p.k_chunk < p.K) ? k_begin + p.k_chunk : p.K;
-      const int KT = (k_end - k_begin + BK - 1) / BK;
-      for (int kt = 0; kt < KT; ++kt) {
+    for (int si = 0; si < nseg; ++si) {
+      const Seg sg = get_seg(p, si, KT_full);
+      const int tm = sg.tm, tn = sg.tn;
+      const int k_begin = sg.split * p.k_chunk;
+      for (int kt = sg.kt0; kt < sg.kt1; ++kt) {
         mbar_wait(bars + 8 * (STAGES + stage), phase ^ 1u);      // slot free (passes at once on a fresh barrier)
         const unsigned full = bars + 8 * stage;
         mbar_expect_tx(full, STAGE_BYTES);
@@ -237,12 +290,10 @@ __global__ void __launch_bounds__(THREADS, 1)
   unsigned phase = 0;
   const c128 alpha = p.alpha, beta = p.beta;
   const bool use_beta = (beta.x != 0.0) || (beta.y != 0.0);
-  for (int w = blockIdx.x; w < total; w += gridDim.x) {
-    int tm, tn, split;
-    decode_work(p, w, tm, tn, split);
-    const int k_begin = split * p.k_chunk;
-    const int k_end = (p.splitk > 1 && k_begin + p.k_chunk < p.K) ? k_begin + p.k_chunk : p.K;
-    const int KT = (k_end - k_begin + BK - 1) / BK;
+  for (int si = 0; si < nseg; ++si) {
+    const Seg sg = get_seg(p, si, KT_full);
+    const int tm = sg.tm, tn = sg.tn, split = sg.split;
+    const int KT = sg.kt1 - sg.kt0;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -279,6 +330,41 @@ __global__ void __launch_bounds__(THREADS, 1)
       phase = nphase;
     }
 
+    if (sg.role == 1) {
+      // ---- stream-K head part: publish the partial sums (fragment order: 16-byte stores, consecutive lanes) ----
+      c128* ws = p.sk_ws + (size_t)blockIdx.x * (BM * BN);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+            ws[(size_t)((i * 4 + j) * 2 + e) * (32 * CONSUMER_WARPS) + tid] = c128{cre[i][j][e], cim[i][j][e]};
+      __threadfence();
+      asm volatile("bar.sync 1, %0;\n" ::"n"(32 * CONSUMER_WARPS) : "memory");
+      if (tid == 0) *((volatile int*)(p.sk_flags + blockIdx.x)) = p.epoch;
+      continue;
+    }
+    if (sg.role == 2) {
+      // ---- stream-K tail part: add the head part the previous CTA published (fixed order: head + tail) ----
+      if (tid == 0) {
+        while (*((volatile int*)(p.sk_flags + blockIdx.x - 1)) != p.epoch) {
+        }
+        __threadfence();
+      }
+      asm volatile("bar.sync 1, %0;\n" ::"n"(32 * CONSUMER_WARPS) : "memory");
+      const c128* ws = p.sk_ws + (size_t)(blockIdx.x - 1) * (BM * BN);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const double2 v = __ldcg(reinterpret_cast<const double2*>(ws + (size_t)((i * 4 + j) * 2 + e) * (32 * CONSUMER_WARPS) + tid));
+            cre[i][j][e] = v.x + cre[i][j][e];
+            cim[i][j][e] = v.y + cim[i][j][e];
+          }
+    }
     // ---- epilogue: C = alpha * acc + beta * C (the producer is already filling the ring for the next tile) ----
     c128* __restrict__ Cg = p.C + (long long)split * p.c_split;
     const int tile_m = tm * BM, tile_n = tn * BN;
@@ -495,6 +581,14 @@ cudaError_t zgemm_tma_try(const GemmDesc& d, const GemmCtx& ctx, bool* used) {
   const long long total = (long long)p.tiles_m * p.tiles_n * p.splitk;
   if (total > (1ll << 30)) return cudaSuccess;
   const int grid = (int)(total < ctx.num_sms ? total : ctx.num_sms);
+  // stream-K whenever whole tiles would leave a ragged last round (at least one tile per CTA keeps every tile within two
+  // CTAs); force_cfg 5 = TMA kernel with whole tiles only (A/B tests)
+  const int KT = (d.K + BK - 1) / BK;
+  p.streamk = (p.splitk == 1 && ctx.force_cfg != 5 && ctx.sk_ws && ctx.sk_flags && total >= grid && total % grid != 0 && KT >= 2 &&
+               grid <= ctx.sk_slots) ? 1 : 0;
+  p.sk_flags = ctx.sk_flags;
+  p.sk_ws = ctx.sk_ws;
+  p.epoch = p.streamk ? ++ctx.sk_epoch : 0;
   cudaError_t e;
   {
     ProfScope scope(ctx.stream, d.tag, 8.0 * (double)d.M * (double)d.N * (double)d.K, true);

@@ -44,10 +44,12 @@ GEMM_SHAPES = [
     ("c5 heff stage3 NT pot", 4096, 512, 1536, 0, 1),
     ("c5 keff gemm2 NT", 512, 512, 1536, 0, 1),
     ("qr VhC (skinny, split-K)", 1024, 32, 4096, 1, 0),
+    ("stream-K: 150 tiles on 148 SMs", 1280, 960, 512, 0, 0),
+    ("stream-K: ragged M / N / K tails", 2500, 1100, 1000, 0, 1),
 ]
 # (tile, splitk, c_stream) -- see tdvp_set_gemm_config
 GEMM_CONFIGS = [("auto", 0, 0), ("big", 1, 2), ("big", 1, 1), ("small", 1, 2), ("tiny", 1, 2), ("big", 4, 0), ("tiny", 3, 0),
-                ("tma", 1, 0), ("tma", 2, 0)]
+                ("tma", 1, 0), ("tma", 2, 0), ("tma_tiles", 1, 0)]
 
 
 @pytest.mark.parametrize("cfg", GEMM_CONFIGS, ids=lambda c: f"{c[0]}-S{c[1]}-cs{c[2]}")
