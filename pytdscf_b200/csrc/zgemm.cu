@@ -436,7 +436,7 @@ inline Choice choose(const GemmDesc& d, const GemmCtx& ctx) {
       double waves = (double)((units + slots - 1) / slots);
       if (m.id == 3 && units >= slots) waves = (double)units / slots + 0.5;
       // the TMA kernel cuts the tiles x k-tiles space evenly over the SMs (stream-K): fractional waves + the fix-up
-      if (m.id == 4 && S == 1 && units >= slots && ctx.force_cfg != 5 && ctx.sk_ws) waves = (double)units / slots + 0.1;
+      if (m.id == 4 && S == 1 && units >= slots && d.K >= 256 && ctx.force_cfg != 5 && ctx.sk_ws) waves = (double)units / slots + 0.1;
       double t = waves * (chunk + m.K0) * per_k * m.bias;
       // split-K pays a second launch; in the launch-bound small-D regime that launch costs a full ~9 us slot of the stream
       // (r2 c2 profile: 2300 reduction launches per step), elsewhere ~4 us

@@ -582,9 +582,10 @@ cudaError_t zgemm_tma_try(const GemmDesc& d, const GemmCtx& ctx, bool* used) {
   if (total > (1ll << 30)) return cudaSuccess;
   const int grid = (int)(total < ctx.num_sms ? total : ctx.num_sms);
   // stream-K whenever whole tiles would leave a ragged last round (at least one tile per CTA keeps every tile within two
-  // CTAs); force_cfg 5 = TMA kernel with whole tiles only (A/B tests)
+  // CTAs); short K (< 16 k-tiles: H_eff stage 2) loses more to the fix-up than it gains (r2_zgemm_shapes_tma_streamk.jsonl);
+  // force_cfg 5 = TMA kernel with whole tiles only (A/B tests)
   const int KT = (d.K + BK - 1) / BK;
-  p.streamk = (p.splitk == 1 && ctx.force_cfg != 5 && ctx.sk_ws && ctx.sk_flags && total >= grid && total % grid != 0 && KT >= 2 &&
+  p.streamk = (p.splitk == 1 && ctx.force_cfg != 5 && ctx.sk_ws && ctx.sk_flags && total >= grid && total % grid != 0 && KT >= 16 &&
                grid <= ctx.sk_slots) ? 1 : 0;
   p.sk_flags = ctx.sk_flags;
   p.sk_ws = ctx.sk_ws;
