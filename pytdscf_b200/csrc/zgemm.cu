@@ -435,9 +435,14 @@ inline Choice choose(const GemmDesc& d, const GemmCtx& ctx) {
       // sweep fits as fractional waves + half a wave of tail
       double waves = (double)((units + slots - 1) / slots);
       if (m.id == 3 && units >= slots) waves = (double)units / slots + 0.5;
-      // the TMA kernel cuts the tiles x k-tiles space evenly over the SMs (stream-K): fractional waves + the fix-up
-      if (m.id == 4 && S == 1 && units >= slots && d.K >= 256 && ctx.force_cfg != 5 && ctx.sk_ws) waves = (double)units / slots + 0.1;
-      double t = waves * (chunk + m.K0) * per_k * m.bias;
+      // the TMA kernel cuts the tiles x k-tiles space evenly over the SMs (stream-K): fractional waves + the fix-up (with
+      // half..all as many tiles as SMs a tile is shared by two CTAs, one ~4 us hand-over)
+      double sk_extra = 0.0;
+      if (m.id == 4 && S == 1 && ctx.force_cfg != 5 && ctx.sk_ws) {
+        if (units >= slots && d.K >= 256) waves = (double)units / slots + 0.1;
+        else if (2 * units >= slots && d.K >= 512) { waves = (double)units / slots; sk_extra = 4.0e-6; }
+      }
+      double t = waves * (chunk + m.K0) * per_k * m.bias + sk_extra;
       // split-K pays a second launch; in the launch-bound small-D regime that launch costs a full ~9 us slot of the stream
       // (r2 c2 profile: 2300 reduction launches per step), elsewhere ~4 us
       if (S > 1) t += (double)(S + 2) * d.M * d.N * 16.0 / bw + ((double)d.M * d.N * d.K < 5.0e7 ? 9.0e-6 : 4.0e-6);

@@ -77,7 +77,8 @@ struct TmaParams {
 };
 
 struct Seg {
-  int tm, tn, split, kt0, kt1, role;   // role 0: whole tile (or split-K item), 1: head part -> publish, 2: tail part -> finish
+  int tm, tn, split, kt0, kt1, role;   // role 0: whole tile (or split-K item), 1: head part -> publish, 2: tail part -> finish,
+                                       // 3: middle part (ranges shorter than a tile) -> add the predecessor's sums, publish
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -165,9 +166,9 @@ __device__ __forceinline__ Seg get_seg(const TmaParams& p, int si, int KT) {
   const long long a = I * blockIdx.x / gridDim.x, b = I * (blockIdx.x + 1) / gridDim.x;
   const int first = (int)(a / KT), a_off = (int)(a % KT), last = (int)((b - 1) / KT), b_off = (int)(b - (long long)last * KT);
   int tile;
-  if (first == last) {                       // the whole range lies in one tile (a whole tile when ranges are >= KT long)
+  if (first == last) {                       // the whole range lies in one tile
     tile = first; sg.kt0 = a_off; sg.kt1 = b_off;
-    sg.role = (a_off == 0 && b_off == KT) ? 0 : (a_off == 0 ? 1 : 2);
+    sg.role = (a_off == 0 && b_off == KT) ? 0 : (a_off == 0 ? 1 : (b_off == KT ? 2 : 3));
   } else {
     const int n = last - first + 1;
     // order: [trail, middle..., lead]
@@ -330,23 +331,8 @@ __global__ void __launch_bounds__(THREADS, 1)
       phase = nphase;
     }
 
-    if (sg.role == 1) {
-      // ---- stream-K head part: publish the partial sums (fragment order: 16-byte stores, consecutive lanes) ----
-      c128* ws = p.sk_ws + (size_t)blockIdx.x * (BM * BN);
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-          for (int e = 0; e < 2; ++e)
-            ws[(size_t)((i * 4 + j) * 2 + e) * (32 * CONSUMER_WARPS) + tid] = c128{cre[i][j][e], cim[i][j][e]};
-      __threadfence();
-      asm volatile("bar.sync 1, %0;\n" ::"n"(32 * CONSUMER_WARPS) : "memory");
-      if (tid == 0) *((volatile int*)(p.sk_flags + blockIdx.x)) = p.epoch;
-      continue;
-    }
-    if (sg.role == 2) {
-      // ---- stream-K tail part: add the head part the previous CTA published (fixed order: head + tail) ----
+    if (sg.role >= 2) {
+      // ---- stream-K tail / middle part: add the sums the previous CTA published for this tile (fixed order along k) ----
       if (tid == 0) {
         while (*((volatile int*)(p.sk_flags + blockIdx.x - 1)) != p.epoch) {
         }
@@ -364,6 +350,21 @@ __global__ void __launch_bounds__(THREADS, 1)
             cre[i][j][e] = v.x + cre[i][j][e];
             cim[i][j][e] = v.y + cim[i][j][e];
           }
+    }
+    if (sg.role == 1 || sg.role == 3) {
+      // ---- stream-K head / middle part: publish the sums so far (fragment order: 16-byte stores, consecutive lanes) ----
+      c128* ws = p.sk_ws + (size_t)blockIdx.x * (BM * BN);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+            ws[(size_t)((i * 4 + j) * 2 + e) * (32 * CONSUMER_WARPS) + tid] = c128{cre[i][j][e], cim[i][j][e]};
+      __threadfence();
+      asm volatile("bar.sync 1, %0;\n" ::"n"(32 * CONSUMER_WARPS) : "memory");
+      if (tid == 0) *((volatile int*)(p.sk_flags + blockIdx.x)) = p.epoch;
+      continue;
     }
     // ---- epilogue: C = alpha * acc + beta * C (the producer is already filling the ring for the next tile) ----
     c128* __restrict__ Cg = p.C + (long long)split * p.c_split;
@@ -580,13 +581,27 @@ cudaError_t zgemm_tma_try(const GemmDesc& d, const GemmCtx& ctx, bool* used) {
   p.alpha = d.alpha; p.beta = d.beta; p.c_stream = d.c_stream;
   const long long total = (long long)p.tiles_m * p.tiles_n * p.splitk;
   if (total > (1ll << 30)) return cudaSuccess;
-  const int grid = (int)(total < ctx.num_sms ? total : ctx.num_sms);
-  // stream-K whenever whole tiles would leave a ragged last round (at least one tile per CTA keeps every tile within two
-  // CTAs); short K (< 16 k-tiles: H_eff stage 2) loses more to the fix-up than it gains (r2_zgemm_shapes_tma_streamk.jsonl);
-  // force_cfg 5 = TMA kernel with whole tiles only (A/B tests)
+  int grid = (int)(total < ctx.num_sms ? total : ctx.num_sms);
+  // stream-K whenever whole tiles would leave a ragged last round -- or between half as many tiles as SMs and all of them:
+  // the ranges are then shorter than a tile and a tile's sums pass from one CTA to the next (this replaces split-K + its
+  // reduction kernel for these shapes).  The kernel handles chains of any length, but each link costs ~4 us (128 KB out,
+  // fence, flag, 128 KB in), so with fewer tiles than that the chain loses to split-K (measured: 8 tiles x 80 k-tiles ->
+  // 114 us against 47 us, profiles/r2_zgemm_shapes_auto_chain.jsonl) and is not used.  Short K (< 16 k-tiles: H_eff stage
+  // 2) loses more to the fix-up than it gains; force_cfg 5 = TMA kernel with whole tiles only (A/B tests)
   const int KT = (d.K + BK - 1) / BK;
-  p.streamk = (p.splitk == 1 && ctx.force_cfg != 5 && ctx.sk_ws && ctx.sk_flags && total >= grid && total % grid != 0 && KT >= 16 &&
-               grid <= ctx.sk_slots) ? 1 : 0;
+  p.streamk = 0;
+  if (p.splitk == 1 && ctx.force_cfg != 5 && ctx.sk_ws && ctx.sk_flags && KT >= 16 && ctx.num_sms <= ctx.sk_slots) {
+    if (total >= ctx.num_sms) {
+      p.streamk = (total % ctx.num_sms != 0) ? 1 : 0;
+    } else {
+      if (2 * total >= ctx.num_sms && KT >= 32) { p.streamk = 1; grid = ctx.num_sms; }   // <= 2 links, >= 16 k-tiles each
+      else if (ctx.force_cfg == 4) {                      // forced "tma": long chains too (ranges of >= 4 k-tiles), for the tests
+        long long g = total * KT / 4;
+        if (g > ctx.num_sms) g = ctx.num_sms;
+        if (g > total) { p.streamk = 1; grid = (int)g; }
+      }
+    }
+  }
   p.sk_flags = ctx.sk_flags;
   p.sk_ws = ctx.sk_ws;
   p.epoch = p.streamk ? ++ctx.sk_epoch : 0;
