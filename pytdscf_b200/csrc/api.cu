@@ -33,6 +33,7 @@ int ws_reserve(Handle* h, size_t bytes) {
   // grow geometrically; the old buffer may still be in use by enqueued work -> drain the stream first
   size_t want = bytes + bytes / 4 + (size_t(1) << 20);
   TDVP_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->side) TDVP_CUDA(h, cudaStreamSynchronize(h->side));
   if (h->ws) TDVP_CUDA(h, cudaFree(h->ws));
   h->ws = nullptr;
   h->ws_bytes = 0;
@@ -98,7 +99,13 @@ int tdvp_create(int device, void* cuda_stream, tdvp_handle_t* out) {
   if ((e = cudaMalloc((void**)&h->d_partial, 1024 * 64 * sizeof(double))) != cudaSuccess) { delete h; return (int)e; }
   if ((e = cudaMalloc((void**)&h->d_counter, 16 * sizeof(unsigned int))) != cudaSuccess) { delete h; return (int)e; }
   if ((e = cudaMalloc((void**)&h->d_splitk, tdvp::SPLITK_SCRATCH_ELEMS * sizeof(c128))) != cudaSuccess) { delete h; return (int)e; }
+  if ((e = cudaMalloc((void**)&h->d_partial_side, 1024 * 64 * sizeof(double))) != cudaSuccess ||
+      (e = cudaMalloc((void**)&h->d_counter_side, 16 * sizeof(unsigned int))) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming)) != cudaSuccess) { tdvp_destroy(h); return (int)e; }
   cudaMemsetAsync(h->d_counter, 0, 16 * sizeof(unsigned int), h->stream);
+  cudaMemsetAsync(h->d_counter_side, 0, 16 * sizeof(unsigned int), h->stream);
   cudaMemsetAsync(h->d_scal, 0, 4096 * sizeof(double), h->stream);
   memset(h->h_scal, 0, 4096 * sizeof(double));
   // device limits and kernel attributes are per device: (re)applied for every handle, never cached per process
@@ -138,6 +145,11 @@ int tdvp_destroy(tdvp_handle_t h) {
   if (h->d_partial) cudaFree(h->d_partial);
   if (h->d_counter) cudaFree(h->d_counter);
   if (h->d_splitk) cudaFree(h->d_splitk);
+  if (h->side) { cudaStreamSynchronize(h->side); cudaStreamDestroy(h->side); }
+  if (h->ev_main) cudaEventDestroy(h->ev_main);
+  if (h->ev_side) cudaEventDestroy(h->ev_side);
+  if (h->d_partial_side) cudaFree(h->d_partial_side);
+  if (h->d_counter_side) cudaFree(h->d_counter_side);
   if (h->gemm.sk_ws) cudaFree(h->gemm.sk_ws);
   if (h->gemm.sk_flags) cudaFree(h->gemm.sk_flags);
   delete h;

@@ -21,6 +21,12 @@ struct Handle {
   double* d_partial = nullptr;  // reduction partials: 1024 blocks x 64 doubles
   unsigned int* d_counter = nullptr;  // "last block done" tickets
   c128* d_splitk = nullptr;           // split-K partial products (SPLITK_SCRATCH_ELEMS)
+  // side stream of the Krylov solver: the Ritz vector of the first checked iteration is formed there while the main
+  // stream already runs the next matvec (own reduction partials / ticket, ordered against the main stream by events)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_main = nullptr, ev_side = nullptr;
+  double* d_partial_side = nullptr;
+  unsigned int* d_counter_side = nullptr;
   GemmCtx gemm;                       // stream + scratch + overrides handed to every zgemm_auto call
   // device limits queried once per handle (tdvp_create), never per process
   int num_sms = 148;

@@ -377,13 +377,25 @@ __global__ void __launch_bounds__(512) k_krylov_small_expm(int mode, int k, cons
   const int tid = threadIdx.x;
   const int kk = k * k;
   const c128 sc = {scale_re, scale_im};
+  // "alpha is real" is a property of the k alphas this Ritz step uses (the reference tests them when it builds the matrix,
+  // _integrator.py:617-623), not of whatever later iterations a run-ahead stream may already have produced
+  __shared__ int s_areal;
+  if (tid == 0) {
+    int r = 1;
+    if (mode == 0)
+      for (int i = 0; i < k; ++i)
+        if (fabs(alpha[2 * i + 1]) > 1e-10) r = 0;
+    s_areal = r;
+  }
+  __syncthreads();
+  (void)areal;
   for (int e = tid; e < kk; e += blockDim.x) {
     const int i = e / k, j = e % k;
     c128 t = {0.0, 0.0};
     if (mode == 0) {
       if (i == j) {
         t.x = alpha[2 * i];
-        t.y = (*areal != 0.0) ? 0.0 : alpha[2 * i + 1];
+        t.y = s_areal ? 0.0 : alpha[2 * i + 1];
       } else if (i == j + 1) {
         t.x = beta[j];
       } else if (j == i + 1) {
@@ -651,6 +663,7 @@ int krylov_expm_exec(Handle* h, int kind, double scale_re, double scale_im, doub
   bool have_prev = false;
   int nvec = 1;         // Krylov vectors stored (Arnoldi may stop appending)
   int synced = 0;       // beta_[0 .. synced) are known on the host
+  bool side_pending = false;   // a Ritz step is in flight on the side stream (ev_side marks its end)
   for (int l = 0; l < ndim; ++l) {
     c128* w = V + (size_t)(kind == TDVP_KRYLOV_ARNOLDI ? nvec : l + 1) * N;
     const c128* src = (l == 0) ? psi : (kind == TDVP_KRYLOV_ARNOLDI ? V + (size_t)(nvec - 1) * N : V + (size_t)l * N);
@@ -698,14 +711,19 @@ int krylov_expm_exec(Handle* h, int kind, double scale_re, double scale_im, doub
 
     // ---- Ritz step on device ----
     const int k = l + 1;
-    auto ritz = [&](int kk, c128* yout, const c128* yprev) -> int {
+    auto ritz_on = [&](cudaStream_t rs, double* partial, unsigned int* counter, int kk, c128* yout, const c128* yprev) -> int {
       if (kind == TDVP_KRYLOV_LANCZOS_REF)
-        { ProfScope _ps(st, "vec.k_krylov_small_expm"); k_krylov_small_expm<<<1, 512, 0, st>>>(0, kk, S + S_ALPHA, S + S_BETA, S + S_AREAL, nullptr, scale_re, scale_im, S + S_COEF); }
+        { ProfScope _ps(rs, "vec.k_krylov_small_expm"); k_krylov_small_expm<<<1, 512, 0, rs>>>(0, kk, S + S_ALPHA, S + S_BETA, S + S_AREAL, nullptr, scale_re, scale_im, S + S_COEF); }
       else
-        { ProfScope _ps(st, "vec.k_krylov_small_expm"); k_krylov_small_expm<<<1, 512, 0, st>>>(1, kk, nullptr, nullptr, nullptr, S + S_HESS, scale_re, scale_im, S + S_COEF); }
+        { ProfScope _ps(rs, "vec.k_krylov_small_expm"); k_krylov_small_expm<<<1, 512, 0, rs>>>(1, kk, nullptr, nullptr, nullptr, S + S_HESS, scale_re, scale_im, S + S_COEF); }
       TDVP_TRY(lc(h, "k_krylov_small_expm"));
-      { ProfScope _ps(st, "vec.k_combine"); k_combine<<<nb, RED_THREADS, 0, st>>>(V, N, kk, S + S_COEF, yout, yprev, N, h->d_partial, h->d_counter, S + S_ERR, S + S_YNORM); }
+      { ProfScope _ps(rs, "vec.k_combine"); k_combine<<<nb, RED_THREADS, 0, rs>>>(V, N, kk, S + S_COEF, yout, yprev, N, partial, counter, S + S_ERR, S + S_YNORM); }
       return lc(h, "k_combine");
+    };
+    // Ritz step on the main stream (after whatever the side stream still has in flight: it shares S_COEF / S_ERR)
+    auto ritz = [&](int kk, c128* yout, const c128* yprev) -> int {
+      if (side_pending) { TDVP_CUDA(h, cudaStreamWaitEvent(st, h->ev_side, 0)); side_pending = false; }
+      return ritz_on(st, h->d_partial, h->d_counter, kk, yout, yprev);
     };
     auto finish = [&](c128* yfin, int iters) -> int {
       // rescale: y / |y| (conserve_norm) or y * b0, written back into psi
@@ -717,6 +735,21 @@ int krylov_expm_exec(Handle* h, int kind, double scale_re, double scale_im, doub
     };
     c128* y = ybuf[cur];
     const c128* prev = have_prev ? ybuf[cur ^ 1] : nullptr;
+    // The first checked iteration cannot stop on the change of the Ritz vector (there is no previous one): only on a
+    // breakdown (beta < eps), which the next read-back detects and replays from the stored basis exactly like a breakdown
+    // inside the warm-up.  So nothing is read back here; the Ritz vector (needed as "previous" by the next check) is
+    // formed on the side stream while the main stream goes on with the next matvec.
+    if (!have_prev && (long long)(l + 1) < Nref && l + 1 < ndim && h->side) {
+      TDVP_CUDA(h, cudaEventRecord(h->ev_main, st));
+      TDVP_CUDA(h, cudaStreamWaitEvent(h->side, h->ev_main, 0));
+      TDVP_TRY(ritz_on(h->side, h->d_partial_side, h->d_counter_side, k, y, nullptr));
+      TDVP_CUDA(h, cudaEventRecord(h->ev_side, h->side));
+      side_pending = true;
+      if (kind == TDVP_KRYLOV_ARNOLDI) ++nvec;    // speculative, as in the warm-up
+      have_prev = true;
+      cur ^= 1;
+      continue;
+    }
     TDVP_TRY(ritz(k, y, prev));
     // one read-back per checked iteration: beta_[synced .. l] and the change of the Ritz vector
     TDVP_CUDA(h, cudaMemcpyAsync(h->h_scal + S_BETA + synced, S + S_BETA + synced, sizeof(double) * (l + 1 - synced), cudaMemcpyDeviceToHost, st));
