@@ -65,6 +65,10 @@ struct GemmDesc {
   int k_chunk = 0;
   long long c_split = 0;
   int c_stream = 0;   // set by the launcher: outputs larger than half of L2 are stored with evict-first (st.global.cs)
+  // cluster split-K (tiny / small tiles, S <= 16): the S CTAs of a tile form a thread-block cluster along blockIdx.z; each
+  // keeps its partial tile in its own shared memory and, after one cluster barrier, finishes 1/S of the tile by reading
+  // the S partials through distributed shared memory in rank order.  C, alpha, beta are then the real ones (no scratch).
+  int cluster_sk = 0;
 };
 
 // Per-handle (= per-device) launch context of the GEMM: stream, split-K scratch, device limits and the test /

@@ -16,6 +16,8 @@
 //    every fragment LDS.128 is bank-conflict free for both operand majors.
 //  * rows of A/C and columns of B may be two-level indices (GemmDesc) so contractions such as
 //    T2[a,i,t,s] = sum_{c,j} T1[a,c,j,s] W[c,i,j,t] run on their natural layouts (no transposes).
+#include <cooperative_groups.h>
+
 #include <atomic>
 #include <cstring>
 #include <map>
@@ -332,6 +334,49 @@ __global__ void __launch_bounds__(C::THREADS, C::THREADS == 256 ? 1 : 4) zgemm_d
   // ---- epilogue: C = alpha * acc + beta * C ----
   const c128 alpha = d.alpha, beta = d.beta;
   const bool use_beta = (beta.x != 0.0) || (beta.y != 0.0);
+  if (d.cluster_sk) {
+    // Cluster split-K: partial tiles meet in distributed shared memory instead of a scratch buffer + reduction launch.
+    // Layout [register c = (i, j, e)][thread]: a warp reads 32 consecutive 16-byte words of the remote CTA.
+    static_assert(WI * WJ * 2 * C::THREADS * (int)sizeof(c128) <= C::SMEM_BYTES, "partial tile must fit the stage buffers");
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __syncthreads();                                   // every warp is done with the stage buffers
+    c128* part = reinterpret_cast<c128*>(smem_raw);
+#pragma unroll
+    for (int i = 0; i < WI; ++i)
+#pragma unroll
+      for (int j = 0; j < WJ; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) part[((i * WJ + j) * 2 + e) * C::THREADS + tid] = c128{cre[i][j][e], cim[i][j][e]};
+    cluster.sync();
+    const int S = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+#pragma unroll
+    for (int i = 0; i < WI; ++i) {
+      const int m = tile_m + wm * C::WTM + 8 * i + g;
+      const long long roff = (long long)(m / d.c_m_inner) * d.c_m1 + (long long)(m % d.c_m_inner) * d.c_m0;
+#pragma unroll
+      for (int j = 0; j < WJ; ++j) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int c = (i * WJ + j) * 2 + e;
+          const int n = tile_n + wn * C::WTN + 8 * j + 2 * q + e;
+          if (c % S != rank || m >= d.M || n >= d.N) continue;
+          double sx = 0.0, sy = 0.0;
+          for (int r = 0; r < S; ++r) {                // fixed order: rank 0 .. S-1 = ascending k
+            const c128 v = cluster.map_shared_rank(part, r)[c * C::THREADS + tid];
+            sx += v.x;
+            sy += v.y;
+          }
+          c128* p = d.C + bz * d.c_batch + roff + (long long)n * d.c_n;
+          c128 out = cmul(alpha, c128{sx, sy});
+          if (use_beta) out = cadd(out, cmul(beta, *p));
+          *p = out;
+        }
+      }
+    }
+    cluster.sync();                                    // nobody leaves while its partial may still be read
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < WI; ++i) {
     const int m = tile_m + wm * C::WTM + 8 * i + g;
@@ -357,6 +402,12 @@ __global__ void __launch_bounds__(C::THREADS, C::THREADS == 256 ? 1 : 4) zgemm_d
 template <typename C>
 cudaError_t configure_cfg() {
   cudaError_t e;
+  if (C::THREADS < 256) {   // tiny / small tiles: cluster split-K with up to 16 CTAs per tile
+    if ((e = cudaFuncSetAttribute(zgemm_dmma_kernel<C, true, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1))) return e;
+    if ((e = cudaFuncSetAttribute(zgemm_dmma_kernel<C, true, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1))) return e;
+    if ((e = cudaFuncSetAttribute(zgemm_dmma_kernel<C, false, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1))) return e;
+    if ((e = cudaFuncSetAttribute(zgemm_dmma_kernel<C, false, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1))) return e;
+  }
   if ((e = cudaFuncSetAttribute(zgemm_dmma_kernel<C, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES))) return e;
   if ((e = cudaFuncSetAttribute(zgemm_dmma_kernel<C, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES))) return e;
   if ((e = cudaFuncSetAttribute(zgemm_dmma_kernel<C, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES))) return e;
@@ -368,6 +419,27 @@ cudaError_t launch_cfg(const GemmDesc& d, cudaStream_t stream) {
   dim3 grid((d.N + C::BN - 1) / C::BN, (d.M + C::BM - 1) / C::BM, d.batch * d.splitk);
   const bool ak = (d.a_k == 1), bk = (d.b_k == 1);
   ProfScope scope(stream, d.tag, 8.0 * (double)d.M * (double)d.N * (double)d.K * (double)d.batch, true);
+  if (d.cluster_sk) {
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = grid;
+    lc.blockDim = dim3(C::THREADS);
+    lc.dynamicSmemBytes = C::SMEM_BYTES;
+    lc.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 1;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = (unsigned)d.splitk;
+    lc.attrs = at;
+    lc.numAttrs = 1;
+    cudaError_t e;
+    if (ak && bk) e = cudaLaunchKernelEx(&lc, zgemm_dmma_kernel<C, true, true>, d);
+    else if (ak && !bk) e = cudaLaunchKernelEx(&lc, zgemm_dmma_kernel<C, true, false>, d);
+    else if (!ak && bk) e = cudaLaunchKernelEx(&lc, zgemm_dmma_kernel<C, false, true>, d);
+    else e = cudaLaunchKernelEx(&lc, zgemm_dmma_kernel<C, false, false>, d);
+    count_launch();
+    return e != cudaSuccess ? e : cudaGetLastError();
+  }
   if (ak && bk)
     zgemm_dmma_kernel<C, true, true><<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(d);
   else if (ak && !bk)
@@ -397,6 +469,12 @@ constexpr CfgModel MODELS[4] = {
     {3, 32, 32, 8, 4, 32, 0.040e-6, 0.140e-6, 16.0, 1.00},     // tiny  (832 us / 10.9 waves / 528 k on 1536x4096x512)
 };
 struct Choice { int cfg = 1, S = 1, chunk = 0; double t = 1e30; };
+
+// split-K through a thread-block cluster (GemmDesc::cluster_sk): tiny and small tiles, clusters of up to 16 CTAs (the
+// non-portable size sm_100 offers; allowed per kernel in configure_cfg), one batch; force_cstream = 1 (a test override) keeps the scratch + reduction-kernel path reachable for the tests
+inline bool cluster_splitk_ok(int cfg, int S, const GemmDesc& d, const GemmCtx& ctx) {
+  return (cfg == 2 || cfg == 3) && S >= 2 && S <= 16 && d.batch == 1 && ctx.force_cstream != 1;
+}
 
 inline Choice choose(const GemmDesc& d, const GemmCtx& ctx) {
   Choice best;
@@ -445,7 +523,10 @@ inline Choice choose(const GemmDesc& d, const GemmCtx& ctx) {
       double t = waves * (chunk + m.K0) * per_k * m.bias + sk_extra;
       // split-K pays a second launch; in the launch-bound small-D regime that launch costs a full ~9 us slot of the stream
       // (r2 c2 profile: 2300 reduction launches per step), elsewhere ~4 us
-      if (S > 1) t += (double)(S + 2) * d.M * d.N * 16.0 / bw + ((double)d.M * d.N * d.K < 5.0e7 ? 9.0e-6 : 4.0e-6);
+      // -- unless the S CTAs of a tile can be a cluster (tiny / small tiles, S <= 8): then the partials meet in
+      // distributed shared memory inside the same launch (two cluster barriers, ~2 us)
+      if (S > 1 && cluster_splitk_ok(mid, S, d, ctx)) t += 2.0e-6;
+      else if (S > 1) t += (double)(S + 2) * d.M * d.N * 16.0 / bw + ((double)d.M * d.N * d.K < 5.0e7 ? 9.0e-6 : 4.0e-6);
       if (t < best.t * (S > 1 && best.cfg == mid ? 0.97 : 1.0)) { best.t = t; best.cfg = mid; best.S = S; best.chunk = chunk; }
     }
   }
@@ -511,6 +592,14 @@ cudaError_t zgemm_auto(const GemmDesc& d, const GemmCtx& ctx) {
     // outputs larger than half of L2 are written with evict-first stores
     g1.c_stream = ctx.force_cstream ? (ctx.force_cstream == 1) : ((double)d.M * d.N * d.batch * 16.0 > 64.0e6);
     return launch(g1);
+  }
+  if (!want_tma && cluster_splitk_ok(ch.cfg, S, d, ctx)) {
+    GemmDesc g = d;
+    g.splitk = S;
+    g.k_chunk = chunk;
+    g.c_split = 0;
+    g.cluster_sk = 1;
+    return launch_by_cfg(ch.cfg, g, stream);
   }
   GemmDesc g = d;
   g.C = scratch;

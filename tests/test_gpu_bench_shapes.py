@@ -48,7 +48,10 @@ GEMM_SHAPES = [
     ("stream-K: ragged M / N / K tails", 2500, 1100, 1000, 0, 1),
 ]
 # (tile, splitk, c_stream) -- see tdvp_set_gemm_config
+# split-K of the tiny / small tiles runs as a thread-block cluster of S <= 16 CTAs (partials reduced through distributed
+# shared memory); c_stream = 1 (or the big tile) keeps the scratch + reduction-kernel path under test
 GEMM_CONFIGS = [("auto", 0, 0), ("big", 1, 2), ("big", 1, 1), ("small", 1, 2), ("tiny", 1, 2), ("big", 4, 0), ("tiny", 3, 0),
+                ("tiny", 8, 0), ("small", 4, 0), ("tiny", 3, 1), ("tiny", 16, 0), ("tiny", 12, 1),
                 ("tma", 1, 0), ("tma", 2, 0), ("tma_tiles", 1, 0)]
 
 
