@@ -76,7 +76,6 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the heff_matvec / d256 / site_parallel / c1 blocks")
     ap.add_argument("--gemm", default="auto", choices=["auto", "big", "small", "tiny", "tma"], help="force a GEMM tile configuration (tuning)")
-    ap.add_argument("--no-graphs", action="store_true", help="disable CUDA-graph replay of the small-D site updates (tuning)")
     ap.add_argument("--no-merge", action="store_true", help="D <= 64 workloads: keep one GEMM chain per MPO key (tuning)")
     return ap.parse_args()
 
@@ -396,8 +395,6 @@ class Bench:
         self.eng = Engine(dev)
         if args.gemm != "auto":
             self.eng.set_gemm_config(args.gemm, 0, 0)
-        if args.no_graphs and hasattr(self.eng, "use_graphs"):
-            self.eng.use_graphs = False
 
     def barrier(self, group: bool = True):
         self.torch.cuda.synchronize()
@@ -476,7 +473,6 @@ class Bench:
             breakdown = eng.profile_breakdown()
         st = eng.stats()
         launches = st["launches"] - launches0
-        graph_replays = st.get("graph_replays", 0)
         trace = np.array(mps.trace)
         mps.record_trace = False
         if not in_region:
@@ -506,7 +502,7 @@ class Bench:
         gemm_tflops = prof["flops"] / (prof["ms"] * 1e-3) / 1e12 if prof["ms"] > 0 else 0.0
         top = sorted(breakdown.items(), key=lambda kv: -kv[1]["ms"])
         return {"mps": mps, "H": H, "cfg": cfg, "merged": bool(getattr(H, "merged", False)), "ms": ms, "ms_prof": ms_prof, "steps": steps, "clocks": clocks, "launches": int(launches),
-                "graph_replays": int(graph_replays), "trace_len": len(trace), "flops_all": flops_all,
+                "trace_len": len(trace), "flops_all": flops_all,
                 "avg_matvecs_H": float(nH.mean()), "avg_matvecs_K": float(nK.mean()) if len(nK) else 0.0,
                 "gemm_tflops": gemm_tflops, "gemm_launches": int(prof["launches"]), "gemm_share": prof["ms"] / ms_prof,
                 "in_region": in_region, "us_per_launch": us_per_launch,
@@ -666,8 +662,7 @@ def run_cuda(args):
             n1 = len(w1.dims)
             extras["c1"] = {"workload": w1.name, "sweeps_per_s": 2 * 10 / (m1["ms"] * 1e-3),
                             "us_per_site_update": m1["ms"] * 1e3 / (10 * 2 * n1), "launches_per_sweep": m1["launches"] / 20,
-                            "mpo_direct_sum": m1["merged"],
-                            "graph_replays_per_sweep": m1["graph_replays"] / 20}
+                            "mpo_direct_sum": m1["merged"]}
             del m1
             torch.cuda.empty_cache()
         b.barrier()

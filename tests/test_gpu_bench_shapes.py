@@ -177,7 +177,7 @@ def test_site_update_replay_at_bench_shape(eng, name, d, cfg):
 @pytest.mark.parametrize("merge", [False, True], ids=["per-key", "direct-sum"])
 def test_c2_full_step_matches_oracle(eng, merge):
     """One full time step (2 half sweeps, 64 sites, D = 64, 254 Krylov solves) of BASELINE config 2 -- the launch-bound
-    regime that uses the tiny GEMM tiles and, from round 2 on, captured CUDA graphs -- against ``TDVPOracle`` on the host.
+    regime that uses the tiny GEMM tiles, cluster split-K and the fused Lanczos step -- against ``TDVPOracle`` on the host.
 
     The oracle's own Krylov trace is not stable under one-ulp perturbations at this size (tests/golden/noise_floor_c2.json:
     2 of 3 seeded 2e-16 perturbations of the H_eff outputs move one stop decision by +-1 and the autocorrelation by
