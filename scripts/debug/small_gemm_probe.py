@@ -44,3 +44,32 @@ for w in (2, 3):
     L, R, sig, psi = rnd(D, w, D), rnd(D, w, D), rnd(D, D), rnd(D, d, D)
     core = eng.upload_core(rnd(w, d, d, w).cpu().numpy())
     print(f"w={w}: keff_apply {timeit(lambda: eng.keff_apply([(L, R, 1.0)], sig)):7.2f} us   heff_apply {timeit(lambda: eng.heff_apply([(L, core, R, 1.0)], psi)):7.2f} us", flush=True)
+
+# host enqueue time vs. GPU time: is the stream starved by the host, or are the kernels themselves slow?
+import time  # noqa: E402
+
+
+def split(fn, n=300):
+    for _ in range(10):
+        fn()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(n):
+        fn()
+    t1 = time.perf_counter()
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    return (t1 - t0) * 1e6 / n, (t2 - t0) * 1e6 / n
+
+
+w = 3
+L, R, sig, psi = rnd(D, w, D), rnd(D, w, D), rnd(D, D), rnd(D, d, D)
+core = eng.upload_core(rnd(w, d, d, w).cpu().numpy())
+A, B, Cm = rnd(192, 64), rnd(64, 512), rnd(192, 512)
+x = torch.zeros(1024, dtype=torch.complex128, device="cuda")
+for label, fn in [("torch x.add_(1) (1 launch)", lambda: x.add_(1.0)),
+                  ("zgemm 192x512x64 (1 launch)", lambda: eng.zgemm(A, B, 0, 0, 1.0, 0.0, Cm)),
+                  ("keff_apply (2 launches)", lambda: eng.keff_apply([(L, R, 1.0)], sig)),
+                  ("heff_apply (3 launches)", lambda: eng.heff_apply([(L, core, R, 1.0)], psi))]:
+    enq, tot = split(fn)
+    print(f"{label:32s} host enqueue {enq:6.2f} us/call   enqueue + drain {tot:6.2f} us/call", flush=True)

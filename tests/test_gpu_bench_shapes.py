@@ -44,6 +44,9 @@ GEMM_SHAPES = [
     ("c5 heff stage3 NT pot", 4096, 512, 1536, 0, 1),
     ("c5 keff gemm2 NT", 512, 512, 1536, 0, 1),
     ("qr VhC (skinny, split-K)", 1024, 32, 4096, 1, 0),
+    ("c2 heff stage1 NN", 192, 512, 64, 0, 0),
+    ("c2 heff stage3 NT (cluster split-K)", 512, 64, 192, 0, 1),
+    ("c2 env step3 CN", 64, 192, 500, 2, 0),
     ("stream-K: 150 tiles on 148 SMs", 1280, 960, 512, 0, 0),
     ("stream-K: ragged M / N / K tails", 2500, 1100, 1000, 0, 1),
 ]
