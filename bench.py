@@ -351,7 +351,8 @@ def run_reference(args):
     t_start = time.perf_counter()
     cb = cpu_baseline(wl, None, budget="long")
     check = None
-    if rr.source_kind() is not None and args.workload == "c4":
+    # (N = 1 line only: the check costs ~70 s of host time and would say the same thing in every --gpus N line)
+    if rr.source_kind() is not None and args.workload == "c4" and int(os.environ.get("WORLD_SIZE", "1")) == 1:
         w3 = make_workload(args, "c3")
         full = rr.time_full_steps(w3, 2, warm_steps=1)
         p0 = first_full_site(w3)
