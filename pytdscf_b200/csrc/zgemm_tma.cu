@@ -71,6 +71,7 @@ struct TmaParams {
   // stream-K (splitk == 1, at least one tile per CTA): the tiles x k-tiles iteration space is cut into gridDim.x equal
   // contiguous ranges; a tile that straddles two ranges is finished by the second CTA from the first one's partial sums
   int streamk;         // 0: whole tiles round-robin (and split-K work items)
+  int sk_tiles;        // stream-K: tiles [0, sk_tiles) are cut evenly over the CTAs, the rest are whole waves
   int epoch;           // value the head writer stores into sk_flags[cta] (grows with every launch: no reset needed)
   int* sk_flags;       // one per CTA
   c128* sk_ws;         // one BM x BN accumulator image per CTA, in fragment order
@@ -136,22 +137,31 @@ __device__ __forceinline__ void decode_work(const TmaParams& p, int w, int& tm, 
   tn = (pid % in_group) / gsz;
 }
 
-// Number of segments of this CTA and the si-th of them.  Stream-K order inside a CTA: the trailing partial tile (the HEAD
-// part of a tile the next CTA finishes) first, then the whole tiles, the leading partial tile (TAIL part, finished here from
-// the previous CTA's partial) last -- so a finisher never waits for work its neighbour has not started with.
-__device__ __forceinline__ int seg_count(const TmaParams& p, int KT) {
-  const int total = p.tiles_m * p.tiles_n * p.splitk;
-  if (!p.streamk) return (int)blockIdx.x < total ? (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-  const long long I = (long long)total * KT;
+// Number of segments of this CTA and the si-th of them.  Stream-K is applied to the FIRST p.sk_tiles tiles of the raster only
+// (between one and two waves' worth, or everything when there are fewer tiles than that): their tiles x k-tiles space is cut
+// into gridDim.x equal contiguous ranges.  The remaining tiles are whole waves and keep the strided persistent order
+// (tile = sk_tiles + w * grid + cta), in which the CTAs of a wave share A rows / B columns in L2 -- cutting the WHOLE raster
+// into per-CTA ranges would put every CTA into a different region of the matrix at any moment and defeat that reuse
+// (measured: 11 GB of DRAM reads instead of 0.5 GB on 8192 x 4096 x 1024).
+// Order inside the stream-K part: the trailing partial tile (the HEAD part of a tile the next CTA finishes) first, then the
+// whole tiles, the leading partial tile (TAIL part, finished here from the previous CTA's partial) last -- so a finisher
+// never waits for work its neighbour has not started with.
+__device__ __forceinline__ int sk_seg_count(const TmaParams& p, int KT) {
+  const long long I = (long long)p.sk_tiles * KT;
   const long long a = I * blockIdx.x / gridDim.x, b = I * (blockIdx.x + 1) / gridDim.x;
   if (b <= a) return 0;
   const int first = (int)(a / KT), last = (int)((b - 1) / KT);
   return last - first + 1;       // lead (partial or whole) + middle tiles + trail (partial or whole)
 }
+__device__ __forceinline__ int seg_count(const TmaParams& p, int KT) {
+  const int total = p.tiles_m * p.tiles_n * p.splitk;
+  if (!p.streamk) return (int)blockIdx.x < total ? (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int rest = total - p.sk_tiles;    // a multiple of gridDim.x
+  return sk_seg_count(p, KT) + rest / (int)gridDim.x;
+}
 
 __device__ __forceinline__ Seg get_seg(const TmaParams& p, int si, int KT) {
   Seg sg;
-  const int total = p.tiles_m * p.tiles_n * p.splitk;
   if (!p.streamk) {
     const int w = blockIdx.x + si * gridDim.x;
     decode_work(p, w, sg.tm, sg.tn, sg.split);
@@ -162,7 +172,13 @@ __device__ __forceinline__ Seg get_seg(const TmaParams& p, int si, int KT) {
     sg.role = 0;
     return sg;
   }
-  const long long I = (long long)total * KT;
+  const int n = sk_seg_count(p, KT);
+  if (si >= n) {                             // whole waves after the stream-K part
+    decode_work(p, p.sk_tiles + (si - n) * (int)gridDim.x + (int)blockIdx.x, sg.tm, sg.tn, sg.split);
+    sg.kt0 = 0; sg.kt1 = KT; sg.role = 0;
+    return sg;
+  }
+  const long long I = (long long)p.sk_tiles * KT;
   const long long a = I * blockIdx.x / gridDim.x, b = I * (blockIdx.x + 1) / gridDim.x;
   const int first = (int)(a / KT), a_off = (int)(a % KT), last = (int)((b - 1) / KT), b_off = (int)(b - (long long)last * KT);
   int tile;
@@ -170,7 +186,6 @@ __device__ __forceinline__ Seg get_seg(const TmaParams& p, int si, int KT) {
     tile = first; sg.kt0 = a_off; sg.kt1 = b_off;
     sg.role = (a_off == 0 && b_off == KT) ? 0 : (a_off == 0 ? 1 : (b_off == KT ? 2 : 3));
   } else {
-    const int n = last - first + 1;
     // order: [trail, middle..., lead]
     if (si == 0) { tile = last; sg.kt0 = 0; sg.kt1 = b_off; sg.role = b_off == KT ? 0 : 1; }
     else if (si == n - 1) { tile = first; sg.kt0 = a_off; sg.kt1 = KT; sg.role = a_off == 0 ? 0 : 2; }
@@ -566,11 +581,13 @@ cudaError_t zgemm_tma_try(const GemmDesc& d, const GemmCtx& ctx, bool* used) {
   p.M = d.M; p.N = d.N; p.K = d.K;
   p.tiles_m = (d.M + BM - 1) / BM;
   p.tiles_n = (d.N + BN - 1) / BN;
-  // group of M-tiles whose A rows (group_m * BM * K complex) take about half of the 126 MB L2: B is then read once per
-  // group instead of once per 16 M-tiles (ncu, 8192 x 4096 x 1024: 1.39x the algorithmic DRAM bytes with groups of 16)
+  // group of M-tiles whose A rows (group_m * BM * K complex) take ~32 MB: they stay in L2 while the group walks the N-tiles,
+  // so B is read once per group.  ncu sweep on 8192 x 4096 x 1024 (algorithmic reads 201 MB): 693 / 617 / 778 / 1738 MB of
+  // DRAM reads for 16 / 32 / 48 / 64 MB groups -- the two L2 partitions duplicate lines that SMs of both dies read, so the
+  // usable capacity for an operand shared by all CTAs is about half of the 126 MB
   {
     const double a_tile_bytes = (double)BM * (double)d.K * 16.0;
-    int gm = (int)(64.0e6 / a_tile_bytes);
+    int gm = (int)(32.0e6 / a_tile_bytes);
     p.group_m = gm < 8 ? 8 : (gm > 64 ? 64 : gm);
   }
   p.splitk = d.splitk < 1 ? 1 : d.splitk;
@@ -590,10 +607,18 @@ cudaError_t zgemm_tma_try(const GemmDesc& d, const GemmCtx& ctx, bool* used) {
   // 2) loses more to the fix-up than it gains; force_cfg 5 = TMA kernel with whole tiles only (A/B tests)
   const int KT = (d.K + BK - 1) / BK;
   p.streamk = 0;
+  p.sk_tiles = (int)total;
   if (p.splitk == 1 && ctx.force_cfg != 5 && ctx.sk_ws && ctx.sk_flags && KT >= 16 && ctx.num_sms <= ctx.sk_slots) {
     if (total >= ctx.num_sms) {
-      p.streamk = (total % ctx.num_sms != 0) ? 1 : 0;
+      // only when the ragged last wave costs more than 3 %: with many waves stream-K gains nothing measurable and its
+      // k-shifted first waves cost L2 reuse (8192 x 4096 x 1024, 27.7 waves: 617 MB of DRAM reads with, 522 MB without)
+      const long long waves = (total + ctx.num_sms - 1) / ctx.num_sms;
+      p.streamk = ((waves * ctx.num_sms - total) * 100 > 3 * waves * ctx.num_sms || ctx.force_cfg == 4) ? 1 : 0;
+      if (total % ctx.num_sms == 0) p.streamk = 0;
+      p.sk_tiles = (int)(total % ctx.num_sms) + (total >= 2 * ctx.num_sms ? ctx.num_sms : 0);   // one to two waves' worth
+      if (total < 2 * ctx.num_sms) p.sk_tiles = (int)total;
     } else {
+      p.sk_tiles = (int)total;
       if (2 * total >= ctx.num_sms && KT >= 32) { p.streamk = 1; grid = ctx.num_sms; }   // <= 2 links, >= 16 k-tiles each
       else if (ctx.force_cfg == 4) {                      // forced "tma": long chains too (ranges of >= 4 k-tiles), for the tests
         long long g = total * KT / 4;
