@@ -630,6 +630,58 @@ class MPSCoefCuda:
             canonicalizeA(self.eng, sb[min(changed): reorth_center + 1])
             self.op_sys_sites = None
 
+    def hermitise(self):
+        """rho <- (rho + rho^dagger) / 2 of a Liouville-space MPDO, compressed back to the bond dimensions it had (reference
+        ``MPSCoef.hermitise`` / ``svd_conj_mpdo``, _mps_cls.py:2289-2312, 2516-2562; the reference leaves its call inside
+        ``propagate`` commented out, :501-503, so this is an explicit user call here as well).  The sum is the direct-sum
+        MPDO [rho/2 | rho^dagger/2] (first site: along the right bond; inner sites: block diagonal; last site: along the
+        left bond) with doubled bonds; a left-to-right pass of two-site SVDs truncates every bond back to its original
+        dimension (U to the left, S Vh to the right), then the chain is re-canonicalised with the centre on site 0.  One GEMM and
+        one thin Jacobi SVD per bond, on the device; the cached environments are dropped."""
+        if self.subspace:
+            raise NotImplementedError("hermitise: sub-space sites have no square physical index (the reference asserts the same)")
+        eng, sb, n = self.eng, self.sites, self.nsite
+
+        def four(t):
+            Dl, dd, Dr = t.shape
+            q = math.isqrt(dd)
+            if q * q != dd:
+                raise ValueError("hermitise: Liouville-space sites need a square physical dimension")
+            return t.reshape(Dl, q, q, Dr)
+
+        if n == 1:
+            rho = four(sb[0].data)
+            sb[0].data = (0.5 * (rho + rho.conj().permute(0, 2, 1, 3))).reshape(sb[0].data.shape).contiguous()
+            return
+        bonds = [int(s.data.shape[-1]) for s in sb[:-1]]
+        for i, s in enumerate(sb):
+            rho = four(s.data)
+            dag = rho.conj().permute(0, 2, 1, 3)
+            a, q, _, d = rho.shape
+            if i == 0:
+                data = torch.cat((0.5 * rho, 0.5 * dag), dim=3)
+            elif i == n - 1:
+                data = torch.cat((rho, dag), dim=0)
+            else:
+                data = torch.zeros((2 * a, q, q, 2 * d), dtype=rho.dtype, device=rho.device)
+                data[:a, :, :, :d] = rho
+                data[a:, :, :, d:] = dag
+            s.data = data.reshape(data.shape[0], q * q, data.shape[3]).contiguous()
+        for i in range(n - 1):
+            L, R = sb[i].data, sb[i + 1].data
+            a, j, k = L.shape
+            _, l, m = R.shape
+            chi = bonds[i]
+            if chi > min(a * j, l * m):
+                raise ValueError("hermitise: bond dimension exceeds the rank of the two-site matrix")
+            two = eng.zgemm(L.reshape(a * j, k).contiguous(), R.reshape(k, l * m).contiguous())
+            U, sv, Vh = eng.svd(two)
+            scale = torch.as_tensor(np.asarray(sv[:chi]), dtype=torch.float64, device=U.device)
+            sb[i].data = U[:, :chi].contiguous().reshape(a, j, chi)
+            sb[i + 1].data = (scale[:, None] * Vh[:chi, :]).contiguous().reshape(chi, l, m)
+        canonicalize(eng, sb, 0, incremental=False)
+        self.op_sys_sites = None
+
     # -- observables ---------------------------------------------------------------------------------
     def _liouville_four(self, isite: int) -> torch.Tensor:
         """Site tensor of an MPDO as (D_l, q, q, D_r); sub-space sites are embedded back into the full q x q index first

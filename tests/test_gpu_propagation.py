@@ -275,6 +275,23 @@ def test_liouville_observables_and_subspace(tag, tmp_path):
     check_case(tag, sim, wf, tol_expect=REL, tol_state=1e-9)
 
 
+@pytest.mark.parametrize("tag", ["prop", "rand"])
+def test_hermitise_mpdo_gpu(tag):
+    """rho <- (rho + rho^dagger) / 2 with re-compression to the original bonds (reference ``MPSCoef.hermitise`` /
+    ``svd_conj_mpdo``, _mps_cls.py:2289-2312, 2516-2562) on the device (GEMM + Jacobi SVD per bond, QR re-canonicalisation):
+    the dense density operator equals the unmodified reference's (tests/golden/hermitise.npz) to 1e-11 relative."""
+    from pytdscf_b200._engine import Engine
+    from tests.hermitise_cases import run_and_check
+
+    eng = Engine(0)
+    try:
+        err, asym = run_and_check(tag, eng, tol=1e-11)
+        if tag == "prop":
+            assert asym < 1e-11
+    finally:
+        eng.close()
+
+
 def test_restart_from_reference_checkpoint_on_gpu(tmp_path):
     """A ``wf_*.pkl`` written by the reference (dill dump of its WFunc) restarts on the GPU and continues with the
     reference's own energies (tests/golden/make_golden_checkpoint.py), SURVEY 8(f4)."""
