@@ -123,8 +123,8 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// Work item w -> (tile_m, tile_n, split): splits outermost, then the grouped rasterisation of zgemm_dmma_kernel (16 M-tiles
-// per N-tile), so the CTAs of one persistent "wave" (consecutive w) share A rows / B columns in L2.
+// Work item w -> (tile_m, tile_n, split): splits outermost, then the grouped rasterisation of zgemm_dmma_kernel (group_m
+// M-tiles per N-tile), so the CTAs of one persistent "wave" (consecutive w) share A rows / B columns in L2.
 __device__ __forceinline__ void decode_work(const TmaParams& p, int w, int& tm, int& tn, int& split) {
   const int GROUP_M = p.group_m;
   const int per_split = p.tiles_m * p.tiles_n;
