@@ -270,6 +270,54 @@ def canonicalize(eng, sb: list, center: int, incremental: bool = False):
 
 
 
+def oversize_bonds(sb: list) -> list[int]:
+    """Bonds (index of the site on their left) larger than the matricisations next to them allow: D_r > D_l d of the left
+    site or D_l > d D_r of the right one.  ``LatticeInfo.get_bond_dim`` (_mps_cls.py:2616-2631) never produces such bonds,
+    hand-made site tensors can."""
+    bad = []
+    for i in range(len(sb) - 1):
+        a, d, D = sb[i].data.shape
+        _, d2, e = sb[i + 1].data.shape
+        if D > a * d or D > d2 * e:
+            bad.append(i)
+    return bad
+
+
+def compress_oversize_bonds(eng, sb: list, center: int = 0) -> bool:
+    """Exact compression of every bond that exceeds the rank its neighbours can carry, then re-canonicalisation around
+    ``center``.  The reference never sees such bonds as an error: its economic QR in ``gauge_trf`` (_site_cls.py:138-292)
+    silently shrinks a bond to min(rows, columns) at the first sweep.  Here ``tdvp_qr_shift`` factors tall matrices only, so
+    explicit site tensors (``Simulator.set_initial_mps``, own-format checkpoints) are brought to the reference's bond rule once,
+    at upload: thin SVDs of the offending matricisations (U to one side, S Vh folded into the neighbour) -- the represented
+    state is unchanged to rounding.  Returns True when something was compressed."""
+    if not oversize_bonds(sb):
+        return False
+    for _ in range(len(sb) + 1):                 # bonds only shrink: at most nsite passes
+        bad = oversize_bonds(sb)
+        if not bad:
+            break
+        for i in bad:
+            L, R = sb[i].data, sb[i + 1].data
+            a, d, D = L.shape
+            _, d2, e = R.shape
+            if D > a * d:                        # left matricisation (a d) x D is wide: rank <= a d
+                U, sv, Vh = eng.svd(L.reshape(a * d, D).contiguous())
+                k = U.shape[1]
+                scale = torch.as_tensor(np.asarray(sv[:k]), dtype=torch.float64, device=U.device)
+                sb[i].data = U.contiguous().reshape(a, d, k)
+                sb[i + 1].data = eng.zgemm((scale[:, None] * Vh[:k, :]).contiguous(), R.reshape(D, d2 * e).contiguous()).reshape(k, d2, e)
+            elif D > d2 * e:                     # right matricisation D x (d2 e) is tall: rank <= d2 e
+                U, sv, Vh = eng.svd(R.reshape(D, d2 * e).contiguous())
+                k = Vh.shape[0]
+                scale = torch.as_tensor(np.asarray(sv[:k]), dtype=torch.float64, device=U.device)
+                sb[i + 1].data = Vh.contiguous().reshape(k, d2, e)
+                sb[i].data = eng.zgemm(L.reshape(a * d, D).contiguous(), (U[:, :k] * scale[None, :]).contiguous()).reshape(a, d, k)
+    if oversize_bonds(sb):
+        raise RuntimeError("compress_oversize_bonds did not reach the bond-dimension rule")
+    canonicalize(eng, sb, center, incremental=False)
+    return True
+
+
 class MPSCoefCuda:
     """Device-resident MPS in mixed-canonical form with the orthogonality centre at site 0 between steps."""
 
@@ -287,6 +335,17 @@ class MPSCoefCuda:
         self.site_offset = 0   # global index of local site 0 (site-parallel segments share one global MPO)
         self.site_now = 0      # reference: helper._Debug.site_now, the key of the Krylov warm-up history
         self.subspace: dict[int, tuple[int, tuple[int, ...]]] = {}   # Liouville sub-space sites: site -> (full d, kept indices)
+
+    @classmethod
+    def from_user_cores(cls, eng: Engine, cores: list, gauges: list[str] | None = None) -> "MPSCoefCuda":
+        """Explicit site tensors (``Simulator.set_initial_mps``, checkpoints): uploaded as given; bonds beyond the reference's
+        bond-dimension rule are compressed exactly and the chain is re-canonicalised around its centre (see
+        ``compress_oversize_bonds``)."""
+        mps = cls(eng, [c if isinstance(c, torch.Tensor) else eng.to_device(np.ascontiguousarray(c, dtype=np.complex128)) for c in cores], gauges)
+        sb = mps.sites
+        centres = [i for i, s in enumerate(sb) if s.gauge == "Psi"]
+        compress_oversize_bonds(eng, sb, centres[0] if len(centres) == 1 else 0)
+        return mps
 
     # ------------------------------------------------------------------------------------------
     @classmethod

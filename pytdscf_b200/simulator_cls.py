@@ -146,7 +146,7 @@ class Simulator:
             with open(path, "rb") as f:
                 d = pickle.load(f)
         eng = self._engine()
-        return WFunc(MPSCoefCuda(eng, [eng.to_device(c) for c in d["cores"]], d["gauges"]), eng, self.model.space)
+        return WFunc(MPSCoefCuda.from_user_cores(eng, d["cores"], d["gauges"]), eng, self.model.space)
 
     def set_initial_mps(self, cores: list, gauges: list[str] | None = None):
         """Lower-level entry: start from explicit site tensors (site 0 = centre, the rest right-canonical)."""
@@ -158,7 +158,7 @@ class Simulator:
         eng = self._engine()
         if getattr(self, "_initial_mps", None) is not None:
             cores, gauges = self._initial_mps
-            return WFunc(MPSCoefCuda(eng, [eng.to_device(c) for c in cores], gauges), eng, self.model.space)
+            return WFunc(MPSCoefCuda.from_user_cores(eng, cores, gauges), eng, self.model.space)
         return WFunc(MPSCoefCuda.alloc_random(eng, self.model), eng, self.model.space)
 
     def _distributed_wavefunction(self, split: list[tuple[int, ...]]) -> WFunc:
