@@ -82,6 +82,43 @@ class _DatFile:
         self.f.close()
 
 
+def _write_reduced_density_nc(path: str, rows: list, display_time_unit: str = "fs") -> str | None:
+    """``<job>/reduced_density.nc`` with the reference's layout (pytdscf/properties.py:160-213): unlimited dimension ``step``,
+    ``state``, one dimension ``Q<site>`` per site of a key, variable ``time`` (display unit) and one variable
+    ``rho_<key>_<state>`` per key with dimensions (step, Q.., Q..).  The reference writes NETCDF4 with a compound
+    (real, imag) type through the netCDF4 package; neither that package nor HDF5 exists here, so the file is NetCDF-3
+    (64-bit offset, written by ``scipy.io.netcdf_file``; the netCDF4 package and xarray read it too) and the complex values carry a
+    trailing dimension ``complex`` of length 2 = (real, imag) instead of the compound type.  Skipped when SciPy is missing."""
+    try:
+        from scipy.io import netcdf_file
+    except ImportError:      # pragma: no cover
+        return None
+    from .units import au_in_fs
+
+    scale = {"fs": au_in_fs, "ps": au_in_fs * 1.0e-3, "au": 1.0}.get(display_time_unit, au_in_fs)
+    with netcdf_file(path, "w", version=2) as f:
+        f.createDimension("step", None)
+        f.createDimension("state", 1)
+        f.createDimension("complex", 2)
+        t = f.createVariable("time", "d", ("step",))
+        t.units = display_time_unit if display_time_unit in ("fs", "ps", "au") else "fs"
+        var = {}
+        for key, rho in rows[0]["reduced_densities"].items():
+            dims = []
+            for idof, n in zip(key, np.asarray(rho).shape, strict=True):
+                name = f"Q{idof}"
+                if name not in f.dimensions:
+                    f.createDimension(name, int(n))
+                dims.append(name)
+            var[key] = f.createVariable(f"rho_{tuple(key)}_0", "d", ("step", *dims, "complex"))
+        for i, r in enumerate(rows):
+            t[i] = r["time_au"] * scale
+            for key, rho in r["reduced_densities"].items():
+                rho = np.asarray(rho)
+                var[key][i] = np.stack([rho.real, rho.imag], axis=-1)
+    return path
+
+
 class Simulator:
     """The simulator of the PyTDSCF-style API, running on one B200 through libtdvp_b200.
 
@@ -292,6 +329,7 @@ class Simulator:
                 for key in rows[0]["reduced_densities"]:
                     out["rho_" + "_".join(map(str, key))] = np.stack([r["reduced_densities"][key] for r in rows])
                 np.savez(os.path.join(cfg.jobname, "reduced_density.npz"), **out)
+                _write_reduced_density_nc(os.path.join(cfg.jobname, "reduced_density.nc"), rows, display_time_unit)
         return (last_energy, wf)
 
     def relax(self, stepsize: float = 0.1, maxstep: int = 20, improved: bool = True, restart: bool = False,

@@ -169,6 +169,18 @@ def test_simulator_reduced_density_argument(tmp_path):
     assert abs(np.trace(rho[(3, 3)]) - 1.0) < 1e-12 and abs(rho[(0,)].sum() - 1.0) < 1e-12
     z = np.load(os.path.join("rd_cpu_prop", "reduced_density.npz"))
     assert z["rho_3_3"].shape == (2, 2, 2) and len(z["time_au"]) == 2
+    # <job>/reduced_density.nc in the reference's layout (pytdscf/properties.py:160-213): step / Q<site> dimensions, `time`,
+    # rho_<key>_<state>; NetCDF-3 with a trailing (real, imag) dimension instead of NETCDF4's compound type
+    from scipy.io import netcdf_file
+
+    with netcdf_file(os.path.join("rd_cpu_prop", "reduced_density.nc"), "r", mmap=False) as f:
+        assert f.dimensions["step"] is None and f.dimensions["Q3"] == 2 and f.dimensions["Q1"] == 8 and f.dimensions["state"] == 1
+        assert set(f.variables) == {"time", "rho_(3, 3)_0", "rho_(0,)_0", "rho_(1, 2)_0"}
+        assert f.variables["rho_(1, 2)_0"].dimensions == ("step", "Q1", "Q2", "complex")
+        assert np.allclose(f.variables["time"][:], [r["time_au"] * tb.units.au_in_fs for r in recs])
+        for key, name in (((3, 3), "rho_(3, 3)_0"), ((0,), "rho_(0,)_0"), ((1, 2), "rho_(1, 2)_0")):
+            v = f.variables[name][:]
+            assert np.array_equal(v[..., 0] + 1j * v[..., 1], np.stack([r["reduced_densities"][key] for r in recs]))
 
 
 @pytest.mark.parametrize("reorder", [False, True])
