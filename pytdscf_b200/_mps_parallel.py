@@ -494,11 +494,12 @@ class MPSCoefParallelCuda(MPSCoefCuda):
         self.save_all_B(True)
 
     # -- observables (results on rank 0) ----------------------------------------------------------------------
-    def ovlp(self, conj: bool = True):
-        eng, c = self.eng, self.comm
-        rank, size = self.rank, self.size
-        mid = size // 2
-        forward = rank < mid
+    def _segment_tensors(self) -> list:
+        """This rank's site tensors such that the segments of all ranks, concatenated, are an MPS of the whole state: the
+        boundary bond matrix is carried by both neighbours, so the last tensor of every segment but the final one takes
+        its inverse (even ranks, B gauge) or the stored inverse (odd ranks, A gauge) -- reference ``ovlp``,
+        _mps_parallel.py:855-934."""
+        eng, rank, size = self.eng, self.rank, self.size
         data = [s.data for s in self.sites]
         if rank != size - 1:
             if rank % 2 == 0 and self.sites[-1].gauge == "B":
@@ -507,6 +508,77 @@ class MPSCoefParallelCuda(MPSCoefCuda):
                 data[-1] = eng.absorb("B", self.joint_sigvec, data[-1])
             else:
                 raise ValueError(f"{self.sites[-1].gauge=} {rank=}")
+        return data
+
+    def get_reduced_densities(self, remain_nleg, space: str = "hilbert"):
+        """Reduced densities inside a site-parallel run (reference ``MPSCoefParallel.get_reduced_densities``,
+        _mps_parallel.py:1035-1208): list of arrays on rank 0, None elsewhere.  The reference contracts, per key, the all-A
+        copies of the ranks up to a middle rank and the all-B copies of the ranks after it, joined by that rank's bond
+        matrix ``joint_sigvec_not_pinv`` (the middle of the ranks the key touches).  The three views of the state that a
+        parallel run keeps -- current sites, all-A, all-B -- agree only to the accuracy of the scheme (1e-6 on the test
+        systems), so the SAME view has to be used to get the reference's numbers.  Here every rank sends its two copies and
+        its bond matrix to rank 0 (p2p, one message per call), which assembles that chain per key -- A ... A (A sigma) B ... B,
+        canonical around the joining site -- moves the centre to site 0 and evaluates the key with the serial routine
+        (isometric sites outside the key contract to unit matrices there exactly as the reference skips them)."""
+        if space != "hilbert":
+            raise NotImplementedError("liouville space is not supported for parallel MPS (as in the reference)")
+        if isinstance(remain_nleg, tuple):
+            remain_nleg = [remain_nleg]
+        c, eng = self.comm, self.eng
+        pack = {"A": [s.data for s in self.superblock_all_A], "B": [s.data for s in self.superblock_all_B],
+                "sig": self.joint_sigvec_not_pinv if self.rank != self.size - 1 else None}
+        if self.rank != 0:
+            c.send(pack, 0)
+            return None
+        packs = [pack] + [c.recv(r) for r in range(1, self.size)]
+        split, size = self.split, self.size
+        out = []
+        for legs in remain_nleg:
+            open_sites = [i for i, n in enumerate(legs) if n]
+            if not open_sites:
+                raise ValueError(f"invalid remain_nleg {legs}")
+            left_site, right_site = open_sites[0], open_sites[-1]
+            needed = []
+            for r in range(size):                       # the ranks whose segments the key touches (_mps_parallel.py:1053-1067)
+                if split[r] > right_site:
+                    break
+                if r + 1 < size and split[r + 1] - 1 < left_site:
+                    continue
+                needed.append(r)
+            mid = (len(needed) - 1) // 2 + needed[0]
+            sb = []
+            for r in range(size):
+                tensors = packs[r]["A"] if r <= mid else packs[r]["B"]
+                for t in tensors:
+                    sb.append(SiteCoef(t, "A" if r <= mid else "B", len(sb)))
+            centre = (split[mid + 1] - 1) if mid < size - 1 else len(sb) - 1
+            if mid < size - 1:
+                sb[centre] = SiteCoef(eng.absorb("B", packs[mid]["sig"], sb[centre].data), "Psi", centre)
+            else:
+                sb[centre].gauge = "Psi"
+            sb = _clone_sites(sb)                        # the QR shifts below must not touch the copies of the next key
+            canonicalize(eng, sb, 0, incremental=True)
+            whole = MPSCoefCuda(eng, [s.data for s in sb], [s.gauge for s in sb])
+            rho = whole._pure_reduced_density(tuple(legs))
+            # the reference's PARALLEL routine orders the two legs of a site (bra, ket) ("...ad,abc,def->...becf" with the
+            # conjugated core first, _mps_parallel.py:1115-1124), its serial one (ket, bra): keep each routine's own order
+            axis, perm = 0, []
+            for n in legs:
+                if n == 2:
+                    perm += [axis + 1, axis]
+                    axis += 2
+                elif n == 1:
+                    perm.append(axis)
+                    axis += 1
+            out.append(np.ascontiguousarray(rho.transpose(perm)))
+        return out
+
+    def ovlp(self, conj: bool = True):
+        eng, c = self.eng, self.comm
+        rank, size = self.rank, self.size
+        mid = size // 2
+        forward = rank < mid
+        data = self._segment_tensors()
         if forward:
             block = None if rank == 0 else c.recv(rank - 1)
             if block is None:

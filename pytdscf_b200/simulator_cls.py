@@ -234,8 +234,6 @@ class Simulator:
         """Real-time propagation; returns ``(energy, wf)`` like the reference (energy of the last evaluated step)."""
         self._rd = None
         if reduced_density is not None:
-            if parallel_split_indices is not None:
-                raise NotImplementedError("reduced densities are not implemented for site-parallel runs")
             keys, rd_step = reduced_density
             legs = []
             for key in keys:   # site indices -> legs per site, as properties.py:64-83: (0, 0) -> (2,), (1, 2) -> (0, 1, 1)
@@ -310,7 +308,9 @@ class Simulator:
                 rec["bonddim"] = wf.bonddim()
             rd = getattr(self, "_rd", None)
             if rd is not None and not relax and istep % rd[2] == 0:
-                rec["reduced_densities"] = dict(zip(rd[0], wf.get_reduced_densities(rd[1]), strict=True))
+                dens = wf.get_reduced_densities(rd[1])        # site-parallel runs: a collective call, values on rank 0
+                if dens is not None:
+                    rec["reduced_densities"] = dict(zip(rd[0], dens, strict=True))
             self.history.append(rec)
             if files is not None:
                 self._export(files, cfg, rec, elapsed)

@@ -72,3 +72,64 @@ def test_site_parallel_matches_reference(name, tmp_path):
         for a, b in zip(res[r]["sites"], g["ranks"][r]["sites"], strict=True):
             np.testing.assert_allclose(a, b, rtol=0, atol=1e-10)
     assert "main.log" in res[0]["files"] and "autocorr.dat" in res[0]["files"]
+
+
+# ---------------------------------------------------------------------------------------------------------
+RDM_KEYS = [(0,), (5,), (2, 2), (5, 5), (3, 4), (1, 6), (3, 3, 4), (7, 7)]
+
+
+def _worker_rdm(rank, world, port, name, tmp, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port), OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1")
+    try:
+        import torch
+
+        torch.set_num_threads(1)
+        import pytdscf_b200 as tb
+        from oracle.oracle_engine import OracleEngine
+        from pytdscf_b200 import parallel
+        from tests.test_host_sweep_cpu import _build_model
+
+        g = load_parallel(name)
+        os.chdir(tmp)
+        info = parallel.init_from_env("gloo")
+        sim = tb.Simulator(name + "_rdm", _build_model(g), backend="cuda", verbose=0)
+        sim.eng = OracleEngine()
+        sim.rank_info = info
+        sim.set_initial_mps(g["init"])
+        sim.propagate(stepsize=g["dt_fs"], maxstep=3, parallel_split_indices=g["split"], populations=False,
+                      reduced_density=(RDM_KEYS, 1))
+        out = {"history": sim.history if rank == 0 else [("reduced_densities" in r) for r in sim.history],
+               "files": sorted(os.listdir(name + "_rdm_prop")) if rank == 0 else None}
+        q.put((rank, out))
+        parallel.finalize(info)
+    except Exception:  # pragma: no cover
+        import traceback
+
+        q.put((rank, {"error": traceback.format_exc()}))
+
+
+@pytest.mark.parametrize("name", ["par_hh8_P2", "par_hh8_P4"])
+def test_site_parallel_reduced_densities_match_reference(name, tmp_path):
+    """Reduced densities inside a site-parallel run (reference ``MPSCoefParallel.get_reduced_densities``,
+    pytdscf/_mps_parallel.py:1035-1208) against the unmodified reference's values (tests/golden/par_rdm_hh8_P*.npz,
+    tests/golden/make_golden_parallel_rdm.py): one-leg, two-leg and mixed keys on forward and backward ranks."""
+    from tests.golden_io import GOLDEN_DIR
+    from tests.mp_util import run_ranks
+
+    g = load_parallel(name)
+    z = dict(np.load(os.path.join(GOLDEN_DIR, name.replace("par_", "par_rdm_") + ".npz")))
+    assert [eval(k) for k in z["keys"]] == RDM_KEYS and not [k for k in z if k.startswith("fail")]   # noqa: S307 (tuples written by the generator)
+    port = 33000 + (os.getpid() % 2000)
+    res = run_ranks(_worker_rdm, g["nranks"], (port, name, str(tmp_path)), timeout=600)
+    hist = res[0]["history"]
+    assert len(hist) == 3
+    for r in range(1, g["nranks"]):
+        assert not any(res[r]["history"])                       # values live on rank 0 only
+    for step, (rec, row) in enumerate(zip(hist, z["props"], strict=True)):
+        assert abs(rec["energy"] - row[3]) < 1e-12 * max(1.0, abs(row[3]))     # the propagation is not disturbed
+        for ik, key in enumerate(RDM_KEYS):
+            got, ref = rec["reduced_densities"][key], z[f"rho{ik}"][step]
+            assert got.shape == ref.shape
+            assert np.abs(got - ref).max() < 1e-11, (step, key, np.abs(got - ref).max())
+    assert "reduced_density.nc" in res[0]["files"] and "reduced_density.npz" in res[0]["files"]
