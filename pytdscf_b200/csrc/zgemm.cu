@@ -16,6 +16,10 @@
 //    every fragment LDS.128 is bank-conflict free for both operand majors.
 //  * rows of A/C and columns of B may be two-level indices (GemmDesc) so contractions such as
 //    T2[a,i,t,s] = sum_{c,j} T1[a,c,j,s] W[c,i,j,t] run on their natural layouts (no transposes).
+//  * round 2: this file keeps the cp.async kernels (three tile geometries), the launch choice (choose(): tile, split-K
+//    factor) and the two split-K forms -- scratch + fixed-order reduction kernel, and, for the small tiles, a thread-block
+//    cluster per output tile that reduces the partial tiles through distributed shared memory.  The 128x64 work of the
+//    D >= 256 regime runs in the persistent TMA-fed kernel of zgemm_tma.cu whenever tensor maps can describe the operands.
 #include <cooperative_groups.h>
 
 #include <atomic>
