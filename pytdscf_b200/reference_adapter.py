@@ -40,7 +40,10 @@ class _Waist:
         """Environment block: int (the reference's identity placeholder) -> None, ndarray (2 or 3 indices) -> device."""
         if isinstance(b, (int, np.integer)):
             return None
-        return self.eng.to_device(np.asarray(b))
+        a = np.asarray(b)
+        if a.ndim == 2:                       # overlap-type block without an MPO bond: a bond of dimension 1 for the engine
+            a = a.reshape(a.shape[0], 1, a.shape[1])
+        return self.eng.to_device(a)
 
     def core(self, c):
         """Site operator: int -> None; OperatorCore (3-index diagonal / 4-index) or a bare d x d matrix -> device core."""
