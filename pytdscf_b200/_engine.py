@@ -45,6 +45,14 @@ def _ptr(t: torch.Tensor | None):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+def adjoint(M: torch.Tensor) -> torch.Tensor:
+    """Conjugate transpose of a 2-D tensor as a contiguous tensor whose MEMORY holds the conjugated values.  ``M.conj()`` only
+    sets torch's lazy conjugate bit; ``.T.contiguous()`` materialises it when the transpose forces a copy, but a 1 x n or n x 1
+    matrix is already contiguous after ``.T`` and would keep the bit -- the C ABI reads raw memory, so the bit is resolved
+    explicitly."""
+    return M.conj().T.resolve_conj().contiguous()
+
+
 def _chk_tensor(t: torch.Tensor, name: str):
     if not (t.is_cuda and t.dtype == CDTYPE and t.is_contiguous()):
         raise TypeError(f"{name} must be a contiguous complex128 CUDA tensor (got {t.dtype}, cuda={t.is_cuda})")
@@ -284,8 +292,8 @@ class Engine:
         _chk_tensor(M, "M")
         m, n = M.shape
         if m < n:
-            U2, s, Vh2 = self.svd(M.conj().T.contiguous())
-            return Vh2.conj().T.contiguous(), s, U2.conj().T.contiguous()
+            U2, s, Vh2 = self.svd(adjoint(M))
+            return adjoint(Vh2), s, adjoint(U2)
         U, Vh = self.empty(m, n), self.empty(n, n)
         s = (C.c_double * n)()
         check(self.h, self.lib.tdvp_svd(self.h, m, n, _ptr(M), _ptr(U), s, _ptr(Vh)))

@@ -164,3 +164,19 @@ def test_abi_reports_errors_without_device():
     h = C.c_void_p()
     assert lib.tdvp_create(0, None, C.byref(h)) != 0 and not h.value
     assert lib.tdvp_last_error(None) == b"null handle"
+
+
+@pytest.mark.parametrize("shape", [(1, 5), (5, 1), (3, 4), (4, 4), (1, 1)])
+def test_adjoint_resolves_the_lazy_conjugate_bit(shape):
+    """``Engine.svd`` hands the conjugate transpose of a wide matrix to the C ABI, which reads raw memory: the tensor must hold
+    the conjugated VALUES (torch's ``conj()`` alone only sets a flag, and ``.T.contiguous()`` keeps it for 1 x n / n x 1)."""
+    import torch
+
+    from pytdscf_b200._engine import adjoint
+
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+    t = adjoint(torch.from_numpy(a))
+    assert t.is_contiguous() and not t.is_conj() and tuple(t.shape) == shape[::-1]
+    raw = torch.view_as_real(t).numpy()                     # what a data_ptr() reader sees
+    assert np.array_equal(raw[..., 0] + 1j * raw[..., 1], a.conj().T)
