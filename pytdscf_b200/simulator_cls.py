@@ -209,8 +209,11 @@ class Simulator:
             raise ValueError(f"parallel_split_indices has {len(split)} segments but the process group has {info.world} "
                              "ranks (launch with torchrun --nproc-per-node <segments>)")
         n = self.model.get_ndof()
-        flat = [i for seg in split for i in seg]
-        if flat != list(range(n)):
+        # the reference reads only the first and last entry of every tuple (_const_cls.py:236-250): (start, end) pairs -- its
+        # documented form -- and tuples that list every site of the segment are both accepted
+        ok = split[0][0] == 0 and split[-1][-1] == n - 1 and all(seg[0] <= seg[-1] for seg in split)
+        ok = ok and all(split[i][-1] + 1 == split[i + 1][0] for i in range(len(split) - 1))
+        if not ok:
             raise ValueError("parallel_split_indices must partition 0..nsite-1 into consecutive segments")
         eng = self._engine()
         cores = None

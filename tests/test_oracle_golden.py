@@ -132,6 +132,25 @@ def test_reference_known_answers():
     assert g["final_energy"].real == pytest.approx(0.018225341011652626)
 
 
+def test_reference_known_reduced_density():
+    """The 2 x 2 reduced density of the exciton site that the reference's own test pins as a literal
+    (tests/test_exiciton_propagate.py:179-185: last record of reduced_density.nc = the state before the 20th step,
+    atol 1e-9), from the oracle's state after 19 steps."""
+    g = load_run("exciton_D2")
+    H = orc.MPOHamiltonian(len(g["dims"]), g["operators"], g["coupleJ"])
+    o = orc.TDVPOracle(H, [c.copy() for c in g["init"]], thresh=g["thresh_sil"])
+    for _ in range(19):
+        o.propagate(g["dt_au"])
+    psi = o.mps[0]
+    for c in o.mps[1:]:
+        psi = np.tensordot(psi, c, axes=(-1, 0))
+    m = psi.reshape(-1, g["dims"][-1])                      # (vibrational configurations, exciton state)
+    rho = m.T @ m.conj()
+    literal = np.array([[1.86417721e-02 + 1.60379680e-20j, 2.87367863e-02 - 6.91095824e-02j],
+                        [2.87367863e-02 + 6.91095824e-02j, 9.81358228e-01 - 7.40721885e-18j]])
+    np.testing.assert_allclose(rho, literal, rtol=0, atol=1e-9)
+
+
 @pytest.mark.parametrize("name", ["relax_improved_hh4", "relax_imag_hh4"])
 def test_relaxation_matches_reference(name):
     """Improved relaxation (Lanczos eigen-solver per site, K step skipped) and imaginary-time relaxation."""

@@ -133,3 +133,68 @@ def test_site_parallel_reduced_densities_match_reference(name, tmp_path):
             assert got.shape == ref.shape
             assert np.abs(got - ref).max() < 1e-11, (step, key, np.abs(got - ref).max())
     assert "reduced_density.nc" in res[0]["files"] and "reduced_density.npz" in res[0]["files"]
+
+
+# ---------------------------------------------------------------------------------------------------------
+KNOWN_SPLITS = {2: [(0, 5), (6, 11)], 3: [(0, 3), (4, 7), (8, 11)], 4: [(0, 2), (3, 5), (6, 8), (9, 11)]}
+
+
+def _worker_known(rank, world, port, tmp, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port), OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1")
+    try:
+        import torch
+
+        torch.set_num_threads(1)
+        import pytdscf_b200 as tb
+        from oracle.oracle_engine import OracleEngine
+        from pytdscf_b200 import parallel
+
+        n = 12
+        mpo = []
+        for i in range(n):                                   # get_hamiltonian() of the reference's tests/test_mpi.py:95-167
+            core = np.zeros((1, 4, 4, 1), dtype=np.complex128)
+            core[0, :, :, 0] = np.eye(4) * (2.0 if i == 0 else 1.0)
+            mpo.append(core)
+        key = tuple((i, i) for i in range(n))
+        legs = tuple(x for i in range(n) for x in (i, i))
+        ham = tb.TensorHamiltonian(ndof=n, potential=[[{key: tb.TensorOperator(mpo=mpo, legs=legs)}]], backend="cuda")
+        model = tb.Model([tb.Exciton(nstate=4) for _ in range(n)], {"hamiltonian": ham}, bond_dim=1)
+        # weight_vib of get_mps_parallel(adaptive=False), tests/test_mpi.py:66-79 (m_aux_max = 1: a product state)
+        model.init_HartreeProduct = [[[1.0, 0.0, 0.0, 0.0], [1.0, 1.0, 0.0, 0.0], [1.0, 1.0, 1.0, 0.0]] + [[1.0] * 4] * 9]
+        os.chdir(tmp)
+        info = parallel.init_from_env("gloo")
+        sim = tb.Simulator("known", model, backend="cuda", verbose=0)
+        sim.eng = OracleEngine()
+        sim.rank_info = info
+        sim.propagate(stepsize=0.1, maxstep=2, parallel_split_indices=KNOWN_SPLITS[world], populations=False,
+                      reduced_density=([(5, 5), (0,), (0, 1, 4)], 1))
+        q.put((rank, {"history": sim.history if rank == 0 else None}))
+        parallel.finalize(info)
+    except Exception:  # pragma: no cover
+        import traceback
+
+        q.put((rank, {"error": traceback.format_exc()}))
+
+
+@pytest.mark.parametrize("P", [2, 3, 4])
+def test_site_parallel_known_answers_of_the_reference_tests(P, tmp_path):
+    """The known answers the reference's own MPI tests assert (tests/test_mpi.py:186-268, 12 sites of d = 4, product state,
+    2 / 3 / 4 ranks with its split indices): autocorrelation and norm 1 (abs 1e-5), <H> = 2, rho_(5,5) = 1/4 everywhere,
+    rho_(0,) = e_0, the leading block of rho_(0,1,4) = 1/8 -- on the distributed initial state, and (tests/test_mpi.py:278-285)
+    two propagation steps run; H = 2 x identity, so energy and densities stay what they were."""
+    from tests.mp_util import run_ranks
+
+    port = 35000 + (os.getpid() % 2000) + P
+    res = run_ranks(_worker_known, P, (port, str(tmp_path)), timeout=600)
+    hist = res[0]["history"]
+    assert len(hist) == 2
+    assert abs(hist[0]["autocorr"] - 1.0) < 1e-5
+    for rec in hist:
+        assert abs(rec["norm"] - 1.0) < 1e-5
+        assert rec["energy"] == pytest.approx(2.0)
+        rd = rec["reduced_densities"]
+        np.testing.assert_allclose(rd[(5, 5)], np.ones((4, 4)) * 0.25, atol=1e-7)
+        np.testing.assert_allclose(rd[(0,)], np.array([1.0, 0.0, 0.0, 0.0]), atol=1e-7)
+        assert rd[(0, 1, 4)].shape == (4, 4, 4)
+        np.testing.assert_allclose(rd[(0, 1, 4)][:1, :2, :4], np.ones((1, 2, 4)) / 8, atol=1e-7)
