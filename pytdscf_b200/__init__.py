@@ -3,7 +3,7 @@
 Only the MPS/MPO one-site TDVP propagation hot path of PyTDSCF is implemented; it runs
 entirely on the GPU through ``libtdvp_b200.so`` (``include/tdvp_b200.h``).  There is no CPU fallback.
 """
-from . import kraus, units
+from . import kraus, units, util
 from .basis import Boson, Exciton, HarmonicOscillator
 from .dvr_operator_cls import TensorOperator, construct_kinetic_mpo
 from .hamiltonian_cls import TensorHamiltonian
@@ -12,5 +12,5 @@ from .checkpoint import export_mpo_npz, import_mpo_npz, read_reference_wavefunct
 from .simulator_cls import Simulator
 
 __version__ = "0.1.0"
-__all__ = ["kraus", "export_mpo_npz", "import_mpo_npz", "read_reference_wavefunction", "write_reference_wavefunction", "units", "Boson", "Exciton", "HarmonicOscillator", "TensorOperator", "construct_kinetic_mpo",
+__all__ = ["kraus", "util", "export_mpo_npz", "import_mpo_npz", "read_reference_wavefunction", "write_reference_wavefunction", "units", "Boson", "Exciton", "HarmonicOscillator", "TensorOperator", "construct_kinetic_mpo",
            "TensorHamiltonian", "BasInfo", "Model", "Simulator", "__version__"]

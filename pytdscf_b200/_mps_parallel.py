@@ -402,15 +402,35 @@ class MPSCoefParallelCuda(MPSCoefCuda):
         for s in pair:
             s.gauge = "C"
         canonicalize(eng, pair, 0)                     # Psi B
-        op_env = self.renormalize_op_psite(n, op_env_previous, H, False, site=pair[1])
+        shape_out = None
+        op_env_braket = None
+        if getattr(cfg, "adaptive", False):
+            # rank-adaptive boundary bond (_mps_parallel.py:316-333): the pair is sites (n-1, n) of a virtual superblock, the
+            # neighbour rank's B site takes up to dD directions of its orthogonal complement, the projection-error
+            # criterion picks the new bond dimension, and Psi_L is propagated into the enlarged tensor
+            from . import _adaptive as ad
+
+            full = [None] * (n - 1) + ad.get_superblock_full(eng, pair, cfg.dD)
+            virtual = [None] * (n - 1) + pair
+            own, self.superblock_states[0] = self.superblock_states[0], virtual
+            try:
+                newD, _err, op_env, op_env_braket = ad.get_adaptive_rank_and_block(self, n - 1, full, op_env_previous, H, "->", cfg)
+            finally:
+                self.superblock_states[0] = own
+            pair = virtual[n - 1:]                      # pair[1] now carries newD left-bond states
+            shape_out = (pair[0].shape[0], pair[0].shape[1], newD)
+        else:
+            op_env = self.renormalize_op_psite(n, op_env_previous, H, False, site=pair[1])
         key = self.site_now                            # the joint solves reuse the last swept site's Krylov history
         # half step on Psi_L
         hterms = self.operators_for_superH(n - 1, op_sys_previous, op_env, H, True)
-        pair[0] = SiteCoef(self._expm(cfg, -1.0j, dt, pair[0].data, key, 0, hterms=hterms), "Psi", n - 1)
+        pair[0] = SiteCoef(self._expm(cfg, -1.0j, dt, pair[0].data, key, 0, shape_out=shape_out, hterms=hterms), "Psi", n - 1)
         # bond matrix between the ranks (regularised QR)
         A_data, sigma = eng.qr_shift("A", pair[0].data, regularize=True)
         pair[0] = SiteCoef(A_data, "A", n - 1)
         op_sys = self.renormalize_op_psite(n - 1, op_sys_previous, H, True, site=pair[0])
+        if op_env_braket is not None:
+            op_env = op_env_braket
         kterms = self.operators_for_superK(op_sys, op_env, H, True, bond=n)
         sigma = self._expm(cfg, +1.0j, dt, sigma, key, 1, kterms=kterms)
         # half step on Psi_R
@@ -444,13 +464,15 @@ class MPSCoefParallelCuda(MPSCoefCuda):
             self.op_sys_sites = right_blocks if self.rank % 2 == 0 else left_blocks
         last = self.size - 1
         # (1) -> (2)
-        # every message of a step carries a tag naming its place in the protocol: its layout is exchanged once (Comm.send)
-        self.send_op_sys_to_left(True, H, pop_op_sys=True, tag="1a")
-        op_sys_from_right = self.recv_op_sys_from_right(False, tag="1a")
-        self.send_joint_sigvec_to_right(False, tag="1b")
-        self.recv_joint_sigvec_from_left(True, tag="1b")
-        self.send_op_sys_to_right(False, tag="1c")
-        op_sys_from_left = self.recv_op_sys_from_left(True, tag="1c")
+        # every message of a step carries a tag naming its place in the protocol: its layout is exchanged once (Comm.send);
+        # rank-adaptive runs change the shapes from step to step, so their messages stay self-describing (tag None)
+        T = (lambda name: None) if getattr(cfg, "adaptive", False) else (lambda name: name)
+        self.send_op_sys_to_left(True, H, pop_op_sys=True, tag=T("1a"))
+        op_sys_from_right = self.recv_op_sys_from_right(False, tag=T("1a"))
+        self.send_joint_sigvec_to_right(False, tag=T("1b"))
+        self.recv_joint_sigvec_from_left(True, tag=T("1b"))
+        self.send_op_sys_to_right(False, tag=T("1c"))
+        op_sys_from_left = self.recv_op_sys_from_left(True, tag=T("1c"))
         # (2) -> (3): all ranks sweep concurrently, even ranks rightwards, odd ranks leftwards
         if self.rank % 2 == 0:
             self.propagate_along_sweep(H, stepsize, cfg, begin_site=0, end_site=self.nsite - 1,
@@ -459,20 +481,20 @@ class MPSCoefParallelCuda(MPSCoefCuda):
             self.propagate_along_sweep(H, stepsize, cfg, begin_site=self.nsite - 1, end_site=0,
                                        op_sys_initial=op_sys_from_right, skip_end_site=True)
         # (3) -> (4)
-        self.send_Psi_to_left(False, tag="3a")
-        psi_L, psi_R = self.recv_Psi_from_right(True, tag="3a")
-        self.send_op_sys_to_left(False, H, pop_op_sys=False, tag="3b")
-        op_env_previous = self.recv_op_sys_from_right(True, tag="3b")
+        self.send_Psi_to_left(False, tag=T("3a"))
+        psi_L, psi_R = self.recv_Psi_from_right(True, tag=T("3a"))
+        self.send_op_sys_to_left(False, H, pop_op_sys=False, tag=T("3b"))
+        op_env_previous = self.recv_op_sys_from_right(True, tag=T("3b"))
         op_sys_from_right, Bsite = self.propagate_joint_two_sites(True, H, stepsize, cfg, op_env_previous, psi_L, psi_R)
-        self.send_B_to_right(True, Bsite, tag="3c")
-        self.recv_B_from_left(False, tag="3c")
+        self.send_B_to_right(True, Bsite, tag=T("3c"))
+        self.recv_B_from_left(False, tag=T("3c"))
         self.save_all_A(True)
         self.save_all_B(False)
         # (4) -> (5)
-        self.send_joint_sigvec_to_right(True, tag="4a")
-        self.recv_joint_sigvec_from_left(False, tag="4a")
-        self.send_op_sys_to_right(True, tag="4b")
-        op_sys_from_left = self.recv_op_sys_from_left(False, tag="4b")
+        self.send_joint_sigvec_to_right(True, tag=T("4a"))
+        self.recv_joint_sigvec_from_left(False, tag=T("4a"))
+        self.send_op_sys_to_right(True, tag=T("4b"))
+        op_sys_from_left = self.recv_op_sys_from_left(False, tag=T("4b"))
         # (5) -> (2): sweep back
         if self.rank % 2 == 0:
             self.propagate_along_sweep(H, stepsize, cfg, begin_site=self.nsite - 1, end_site=0,
@@ -481,19 +503,30 @@ class MPSCoefParallelCuda(MPSCoefCuda):
             self.propagate_along_sweep(H, stepsize, cfg, begin_site=0, end_site=self.nsite - 1,
                                        op_sys_initial=op_sys_from_left, skip_end_site=(self.rank != last))
         # (2) -> (1)
-        self.send_Psi_to_left(True, tag="2a")
-        psi_L, psi_R = self.recv_Psi_from_right(False, tag="2a")
-        self.send_op_sys_to_left(True, H, pop_op_sys=False, tag="2b")
-        op_env_previous = self.recv_op_sys_from_right(False, tag="2b")
+        self.send_Psi_to_left(True, tag=T("2a"))
+        psi_L, psi_R = self.recv_Psi_from_right(False, tag=T("2a"))
+        self.send_op_sys_to_left(True, H, pop_op_sys=False, tag=T("2b"))
+        op_env_previous = self.recv_op_sys_from_right(False, tag=T("2b"))
         op_env_from_left, Bsite = self.propagate_joint_two_sites(False, H, stepsize, cfg, op_env_previous, psi_L, psi_R)
-        self.send_B_to_right(False, Bsite, tag="2c")
-        self.recv_B_from_left(True, tag="2c")
-        self.send_op_env_to_right(False, op_env_from_left, tag="2d")
-        self.recv_op_env_from_left(True, tag="2d")
+        self.send_B_to_right(False, Bsite, tag=T("2c"))
+        self.recv_B_from_left(True, tag=T("2c"))
+        self.send_op_env_to_right(False, op_env_from_left, tag=T("2d"))
+        self.recv_op_env_from_left(True, tag=T("2d"))
         self.save_all_A(False)
         self.save_all_B(True)
 
     # -- observables (results on rank 0) ----------------------------------------------------------------------
+    def bonddim(self):
+        """Bond dimensions of the whole chain on rank 0, None elsewhere (reference ``WFunc.bonddim`` for mpi_size > 1,
+        wavefunction.py:151-174: every rank's right bonds gathered, the last one dropped)."""
+        mine = [int(s.shape[2]) for s in self.sites]
+        if self.rank != 0:
+            self.comm.send(mine, 0)
+            return None
+        dims = mine + [d for r in range(1, self.size) for d in self.comm.recv(r)]
+        dims.pop()
+        return dims
+
     def _segment_tensors(self) -> list:
         """This rank's site tensors such that the segments of all ranks, concatenated, are an MPS of the whole state: the
         boundary bond matrix is carried by both neighbours, so the last tensor of every segment but the final one takes

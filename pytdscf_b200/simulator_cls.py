@@ -251,8 +251,8 @@ class Simulator:
         if parallel_split_indices is not None:
             # reference: one MPI rank per tuple of consecutive sites (simulator_cls.py:243-249, _const_cls.py:236-251);
             # here one torch.distributed rank (= one GPU) per tuple, launched by torchrun
-            if adaptive or restart or self.model.one_gate_to_apply is not None or self.model.kraus_op is not None:  # noqa: SIM102
-                raise NotImplementedError("site-parallel propagation supports neither adaptive bond dimensions, restart nor gates")
+            if restart or self.model.one_gate_to_apply is not None or self.model.kraus_op is not None:  # noqa: SIM102
+                raise NotImplementedError("site-parallel propagation supports neither restart nor gates / Kraus maps")
             self._split = [tuple(int(i) for i in seg) for seg in parallel_split_indices]
         return self._run(Δt if Δt is not None else stepsize, maxstep, False, restart, savefile_ext, loadfile_ext,
                          backup_interval, autocorr=autocorr, energy=energy, norm=norm, populations=populations,

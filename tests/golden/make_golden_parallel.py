@@ -23,6 +23,11 @@ CASES = {
     # boundary pseudo-inverse / regularised SVD to amplify), so independent implementations can agree to 1e-10
     "par_frenkel8_P2": ("frenkel8", 2, [(0, 1, 2, 3), (4, 5, 6, 7)], 4, 0.2, 10),
     "par_frenkel8_P4": ("frenkel8", 4, [(0, 1), (2, 3), (4, 5), (6, 7)], 4, 0.2, 10),
+    # rank-adaptive bond dimensions INSIDE a site-parallel run (the reference's tests/test_mpi_exiciton_propagate.py[adaptive]):
+    # a 7th entry = (Dmax, dD, p_proj, p_svd); the bonds grow inside the segments and across the rank boundaries
+    "par_adaptive_exciton_P2": ("exciton", 2, [(0, 1), (2, 3)], 1, 0.05, 6, (8, 4, 1.0e-5, 1.0e-6)),
+    "par_adaptive_hh8_P2": ("hh8", 2, [(0, 3), (4, 7)], 2, 0.1, 5, (6, 2, 1.0e-6, 1.0e-7)),
+    "par_adaptive_hh8_P4": ("hh8", 4, [(0, 1), (2, 3), (4, 5), (6, 7)], 2, 0.1, 5, (6, 2, 1.0e-6, 1.0e-7)),
 }
 
 
@@ -78,7 +83,9 @@ def worker(case):
     from pytdscf.model_cls import Model
     from pytdscf.simulator_cls import Simulator
 
-    model_name, P, split, D, dt_fs, nstep = CASES[case]
+    model_name, P, split, D, dt_fs, nstep = CASES[case][:6]
+    adaptive = CASES[case][6] if len(CASES[case]) > 6 else None
+    nstep = int(os.environ.get("PAR_NSTEP", nstep))          # debugging aid: shorter runs into PAR_OUT
     if model_name == "exciton":
         prim, ops, hartree = mg.exciton_model()
         vib = None
@@ -94,6 +101,7 @@ def worker(case):
     if vib is not None:
         model.init_weight_VIBSTATE = [vib]
     mg.RECORD["props"].clear()
+    mg.RECORD["trace"].clear()
     sim = Simulator(case, model, backend="numpy", verbose=0)
     model_dump = {}
     if int(os.environ["FAKE_MPI_RANK"]) == 0:
@@ -106,7 +114,13 @@ def worker(case):
             model_dump[f"key{ik}"] = np.array(repr(key))
             for ic, c in enumerate(cores):
                 model_dump[f"key{ik}_core{ic}"] = np.asarray(c)
-    ener, wf = sim.propagate(stepsize=dt_fs, maxstep=nstep, parallel_split_indices=split, populations=False)
+    akw = {} if adaptive is None else dict(adaptive=True, adaptive_Dmax=adaptive[0], adaptive_dD=adaptive[1],
+                                           adaptive_p_proj=adaptive[2], adaptive_p_svd=adaptive[3])
+    # PAR_PERTURB (adaptive cases, second run): the time step scaled by 1 + 1e-14 -- a rounding-level perturbation that shows how
+    # far the reference reproduces ITSELF (the regularised QR / SVD of the boundary update floor singular values of 1e-8 ... 1e-19
+    # to 1e-4 along singular vectors that are rounding noise, so the result is defined only up to that noise)
+    dt_fs = dt_fs * (1.0 + float(os.environ.get("PAR_PERTURB", "0")))
+    ener, wf = sim.propagate(stepsize=dt_fs, maxstep=nstep, parallel_split_indices=split, populations=False, **akw)
     rank = const.mpi_rank
     if rank == 0:
         from pytdscf._mps_mpo import MPSCoefMPO   # the serial initial MPS that rank 0 canonicalises and distributes
@@ -116,6 +130,7 @@ def worker(case):
     out = {"props": np.array([[t, a.real, a.imag, e.real, e.imag, n] for (t, a, e, n) in mg.RECORD["props"]]) if rank == 0 else np.zeros(0),
            "final_energy": np.array(complex(ener) if ener is not None else np.nan)}
     out.update(model_dump)
+    out["trace"] = np.array(mg.RECORD["trace"], dtype=np.int64).reshape(-1, 3)    # this rank's Krylov solves: kind, local site, niter
     mps = wf.ci_coef
     for i, s in enumerate(mps.superblock_states[0]):
         out[f"site{i}"] = np.array(s.data)
@@ -129,7 +144,8 @@ def worker(case):
 def driver():
     sys.path.insert(0, ROOT)
     only = os.environ.get("PAR_ONLY")
-    for case, (model_name, P, split, D, dt_fs, nstep) in CASES.items():
+    for case, spec in CASES.items():
+        model_name, P, split, D, dt_fs, nstep = spec[:6]
         if only and only not in case:
             continue
         with tempfile.TemporaryDirectory() as tmp:
@@ -144,8 +160,25 @@ def driver():
                 for r, o in enumerate(outs):
                     print(f"--- rank {r} rc={procs[r].returncode}\n{o[-3000:]}")
                 raise SystemExit(f"{case}: a rank failed")
+            noise = None
+            if len(spec) > 6:      # the same run again under a rounding-level perturbation: the reference's own reproducibility
+                with tempfile.TemporaryDirectory() as tmp2:
+                    procs2 = []
+                    for r in range(P):
+                        env = dict(os.environ, FAKE_MPI_RANK=str(r), FAKE_MPI_SIZE=str(P), FAKE_MPI_DIR=tmp2, LOGURU_LEVEL="ERROR",
+                                   OPENBLAS_NUM_THREADS="1", PAR_PERTURB="1e-14")
+                        procs2.append(subprocess.Popen([sys.executable, os.path.abspath(__file__), "--worker", case], env=env, cwd=tmp2,
+                                                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+                    for p2 in procs2:
+                        p2.communicate(timeout=900)
+                    if any(p2.returncode != 0 for p2 in procs2):
+                        raise SystemExit(f"{case}: a rank of the perturbed run failed")
+                    noise = np.load(os.path.join(tmp2, "rank0.npz"))["props"]
             merged = {"nranks": np.array(P), "split": np.array([(seg[0], seg[-1]) for seg in split]), "bond_dim": np.array(D), "dt_fs": np.array(dt_fs),
                       "nstep": np.array(nstep), "model": np.array(model_name)}
+            if len(spec) > 6:
+                merged["adaptive"] = np.array(spec[6], dtype=float)
+                merged["props_perturbed"] = noise
             for r in range(P):
                 z = np.load(os.path.join(tmp, f"rank{r}.npz"))
                 for k in z.files:
@@ -153,7 +186,7 @@ def driver():
                         merged[k] = z[k]
                     else:
                         merged[f"r{r}_{k}"] = z[k]
-            np.savez_compressed(os.path.join(HERE, case + ".npz"), **merged)
+            np.savez_compressed(os.path.join(os.environ.get("PAR_OUT", HERE), case + ".npz"), **merged)
             pr = merged["r0_props"]
             print(f"[golden-parallel] {case}: P={P} steps={nstep} E0={pr[0, 3]:.12f} E_last={pr[-1, 3]:.12f} "
                   f"norm_last={pr[-1, 5]:.10f} autocorr_last={pr[-1, 1]:+.8f}{pr[-1, 2]:+.8f}j")

@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from tests.golden_io import PAR_CASES, load_parallel
+from tests.golden_io import PAR_ADAPTIVE_CASES, PAR_CASES, load_parallel
 
 
 def _worker(rank, world, port, name, tmp, q):
@@ -29,10 +29,15 @@ def _worker(rank, world, port, name, tmp, q):
         sim.eng = OracleEngine()
         sim.rank_info = info
         sim.set_initial_mps(g["init"])
-        ener, wf = sim.propagate(stepsize=g["dt_fs"], maxstep=g["nstep"], parallel_split_indices=g["split"], populations=False)
+        akw = {}
+        if g["adaptive"] is not None:
+            Dmax, dD, p_proj, p_svd = g["adaptive"]
+            akw = dict(adaptive=True, adaptive_Dmax=int(Dmax), adaptive_dD=int(dD), adaptive_p_proj=p_proj, adaptive_p_svd=p_svd)
+        ener, wf = sim.propagate(stepsize=g["dt_fs"], maxstep=g["nstep"], parallel_split_indices=g["split"], populations=False,
+                                 record_trace=True, **akw)
         mps = wf.ci_coef
         out = {"history": sim.history if rank == 0 else None, "sites": [s.numpy() for s in mps.sites],
-               "gauges": [s.gauge for s in mps.sites],
+               "gauges": [s.gauge for s in mps.sites], "trace": [tuple(int(v) for v in t) for t in mps.trace],
                "joint": None if mps.joint_sigvec_not_pinv is None else mps.joint_sigvec_not_pinv.cpu().numpy(),
                "files": sorted(os.listdir(name + "_cpu_prop")) if rank == 0 else None}
         q.put((rank, out))
@@ -43,7 +48,7 @@ def _worker(rank, world, port, name, tmp, q):
         q.put((rank, {"error": traceback.format_exc()}))
 
 
-@pytest.mark.parametrize("name", PAR_CASES)
+@pytest.mark.parametrize("name", PAR_CASES + PAR_ADAPTIVE_CASES)
 def test_site_parallel_matches_reference(name, tmp_path):
     from tests.mp_util import run_ranks
 
@@ -59,13 +64,32 @@ def test_site_parallel_matches_reference(name, tmp_path):
         print(name, "max dev", max(abs(rec["autocorr"] - complex(row[1], row[2])) for rec, row in zip(hist, g["props"])),
               max(abs(rec["energy"] - row[3]) for rec, row in zip(hist, g["props"])),
               max(abs(rec["norm"] - row[5]) for rec, row in zip(hist, g["props"])))
+    tol_a = tol_e = tol_n = 1e-12
+    stable = True
+    if g["adaptive"] is not None:
+        # Rank-adaptive runs: the regularised QR / SVD of the boundary update raise singular values of 1e-8 ... 1e-19 (the bond
+        # directions that were just added) to 1e-4 along singular vectors that are rounding noise, so the reference reproduces
+        # ITSELF only to a case-dependent level: the generator ran it a second time with the time step scaled by 1 + 1e-14
+        # (props_perturbed).  Bar: 10 x that self-deviation (+ 1e-11) where it is below 1e-9 (the Henon-Heiles cases: 1e-10-level), 50 x where
+        # the reference amplifies rounding to 2e-4 (the exciton case, whose grown directions stay at rounding level).  The reference's own test of this mode asserts the energy to
+        # rel 1e-1 (tests/test_mpi_exiciton_propagate.py:236).
+        a, b = g["props"], g["props_perturbed"]
+        dev_a = np.abs((a[:, 1] + 1j * a[:, 2]) - (b[:, 1] + 1j * b[:, 2])).max()
+        dev_e, dev_n = np.abs(a[:, 3] - b[:, 3]).max(), np.abs(a[:, 5] - b[:, 5]).max()
+        stable = max(dev_a, dev_n) < 1e-9
+        f = 10 if stable else 50     # one perturbed run is a single sample of a chaotic amplification: wider margin when it is large
+        tol_a, tol_e, tol_n = 1e-11 + f * dev_a, 1e-11 + f * dev_e, 1e-11 + f * dev_n
     for rec, row in zip(hist, g["props"], strict=True):
-        assert abs(rec["autocorr"] - complex(row[1], row[2])) < 1e-12
-        assert abs(rec["energy"] - row[3]) < 1e-12 * max(1.0, abs(row[3]))
-        assert abs(rec["norm"] - row[5]) < 1e-12
+        assert abs(rec["autocorr"] - complex(row[1], row[2])) < tol_a
+        assert abs(rec["energy"] - row[3]) < tol_e * max(1.0, abs(row[3]))
+        assert abs(rec["norm"] - row[5]) < tol_n
     for r in range(P):
         assert res[r]["gauges"] == g["ranks"][r]["gauges"]
-        assert [s.shape for s in res[r]["sites"]] == [s.shape for s in g["ranks"][r]["sites"]]
+        assert [s.shape for s in res[r]["sites"]] == [s.shape for s in g["ranks"][r]["sites"]]     # adaptive: identical bond growth
+        if g["ranks"][r]["trace"] is not None and stable:
+            assert res[r]["trace"] == [tuple(int(v) for v in t) for t in g["ranks"][r]["trace"]]    # identical Krylov counts per rank
+        if g["adaptive"] is not None:
+            continue     # site tensors of grown bonds carry rounding-level directions: compared through the observables
         if r < P - 1:
             a, b = res[r]["joint"], g["ranks"][r]["joint_sigvec_not_pinv"]
             np.testing.assert_allclose(a, b, rtol=0, atol=1e-11)
@@ -139,7 +163,7 @@ def test_site_parallel_reduced_densities_match_reference(name, tmp_path):
 KNOWN_SPLITS = {2: [(0, 5), (6, 11)], 3: [(0, 3), (4, 7), (8, 11)], 4: [(0, 2), (3, 5), (6, 8), (9, 11)]}
 
 
-def _worker_known(rank, world, port, tmp, q):
+def _worker_known(rank, world, port, tmp, adaptive, q):
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
                       MASTER_PORT=str(port), OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1")
     try:
@@ -159,16 +183,17 @@ def _worker_known(rank, world, port, tmp, q):
         key = tuple((i, i) for i in range(n))
         legs = tuple(x for i in range(n) for x in (i, i))
         ham = tb.TensorHamiltonian(ndof=n, potential=[[{key: tb.TensorOperator(mpo=mpo, legs=legs)}]], backend="cuda")
-        model = tb.Model([tb.Exciton(nstate=4) for _ in range(n)], {"hamiltonian": ham}, bond_dim=1)
-        # weight_vib of get_mps_parallel(adaptive=False), tests/test_mpi.py:66-79 (m_aux_max = 1: a product state)
+        model = tb.Model([tb.Exciton(nstate=4) for _ in range(n)], {"hamiltonian": ham}, bond_dim=10 if adaptive else 1)
+        # weight_vib of get_mps_parallel, tests/test_mpi.py:66-84 (m_aux_max = 1, or 10 with zero-padded bonds in the adaptive runs)
         model.init_HartreeProduct = [[[1.0, 0.0, 0.0, 0.0], [1.0, 1.0, 0.0, 0.0], [1.0, 1.0, 1.0, 0.0]] + [[1.0] * 4] * 9]
         os.chdir(tmp)
         info = parallel.init_from_env("gloo")
         sim = tb.Simulator("known", model, backend="cuda", verbose=0)
         sim.eng = OracleEngine()
         sim.rank_info = info
+        akw = dict(adaptive=True, adaptive_Dmax=30, adaptive_dD=30, adaptive_p_proj=1e-04, adaptive_p_svd=1e-7) if adaptive else {}
         sim.propagate(stepsize=0.1, maxstep=2, parallel_split_indices=KNOWN_SPLITS[world], populations=False,
-                      reduced_density=([(5, 5), (0,), (0, 1, 4)], 1))
+                      reduced_density=([(5, 5), (0,), (0, 1, 4)], 1), **akw)
         q.put((rank, {"history": sim.history if rank == 0 else None}))
         parallel.finalize(info)
     except Exception:  # pragma: no cover
@@ -177,16 +202,17 @@ def _worker_known(rank, world, port, tmp, q):
         q.put((rank, {"error": traceback.format_exc()}))
 
 
+@pytest.mark.parametrize("adaptive", [False, True])
 @pytest.mark.parametrize("P", [2, 3, 4])
-def test_site_parallel_known_answers_of_the_reference_tests(P, tmp_path):
+def test_site_parallel_known_answers_of_the_reference_tests(P, adaptive, tmp_path):
     """The known answers the reference's own MPI tests assert (tests/test_mpi.py:186-268, 12 sites of d = 4, product state,
-    2 / 3 / 4 ranks with its split indices): autocorrelation and norm 1 (abs 1e-5), <H> = 2, rho_(5,5) = 1/4 everywhere,
+    2 / 3 / 4 ranks with its split indices, ``adaptive`` False and True): autocorrelation and norm 1 (abs 1e-5), <H> = 2, rho_(5,5) = 1/4 everywhere,
     rho_(0,) = e_0, the leading block of rho_(0,1,4) = 1/8 -- on the distributed initial state, and (tests/test_mpi.py:278-285)
     two propagation steps run; H = 2 x identity, so energy and densities stay what they were."""
     from tests.mp_util import run_ranks
 
-    port = 35000 + (os.getpid() % 2000) + P
-    res = run_ranks(_worker_known, P, (port, str(tmp_path)), timeout=600)
+    port = 35000 + (os.getpid() % 2000) + P + (10 if adaptive else 0)
+    res = run_ranks(_worker_known, P, (port, str(tmp_path), adaptive), timeout=600)
     hist = res[0]["history"]
     assert len(hist) == 2
     assert abs(hist[0]["autocorr"] - 1.0) < 1e-5
