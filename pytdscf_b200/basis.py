@@ -60,6 +60,22 @@ class Boson:
         a = self.get_annihilation_matrix()
         return 1.0j * (a.T - a) / math.sqrt(2.0)
 
+    def _ladder_sum_squared(self, sign: float) -> np.ndarray:
+        """(b+ + sign b)^2 evaluated in a space one level larger and cut back, so that the last diagonal element is the exact
+        matrix element instead of the truncation artefact of squaring the cut matrices (reference ``margin=1``,
+        pytdscf/basis/boson.py:129-153)."""
+        b = np.diag(np.sqrt(np.arange(1, self.nstate + 1, dtype=float)), k=1)
+        s = b.T + sign * b
+        return (s @ s)[:-1, :-1]
+
+    def get_q2_matrix(self) -> np.ndarray:
+        """q^2 = (b+ + b)^2 / 2."""
+        return 0.5 * self._ladder_sum_squared(+1.0)
+
+    def get_p2_matrix(self) -> np.ndarray:
+        """p^2 = -(b+ - b)^2 / 2."""
+        return -0.5 * self._ladder_sum_squared(-1.0)
+
     @property
     def nprim(self) -> int:
         return self.nstate
@@ -116,6 +132,18 @@ class HarmonicOscillator:
     def get_unitary(self) -> np.ndarray:
         """u[j, alpha]: FBR index j (HO quantum number) x DVR index alpha."""
         return self._diagonalise()[1]
+
+    def get_1st_derivative_matrix_fbr(self) -> np.ndarray:
+        """First-derivative matrix in the HO eigenbasis WITH THE REFERENCE'S SIGN (pytdscf/basis/ho.py:130-145):
+        D[j, j+1] = -sqrt(omega (j+1) / 2), D[j+1, j] = +sqrt(omega (j+1) / 2).  With the position matrix of
+        ``get_pos_rep_matrix`` this D satisfies [D, q] = -1, i.e. it is -d/dq for real HO functions; MPO cores built from it
+        must equal the reference's, so its convention is kept (the second-derivative matrix does not depend on it)."""
+        up = np.sqrt(self.omega * np.arange(1, self.ngrid) / 2.0)
+        return np.diag(up, -1) - np.diag(up, 1)
+
+    def get_1st_derivative_matrix_dvr(self) -> np.ndarray:
+        U = self.get_unitary()
+        return U.conj().T @ self.get_1st_derivative_matrix_fbr() @ U
 
     def get_2nd_derivative_matrix_fbr(self) -> np.ndarray:
         n = self.ngrid

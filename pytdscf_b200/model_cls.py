@@ -100,6 +100,9 @@ class Model:
     def get_nspf(self, istate: int, idof: int) -> int:
         return self.basinfo.get_nspf(istate, idof)
 
+    def get_nprim(self, istate: int, idof: int) -> int:
+        return self.basinfo.get_nprim(istate, idof)
+
     def get_nspf_list(self, istate: int) -> list[int]:
         return self.basinfo.get_nspf_list(istate)
 

@@ -180,3 +180,36 @@ def test_adjoint_resolves_the_lazy_conjugate_bit(shape):
     assert t.is_contiguous() and not t.is_conj() and tuple(t.shape) == shape[::-1]
     raw = torch.view_as_real(t).numpy()                     # what a data_ptr() reader sees
     assert np.array_equal(raw[..., 0] + 1j * raw[..., 1], a.conj().T)
+
+
+def test_basis_operator_matrices_match_the_reference():
+    """d x d operator matrices users build MPO cores from (host-side input preparation): Boson q^2 / p^2 with the reference's
+    one-level margin and the HO first-derivative matrices, against the unmodified reference when its tree is present and
+    against their defining properties always."""
+    b = tb.Boson(5)
+    big = tb.Boson(9)
+    q, p = big.get_q_matrix(), big.get_p_matrix()
+    np.testing.assert_allclose(b.get_q2_matrix(), (q @ q)[:5, :5].real, atol=1e-14)      # exact matrix elements of the full space
+    np.testing.assert_allclose(b.get_p2_matrix(), (p @ p)[:5, :5].real, atol=1e-14)
+    np.testing.assert_allclose(0.5 * (b.get_q2_matrix() + b.get_p2_matrix()), b.get_number_matrix() + 0.5 * np.eye(5), atol=1e-14)
+    ho = tb.HarmonicOscillator(7, 1500.0, units="cm-1")
+    d1 = ho.get_1st_derivative_matrix_fbr()
+    np.testing.assert_allclose(d1, -d1.T, atol=0)                                       # anti-Hermitian
+    d1d = ho.get_1st_derivative_matrix_dvr()
+    # the reference's sign convention: [D, q] = -1 on the states the truncation does not touch (DVR position operator = diag(grids))
+    comm = ho.get_unitary() @ (d1d @ np.diag(ho.get_grids()) - np.diag(ho.get_grids()) @ d1d) @ ho.get_unitary().conj().T
+    np.testing.assert_allclose(comm[:6, :6], -np.eye(6), atol=1e-12)
+    np.testing.assert_allclose((d1 @ d1)[:5, :5], ho.get_2nd_derivative_matrix_fbr()[:5, :5], atol=1e-12)   # D^2 = d^2/dq^2 either way
+    assert tb.Model([b, ho], {"hamiltonian": [np.zeros((1, 5, 1)), np.zeros((1, 7, 1))]}, bond_dim=2).get_nprim(0, 1) == 7
+    if os.path.isdir("/root/reference/pytdscf"):
+        from oracle.reference_loader import load_reference
+
+        load_reference()
+        from pytdscf.basis import Boson as RefBoson
+        from pytdscf.basis import HarmonicOscillator as RefHO
+
+        np.testing.assert_allclose(b.get_q2_matrix(), RefBoson(5).get_q2_matrix(), atol=1e-14)
+        np.testing.assert_allclose(b.get_p2_matrix(), RefBoson(5).get_p2_matrix(), atol=1e-14)
+        rho = RefHO(7, 1500.0, units="cm-1")
+        np.testing.assert_allclose(d1, rho.get_1st_derivative_matrix_fbr(), atol=1e-14)
+        np.testing.assert_allclose(d1d, rho.get_1st_derivative_matrix_dvr(), atol=1e-12)
