@@ -674,6 +674,3 @@ class MPSCoefParallelCuda(MPSCoefCuda):
                 val = complex(v[0], v[1])
             return val
         return None
-
-    def bonddim(self):
-        return [s.shape[2] for s in self.sites]

@@ -96,6 +96,15 @@ def test_site_parallel_matches_reference(name, tmp_path):
         for a, b in zip(res[r]["sites"], g["ranks"][r]["sites"], strict=True):
             np.testing.assert_allclose(a, b, rtol=0, atol=1e-10)
     assert "main.log" in res[0]["files"] and "autocorr.dat" in res[0]["files"]
+    if g["adaptive"] is not None:
+        # bond dimensions of the whole chain, gathered on rank 0 before every step (wavefunction.py:151-174) and written to
+        # bonddim.dat (properties.py:344-356): they start at the initial MPS's, never shrink and end below the final shapes
+        assert "bonddim.dat" in res[0]["files"]
+        dims = [rec["bonddim"] for rec in hist]
+        assert dims[0] == [c.shape[2] for c in g["init"][:-1]]
+        final = [s.shape[2] for r in range(P) for s in g["ranks"][r]["sites"]][:-1]
+        for a, b in zip(dims, dims[1:] + [final]):
+            assert len(a) == len(final) and all(x <= y for x, y in zip(a, b))
 
 
 # ---------------------------------------------------------------------------------------------------------
