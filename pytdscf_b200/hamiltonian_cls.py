@@ -17,6 +17,16 @@ class TensorHamiltonian:
     def __init__(self, ndof: int, potential, name: str = "hamiltonian", kinetic=None, decompose_type: str = "QRD",
                  rate: float | None = None, bond_dimension=None, backend: str = "cuda"):
         backend = check_backend(backend)
+        self.deferred = potential is None
+        if self.deferred:
+            # The reference's MPI scripts build the operators on rank 0 only and pass ``potential=None`` elsewhere
+            # (tests/test_mpi_exiciton_propagate.py:175-183); its ``distribute_mpo_cores`` (hamiltonian_cls.py:805-850) then
+            # scatters the cores.  Here such a placeholder adopts rank 0's cores when the site-parallel run starts
+            # (``Simulator._distributed_wavefunction`` -> ``adopt``).
+            self.name, self.nstate, self.ndof, self.backend = name, 1, ndof, backend
+            self.coupleJ = [[0.0]]
+            self.mpo = [[MatrixProductOperators(nsite=ndof, operators={}, backend=backend)]]
+            return
         if isinstance(potential, dict):
             potential = [[potential]]
         if kinetic is not None and isinstance(kinetic, dict):
@@ -51,6 +61,19 @@ class TensorHamiltonian:
                         raise ValueError(f"key {key} is already set in potential. Concatenate KEO and PEO or set KEO as SOP")
                     operators[key] = list(d2.decompose())
             self.mpo[i][j] = MatrixProductOperators(nsite=ndof, operators=operators, backend=backend)
+
+    def export_cores(self) -> dict:
+        """What a rank without operators needs to run: the scalar term and the cores of every MPO key (host arrays)."""
+        if self.nstate != 1:
+            raise NotImplementedError("only one state is supported")
+        return {"coupleJ": complex(self.coupleJ[0][0]), "operators": {key: [np.asarray(c) for c in cores]
+                                                                       for key, cores in self.mpo[0][0].operators.items()}}
+
+    def adopt(self, payload: dict):
+        """Fill a ``potential=None`` placeholder with the cores rank 0 exported."""
+        self.coupleJ = [[payload["coupleJ"]]]
+        self.mpo = [[MatrixProductOperators(nsite=self.ndof, operators=dict(payload["operators"]), backend=self.backend)]]
+        self.deferred = False
 
     def apply_backend(self, backend: str):
         self.backend = check_backend(backend)

@@ -216,11 +216,25 @@ class Simulator:
         if not ok:
             raise ValueError("parallel_split_indices must partition 0..nsite-1 into consecutive segments")
         eng = self._engine()
+        comm = Comm(info, eng.torch_device)
+        # operators built on rank 0 only (the reference's MPI idiom, ``TensorHamiltonian(potential=None)`` elsewhere): rank 0
+        # hands its host cores to every rank; nothing is exchanged when every rank built its own
+        ham = self.model.hamiltonian
+        if comm.allreduce_lor(bool(getattr(ham, "deferred", False))):
+            if info.rank == 0:
+                if ham.deferred:
+                    raise ValueError("rank 0 must hold the Hamiltonian (potential=None is for the other ranks)")
+                payload = ham.export_cores()
+                for r in range(1, info.world):
+                    comm.send(payload, r)
+            else:
+                payload = comm.recv(0)
+                if ham.deferred:
+                    ham.adopt(payload)
         cores = None
         if getattr(self, "_initial_mps", None) is not None:
             cores = self._initial_mps[0]
-        mps = MPSCoefParallelCuda.distribute(eng, Comm(info, eng.torch_device), self.model, [seg[0] for seg in split],
-                                             cores=cores)
+        mps = MPSCoefParallelCuda.distribute(eng, comm, self.model, [seg[0] for seg in split], cores=cores)
         return WFunc(mps, eng)
 
     # -----------------------------------------------------------------------------------------------
