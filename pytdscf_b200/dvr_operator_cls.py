@@ -43,6 +43,14 @@ class TensorOperator:
     def decompose(self, **ignored) -> list[np.ndarray]:
         return self.tensor_decomposed
 
+    def restore_from_decoposed(self) -> np.ndarray:
+        """The dense operator tensor the cores represent, legs in site order (small operators only; the reference's name,
+        typo included: dvr_operator_cls.py:547-554)."""
+        t = self.tensor_decomposed[0]
+        for core in self.tensor_decomposed[1:]:
+            t = np.tensordot(t, core, axes=(-1, 0))
+        return t[0, ..., 0]
+
 
 def construct_kinetic_mpo(dvr_prims, coefs=None) -> list[np.ndarray]:
     """sum_i -1/2 c_i d^2/dQ_i^2 as a bond-dimension-2 MPO of full cores."""

@@ -213,3 +213,15 @@ def test_basis_operator_matrices_match_the_reference():
         rho = RefHO(7, 1500.0, units="cm-1")
         np.testing.assert_allclose(d1, rho.get_1st_derivative_matrix_fbr(), atol=1e-14)
         np.testing.assert_allclose(d1d, rho.get_1st_derivative_matrix_dvr(), atol=1e-12)
+
+
+def test_tensor_operator_restores_the_dense_operator():
+    """``TensorOperator.restore_from_decoposed`` (reference dvr_operator_cls.py:547-554) on the kinetic MPO: the cores contract to
+    sum_i -1/2 d^2/dQ_i^2 exactly."""
+    ho = [tb.HarmonicOscillator(4, 1000.0 * (i + 1)) for i in range(3)]
+    dense = tb.TensorOperator(mpo=tb.construct_kinetic_mpo(ho)).restore_from_decoposed()
+    d = [-0.5 * h.get_2nd_derivative_matrix_dvr() for h in ho]
+    eye = np.eye(4)
+    ref = (np.einsum("ab,cd,ef->abcdef", d[0], eye, eye) + np.einsum("ab,cd,ef->abcdef", eye, d[1], eye)
+           + np.einsum("ab,cd,ef->abcdef", eye, eye, d[2]))
+    np.testing.assert_allclose(dense, ref, atol=1e-14)
