@@ -433,3 +433,24 @@ def test_direct_sum_mpo_is_the_same_operator(tmp_path):
     for rec, row in zip(sim.history, g["props"], strict=True):
         assert abs(rec["autocorr"] - complex(row[1], row[2])) < 1e-11
         assert abs(rec["energy"] - row[3]) < 1e-11 * max(1.0, abs(row[3]))
+
+
+def test_single_site_chain_reproduces_the_reference_literal(tmp_path):
+    """The f = 1 row of the reference's tests/test_henon_heiles.py:21 (omega = 4000 cm-1, N = 5 HO-DVR points, m = 4, dt = 0.01 fs,
+    first excited state, pinned energy 0.027338011517478895 = 1.5 omega) -- a chain of ONE site: no bond, no QR shift, no K step.
+    The potential of one mode needs no MPO builder (a (1, N, 1) diagonal core on the grid), the kinetic MPO is this package's."""
+    import pytdscf_b200 as tb
+
+    os.chdir(tmp_path)
+    w, N = 4000, 5
+    prim = [tb.HarmonicOscillator(N, w)]
+    q = np.array(prim[0].get_grids())
+    V = [((w / tb.units.au_in_cm1) ** 2 / 2 * q**2).reshape(1, N, 1)]
+    model = tb.Model(prim, operators={"potential": V, "kinetic": tb.construct_kinetic_mpo(prim)}, bond_dim=4)
+    model.init_weight_VIBSTATE = [[[0.0, 1.0] + [0.0] * (N - 2)]]
+    sim = tb.Simulator(jobname="henon_heiles", model=model, backend="cuda", verbose=0)
+    sim.eng = OracleEngine()
+    ener, wf = sim.propagate(maxstep=3, stepsize=0.01)
+    assert ener == pytest.approx(0.027338011517478895)            # the reference's own tolerance (rel 1e-6); measured 7e-16
+    assert [tuple(s.data.shape) for s in wf.ci_coef.sites] == [(1, N, 1)]
+    assert all(abs(abs(rec["autocorr"]) - 1.0) < 1e-12 for rec in sim.history)      # an eigenstate only picks up a phase
