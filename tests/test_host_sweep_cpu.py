@@ -454,3 +454,28 @@ def test_single_site_chain_reproduces_the_reference_literal(tmp_path):
     assert ener == pytest.approx(0.027338011517478895)            # the reference's own tolerance (rel 1e-6); measured 7e-16
     assert [tuple(s.data.shape) for s in wf.ci_coef.sites] == [(1, N, 1)]
     assert all(abs(abs(rec["autocorr"]) - 1.0) < 1e-12 for rec in sim.history)      # an eigenstate only picks up a phase
+
+
+@pytest.mark.parametrize("improved", [True, False])
+def test_harmonic_relaxation_reproduces_the_reference_literal(improved, tmp_path):
+    """The reference's tests/test_harmonic_dvr_func_full_mpssm_jax.py:17-56 (three HO-DVR modes of 1500 / 2000 / 2500 cm-1 with
+    five points, harmonic potential, m_aux_max = 4, ``relax(maxstep=3, stepsize=0.1)``) pins the zero-point energy
+    0.013669005758739458.  The separable potential needs no MPO builder: three one-site diagonal keys plus this package's kinetic
+    MPO.  ``improved=True`` is the reference's default (per-site Lanczos eigen-solver), ``False`` imaginary time."""
+    import pytdscf_b200 as tb
+
+    os.chdir(tmp_path)
+    freqs = [1500, 2000, 2500]
+    prim = [tb.HarmonicOscillator(5, w, 0.0) for w in freqs]
+    pot = {}
+    for i, (p, w) in enumerate(zip(prim, freqs)):
+        q = np.array(p.get_grids())
+        pot[(i,)] = tb.TensorOperator(mpo=[((w / tb.units.au_in_cm1) ** 2 / 2 * q**2).reshape(1, 5, 1)], legs=(i,))
+    kin = {tuple((i, i) for i in range(3)): tb.TensorOperator(mpo=tb.construct_kinetic_mpo(prim))}
+    ham = tb.TensorHamiltonian(ndof=3, potential=[[pot]], kinetic=[[kin]], backend="cuda")
+    model = tb.Model(tb.BasInfo([prim]), {"hamiltonian": ham})
+    model.m_aux_max = 4
+    sim = tb.Simulator("harmonic_dvr", model, backend="cuda", verbose=0)
+    sim.eng = OracleEngine()
+    ener, wf = sim.relax(maxstep=3, stepsize=0.1, improved=improved)
+    assert ener == pytest.approx(0.013669005758739458)            # rel 1e-6 in the reference's test; measured 7e-16 / 2e-16
