@@ -5,12 +5,14 @@ import numpy as np
 import pytest
 
 from oracle.oracle_engine import OracleEngine
+from tests.device_numerics_engine import DeviceNumericsEngine
 from tests.hermitise_cases import run_and_check
 
 
+@pytest.mark.parametrize("engine", [OracleEngine, DeviceNumericsEngine])   # LAPACK's SVD conventions / the device's
 @pytest.mark.parametrize("tag", ["prop", "rand"])
-def test_hermitise_host_logic(tag):
-    err, asym = run_and_check(tag, OracleEngine(), tol=1e-12)
+def test_hermitise_host_logic(tag, engine):
+    err, asym = run_and_check(tag, engine(), tol=1e-12)
     if tag == "prop":
         assert asym < 1e-12     # full bonds: (rho + rho^dagger) / 2 is kept exactly
 

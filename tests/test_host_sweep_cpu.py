@@ -256,16 +256,19 @@ def kraus_observables(sim, wf, g):
     return [(r["energy"], r["norm"]) for r in sim.history], rho, ref
 
 
+@pytest.mark.parametrize("engine", ["lapack", "device"])
 @pytest.mark.parametrize("case", ["kraus_spin4", "kraus2_spin4"])
-def test_host_kraus_logic(case, tmp_path):
+def test_host_kraus_logic(case, engine, tmp_path):
     """Kraus maps between the half sweeps: with the oracle's kernels (same LAPACK SVD) the product reproduces the
-    reference run, Krylov trace included."""
+    reference run, Krylov trace included -- and also with the SVD following the device's conventions
+    (tests/device_numerics_engine.py): the observables are invariant under the ancilla gauge the SVD leaves open."""
     import pytdscf_b200 as tb
+    from tests.device_numerics_engine import DeviceNumericsEngine
 
     g = load_run(case)
     os.chdir(tmp_path)
     sim = tb.Simulator("kraus_cpu", _kraus_model(g), backend="cuda")
-    sim.eng = OracleEngine()
+    sim.eng = OracleEngine() if engine == "lapack" else DeviceNumericsEngine()
     sim.set_initial_mps(g["init"])
     ener, wf = sim.propagate(stepsize=g["dt_au"] * tb.units.au_in_fs, maxstep=g["nstep"], autocorr=False, populations=False,
                              conserve_norm=False, record_trace=True)

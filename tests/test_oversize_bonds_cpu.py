@@ -7,6 +7,9 @@ import pytest
 
 from oracle.oracle_engine import OracleEngine
 from pytdscf_b200._mps_cuda import MPSCoefCuda, oversize_bonds
+from tests.device_numerics_engine import DeviceNumericsEngine
+
+ENGINES = [OracleEngine, DeviceNumericsEngine]     # LAPACK's SVD conventions / the device's (tests/device_numerics_engine.py)
 
 
 def dense(cores):
@@ -24,11 +27,12 @@ def rand_chain(rng, dims, bonds):
 @pytest.mark.parametrize("dims,bonds", [([2, 4, 3, 2], [4, 9, 5]),       # wide first site, oversize middle bond, tall last site
                                          ([2, 2, 2, 2, 2], [7, 7, 7, 7]),  # every bond far beyond 2^k
                                          ([3, 3, 3], [3, 3])])             # already within the rule: untouched
-def test_oversize_bonds_are_compressed_exactly(dims, bonds):
+@pytest.mark.parametrize("engine", ENGINES)
+def test_oversize_bonds_are_compressed_exactly(dims, bonds, engine):
     rng = np.random.default_rng(sum(bonds))
     cores = rand_chain(rng, dims, bonds)
     ref = dense(cores)
-    eng = OracleEngine()
+    eng = engine()
     before = oversize_bonds(MPSCoefCuda(eng, [eng.to_device(c) for c in cores]).sites)
     mps = MPSCoefCuda.from_user_cores(eng, cores)
     got = [np.asarray(s.data) for s in mps.sites]
