@@ -24,6 +24,48 @@ def _core(core: DeviceCore | None):
     return orc.SiteCore((), 0, core.data.numpy(), False, False)
 
 
+def _chk(t, name: str, ndim: int | None = None):
+    """The preconditions of the real engine (``pytdscf_b200/_engine.py::_chk_tensor``) and of the C ABI behind it, which reads raw
+    memory: a contiguous complex128 torch tensor whose lazy conjugate bit is not set.  The NumPy kernels below would accept
+    anything; enforcing the device's contract here makes every CPU host-logic test also a test of what the host hands to the ABI."""
+    if t is None:
+        return
+    if not isinstance(t, torch.Tensor) or t.dtype != torch.complex128:
+        raise TypeError(f"{name} must be a complex128 torch tensor (got {type(t).__name__}, {getattr(t, 'dtype', None)})")
+    if not t.is_contiguous() or t.is_conj():
+        raise TypeError(f"{name} must be contiguous with its conjugate bit resolved (the C ABI reads raw memory)")
+    if ndim is not None and t.dim() != ndim:
+        raise ValueError(f"{name} must have {ndim} indices, got shape {tuple(t.shape)}")
+
+
+def _chk_hterms(terms, psi):
+    Dl, d, Dr = psi.shape
+    for L, core, R, _coef in terms:
+        _chk(L, "L", 3)
+        _chk(R, "R", 3)
+        if L is not None and (L.shape[0] != Dl or L.shape[2] != Dl):
+            raise ValueError(f"left block {tuple(L.shape)} does not match psi {tuple(psi.shape)}")
+        if R is not None and (R.shape[0] != Dr or R.shape[2] != Dr):
+            raise ValueError(f"right block {tuple(R.shape)} does not match psi {tuple(psi.shape)}")
+        if core is not None and core.data is not None:
+            _chk(core.data, "W")
+            if L is not None and L.shape[1] != core.wl or R is not None and R.shape[1] != core.wr:
+                raise ValueError("block / core bond dimension mismatch")
+            if core.data.shape[1] != d:
+                raise ValueError("core / site physical dimension mismatch")
+
+
+def _chk_kterms(terms, sigma):
+    Dl, Dr = sigma.shape
+    for L, R, *_rest in terms:
+        _chk(L, "L", 3)
+        _chk(R, "R", 3)
+        if L is not None and (L.shape[0] != Dl or L.shape[2] != Dl) or R is not None and (R.shape[0] != Dr or R.shape[2] != Dr):
+            raise ValueError("K_eff block does not match the bond matrix")
+        if L is not None and R is not None and L.shape[1] != R.shape[1]:
+            raise ValueError("K_eff term: MPO bond dimensions of L and R differ")
+
+
 class OracleEngine:
     def __init__(self):
         self.torch_device = torch.device("cpu")
@@ -47,6 +89,8 @@ class OracleEngine:
         return torch.from_numpy(np.ascontiguousarray(a))
 
     def heff_apply(self, terms, psi):
+        _chk(psi, "psi", 3)
+        _chk_hterms(terms, psi)
         d = {i: (_np(L), _core(c), _np(R)) for i, (L, c, R, coef) in enumerate(terms)}
         out = None
         for i, (L, c, R, coef) in enumerate(terms):
@@ -55,6 +99,8 @@ class OracleEngine:
         return self._wrap(out)
 
     def keff_apply(self, terms, sigma):
+        _chk(sigma, "sigma", 2)
+        _chk_kterms(terms, sigma)
         out = None
         for (L, R, coef, *_ids) in terms:
             add = orc.keff_term(_np(L), _np(R), sigma.numpy())
@@ -64,6 +110,14 @@ class OracleEngine:
         return self._wrap(out)
 
     def env_update(self, gauge, bra, ket, E, core, out=None, accumulate=False):
+        _chk(bra, "bra", 3)
+        _chk(ket, "ket", 3)
+        _chk(E, "E", 3)
+        _chk(out, "out", 3)
+        if tuple(bra.shape) != tuple(ket.shape):
+            raise ValueError("tdvp_env_update takes bra and ket of one shape (rectangular blocks are zero-padded by the caller)")
+        if core is not None and core.data is not None:
+            _chk(core.data, "W")
         res = orc.env_update_term(gauge, bra.numpy(), ket.numpy(), _np(E), _core(core))
         if out is not None and accumulate:
             out += self._wrap(res)
@@ -71,6 +125,11 @@ class OracleEngine:
         return self._wrap(res)
 
     def krylov_expm(self, kind, scale, thresh, n_warmup, conserve_norm, psi, *, hterms=None, kterms=None, size_override=None):
+        _chk(psi, "psi")
+        if hterms is not None:
+            _chk_hterms(hterms, psi)
+        else:
+            _chk_kterms(kterms, psi)
         last = n_warmup + 2 if n_warmup > 0 else 0
         if hterms is not None:
             mv = lambda x: self.heff_apply(hterms, self._wrap(x)).numpy()  # noqa: E731
@@ -85,12 +144,20 @@ class OracleEngine:
         return n
 
     def lanczos_eigvec(self, psi, hterms, root=0, thresh=1e-9):
+        _chk(psi, "psi", 3)
+        _chk_hterms(hterms, psi)
         mv = lambda x: self.heff_apply(hterms, self._wrap(x)).numpy()  # noqa: E731
         y, n = orc.lanczos_ground_state(mv, psi.numpy().copy(), root, thresh)
         psi.copy_(self._wrap(y / np.linalg.norm(y)))
         return n
 
     def qr_shift(self, gauge, psi, regularize=False):
+        _chk(psi, "psi", 3)
+        Dl, d, Dr = psi.shape
+        if gauge == "A" and Dl * d < Dr:             # Engine.qr_shift / TDVP_ERR_SHAPE: tall matricisations only
+            raise ValueError("QR shift needs Dl*d >= Dr")
+        if gauge != "A" and Dr * d < Dl:
+            raise ValueError("LQ shift needs Dr*d >= Dl")
         if gauge == "A":
             A, s = orc.shift_qr(psi.numpy(), regularize)
             return self._wrap(A), self._wrap(s)
@@ -98,17 +165,27 @@ class OracleEngine:
         return self._wrap(B), self._wrap(s)
 
     def svd(self, M):
+        _chk(M, "M", 2)
         U, s, Vh = np.linalg.svd(M.numpy(), full_matrices=False)
         return self._wrap(U), s, self._wrap(Vh)
 
     def svd_truncate(self, sigma, p, keepdim=False, regularize=False):
+        _chk(sigma, "sigma", 2)
+        if sigma.shape[0] != sigma.shape[1]:
+            raise ValueError("svd_truncate: the bond matrix must be square")        # tdvp_svd_truncate
         U, S, Vh, rank = orc.truncate_bond(None, sigma.numpy(), None, p, regularize, keepdim)
         return self._wrap(U), self._wrap(S.astype(complex)), self._wrap(Vh), rank
 
     def pinv(self, X, rcond=1e-13):
+        _chk(X, "X", 2)
+        if X.shape[0] != X.shape[1]:
+            raise ValueError("pinv: square matrices only")                          # tdvp_pinv
         return self._wrap(np.linalg.pinv(X.numpy(), rcond=rcond))
 
     def zgemm(self, A, B, transA=0, transB=0, alpha=1.0, beta=0.0, C_out=None):
+        _chk(A, "A", 2)          # Engine.zgemm passes shape[1] as the leading dimension: row-major contiguous operands only
+        _chk(B, "B", 2)
+        _chk(C_out, "C", 2)
         a = {0: A.numpy(), 1: A.numpy().T, 2: A.numpy().conj().T}[transA]
         b = {0: B.numpy(), 1: B.numpy().T, 2: B.numpy().conj().T}[transB]
         out = alpha * (a @ b)
@@ -118,15 +195,26 @@ class OracleEngine:
         return self._wrap(out)
 
     def absorb(self, gauge, sigma, site):
+        _chk(sigma, "sigma", 2)
+        _chk(site, "site", 3)
+        if (gauge == "A" and sigma.shape[1] != site.shape[0]) or (gauge != "A" and sigma.shape[0] != site.shape[2]):
+            raise ValueError("absorb: bond dimensions of the matrix and the site differ")
         if gauge == "A":
             return self._wrap(np.tensordot(sigma.numpy(), site.numpy(), axes=(1, 0)))
         return self._wrap(np.tensordot(site.numpy(), sigma.numpy(), axes=(2, 0)))
 
     def inner(self, bra, ket, conj=True):
+        _chk(bra, "bra")
+        _chk(ket, "ket")
+        if bra.numel() != ket.numel():
+            raise ValueError("inner: sizes differ")
         a = bra.numpy().ravel()
         return complex(np.inner(np.conj(a) if conj else a, ket.numpy().ravel()))
 
     def overlap_site(self, bra, ket, block, conj_bra):
+        _chk(bra, "bra", 3)
+        _chk(ket, "ket", 3)
+        _chk(block, "block", 2)
         b = np.conj(bra.numpy()) if conj_bra else bra.numpy()
         return self._wrap(np.einsum("abc,abk->ck", b, np.einsum("ibk,ai->abk", ket.numpy(), block.numpy())))
 

@@ -13,7 +13,7 @@ from __future__ import annotations
 import numpy as np
 
 from oracle import tdvp_oracle as orc
-from oracle.oracle_engine import OracleEngine
+from oracle.oracle_engine import OracleEngine, _chk
 
 NEGLIGIBLE, SIGNIFICANT, EPS = 1.0e-20, 8.0, 2.220446049250313e-16
 SQRT_EPSRHO = 1.0e-4
@@ -90,12 +90,16 @@ class DeviceNumericsEngine(OracleEngine):
         return U, s, Vh
 
     def svd(self, M):
+        _chk(M, "M", 2)
         U, s, Vh = self._svd(M.numpy())
         return self._wrap(np.ascontiguousarray(U)), s, self._wrap(np.ascontiguousarray(Vh))
 
     def svd_truncate(self, sigma, p, keepdim=False, regularize=False):      # tdvp_svd_truncate + Engine.svd_truncate
+        _chk(sigma, "sigma", 2)
         A = sigma.numpy()
         n = A.shape[0]
+        if A.shape[0] != A.shape[1]:
+            raise ValueError("svd_truncate: the bond matrix must be square")
         U, s, Vh = self._svd(A)
         cs = np.cumsum(s)
         idx = n
@@ -115,7 +119,10 @@ class DeviceNumericsEngine(OracleEngine):
         return self._wrap(np.ascontiguousarray(U[:, :idx])), self._wrap(S), self._wrap(np.ascontiguousarray(Vh[:idx])), idx
 
     def pinv(self, X, rcond=1e-13):                                           # tdvp_pinv
+        _chk(X, "X", 2)
         A = X.numpy()
+        if A.shape[0] != A.shape[1]:
+            raise ValueError("pinv: square matrices only")
         off = A - np.diag(np.diag(A))
         if not off.any():                                                     # diagonal probe: no SVD
             d = np.abs(np.diag(A))
@@ -134,6 +141,10 @@ class DeviceNumericsEngine(OracleEngine):
         return np.ascontiguousarray(((U * s_reg[None, :]) @ Vh).reshape(Dl, Dr, d).transpose(0, 2, 1))
 
     def qr_shift(self, gauge, psi, regularize=False):
+        _chk(psi, "psi", 3)
+        Dl, d, Dr = psi.shape
+        if (gauge == "A" and Dl * d < Dr) or (gauge != "A" and Dr * d < Dl):
+            raise ValueError("QR / LQ shift needs a tall matricisation")
         A = self.regularize_site(psi) if regularize else psi.numpy()
         if gauge == "A":
             Q, s = orc.shift_qr(A, False)
