@@ -38,6 +38,25 @@ def _chk(t, name: str, ndim: int | None = None):
         raise ValueError(f"{name} must have {ndim} indices, got shape {tuple(t.shape)}")
 
 
+def _unit_channel(block, ch: int):
+    """Copy of an environment block (D, w, D) with channel ``ch`` replaced by the unit matrix -- what the device library uses for
+    a channel named in ``id_channels`` (it copies instead of multiplying)."""
+    b = block.clone()
+    b[:, ch, :] = torch.eye(b.shape[0], dtype=b.dtype)
+    return b
+
+
+def _chk_shortcut(full: np.ndarray, short: np.ndarray, what: str):
+    """The identity-channel promise of ``tdvp_heff_term.id_channels`` / ``tdvp_keff_term.id_channels``, stated as what it has to
+    guarantee: the product with the promised channels taken as unit matrices equals the full contraction.  (Comparing the
+    blocks themselves would be too strict: a zero-padded or sub-space-projected site leaves zeros on the diagonal of <B|B> for
+    bond states that carry no amplitude, which changes nothing.)"""
+    scale = max(float(np.abs(full).max()), 1.0e-300)
+    dev = float(np.abs(full - short).max()) / scale
+    if dev > 1.0e-9:
+        raise ValueError(f"{what}: the identity-channel shortcut of the device library would change the result by {dev:.2e} (relative)")
+
+
 def _chk_hterms(terms, psi):
     Dl, d, Dr = psi.shape
     for L, core, R, _coef in terms:
@@ -91,23 +110,45 @@ class OracleEngine:
     def heff_apply(self, terms, psi):
         _chk(psi, "psi", 3)
         _chk_hterms(terms, psi)
-        d = {i: (_np(L), _core(c), _np(R)) for i, (L, c, R, coef) in enumerate(terms)}
-        out = None
-        for i, (L, c, R, coef) in enumerate(terms):
-            add = orc.heff_term(*d[i], psi.numpy()) * complex(coef) if complex(coef) != 1.0 else orc.heff_term(*d[i], psi.numpy())
-            out = add.copy() if out is None else out + add
+        out = self._heff_sum(terms, psi)
+        promised = [(L, c, R, coef) for (L, c, R, coef) in terms
+                    if c is not None and c.data is not None and ((L is not None and c.l_id >= 0) or (R is not None and c.r_id >= 0))]
+        if promised:
+            short = [(None if L is None else (_unit_channel(L, c.l_id) if c.l_id >= 0 else L), c,
+                      None if R is None else (_unit_channel(R, c.r_id) if c.r_id >= 0 else R), coef) for (L, c, R, coef) in promised]
+            _chk_shortcut(self._heff_sum(promised, psi), self._heff_sum(short, psi), "H_eff")
         return self._wrap(out)
+
+    @staticmethod
+    def _heff_sum(terms, psi) -> np.ndarray:
+        out = None
+        for L, c, R, coef in terms:
+            add = orc.heff_term(_np(L), _core(c), _np(R), psi.numpy())
+            if complex(coef) != 1.0:
+                add = add * complex(coef)
+            out = add.copy() if out is None else out + add
+        return out
 
     def keff_apply(self, terms, sigma):
         _chk(sigma, "sigma", 2)
         _chk_kterms(terms, sigma)
+        out = self._keff_sum(terms, sigma)
+        promised = [t for t in terms if len(t) > 3 and t[3] is not None and t[0] is not None and t[1] is not None]
+        if promised:
+            short = [(_unit_channel(L, ids[0]) if ids[0] >= 0 else L, _unit_channel(R, ids[1]) if ids[1] >= 0 else R, coef)
+                     for (L, R, coef, ids) in promised]
+            _chk_shortcut(self._keff_sum(promised, sigma), self._keff_sum(short, sigma), "K_eff")
+        return self._wrap(out)
+
+    @staticmethod
+    def _keff_sum(terms, sigma) -> np.ndarray:
         out = None
         for (L, R, coef, *_ids) in terms:
             add = orc.keff_term(_np(L), _np(R), sigma.numpy())
             if complex(coef) != 1.0:
                 add = add * complex(coef)
             out = add.copy() if out is None else out + add
-        return self._wrap(out)
+        return out
 
     def env_update(self, gauge, bra, ket, E, core, out=None, accumulate=False):
         _chk(bra, "bra", 3)
