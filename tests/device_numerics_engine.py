@@ -75,6 +75,8 @@ def jacobi_svd(A: np.ndarray):
 
 
 class DeviceNumericsEngine(OracleEngine):
+    reorder_mpo_channels = True     # as the CUDA engine: DeviceMPO moves identity-prefix / -suffix channels first / last
+
     def __init__(self):
         super().__init__()
         self.svd_log: list = []     # (shape, sweeps)
