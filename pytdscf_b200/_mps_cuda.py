@@ -606,6 +606,59 @@ class MPSCoefCuda:
             self.apply_kraus(kraus_op, reorth_center=n - 1)
         self.propagate_along_sweep(H, stepsize, cfg, begin_site=n - 1, end_site=0)
 
+    # -- operator application |Psi'> = O|Psi> / |O|Psi>| (Simulator.operate) ------------------------------------------
+    def clone(self) -> "MPSCoefCuda":
+        twin = MPSCoefCuda(self.eng, [s.data.clone() for s in self.sites], [s.gauge for s in self.sites])
+        twin.subspace = dict(self.subspace)
+        return twin
+
+    def apply_dipole(self, init: "MPSCoefCuda", O: DeviceMPO) -> float:
+        """One fitting iteration of ``O |init>`` (reference ``MPSCoef.apply_dipole``, _mps_cls.py:421-450): a forward and a
+        backward sweep in which every site tensor of THIS chain is replaced by the H_eff-type contraction of ``O`` between this
+        chain (bra environments) and ``init`` (ket environments and ket site), normalised; returns the norm found at the last
+        site, which converges to |O|init>|.  Both chains are gauge-shifted along the sweep, as in the reference."""
+        n = self.nsite
+        self._apply_dipole_along_sweep(init, O, 0, n - 1)
+        return self._apply_dipole_along_sweep(init, O, n - 1, 0)
+
+    def _apply_dipole_along_sweep(self, init: "MPSCoefCuda", O: DeviceMPO, begin_site: int, end_site: int) -> float:
+        """Reference ``apply_dipole_along_sweep`` + ``apply_superOp_direct`` (_mps_cls.py:718-796, 2733-2778).  Environment blocks
+        with different bra / ket tensors go through ``tdvp_env_update`` as in the adaptive mode (``_adaptive.renormalize_braket``);
+        the site update is one ``tdvp_heff_apply``."""
+        from ._adaptive import renormalize_braket
+
+        eng = self.eng
+        A_is_sys = begin_site < end_site or self.nsite == 1
+        step = 1 if A_is_sys else -1
+        bra, ket = self.sites, init.sites
+        op_sys = self.construct_op_zerosite()
+        cached = getattr(self, "op_sys_sites_dipo", None)
+        if cached is None:
+            env_sites = [self.construct_op_zerosite()]
+            for p in range(end_site, begin_site, -step):
+                env_sites.append(renormalize_braket(self, p, env_sites[-1], O, not A_is_sys, bra[p], ket[p]))
+        else:
+            env_sites = cached[:]
+        self.op_sys_sites_dipo = [op_sys]
+        norm = 0.0
+        gauge = "A" if A_is_sys else "B"
+        for p in range(begin_site, end_site + step, step):
+            op_env = env_sites.pop()
+            hterms = self.operators_for_superH(p, op_sys, op_env, O, A_is_sys)
+            new = eng.heff_apply(hterms, ket[p].data)
+            norm = math.sqrt(eng.inner(new, new, True).real)
+            bra[p] = SiteCoef((new / norm).contiguous(), "Psi", p)
+            if p == end_site:
+                break
+            q = p + step
+            for chain in (bra, ket):                     # ..Psi(p) B(p+1).. -> ..A(p) Psi(p+1)..  on both chains
+                iso, sigma = eng.qr_shift(gauge, chain[p].data)
+                chain[p] = SiteCoef(iso, gauge, p)
+                chain[q] = SiteCoef(eng.absorb(gauge, sigma, chain[q].data), "Psi", q)
+            op_sys = renormalize_braket(self, p, op_sys, O, A_is_sys, bra[p], ket[p])
+            self.op_sys_sites_dipo.append(op_sys)
+        return norm
+
     def apply_kraus(self, kraus_op: dict, reorth_center: int):
         """Kraus maps on a purified MPS (reference ``apply_kraus`` + ``kraus_contract_single_site / _two_site``,
         _mps_cls.py:2375-2418, kraus.py:146-355).  One-site key: the site's physical index is (system d) x (ancilla K);

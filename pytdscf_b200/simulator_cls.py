@@ -59,6 +59,33 @@ class WFunc:
         """Reduced density matrices (reference ``wavefunction.py:67-88``); 0 = traced, 1 = diagonal, 2 = both legs."""
         return self.ci_coef.get_reduced_densities(remain_nleg, space=self.space)
 
+    def apply_dipole(self, matOp, maxstep: int = 10, conv_tol: float = 1.0e-08, log=None) -> float:
+        """|Psi> <- O|Psi> / |O|Psi>| by fitting sweeps; returns |O|Psi>| (reference ``WFunc.apply_dipole`` / ``_is_converged``,
+        wavefunction.py:285-351): at most ``maxstep`` iterations, stopped when the overlap with the previous iterate is 1 to 1e-8."""
+        mps = self.ci_coef
+        O = self.device_op(matOp)
+        init = mps.clone()
+        mps.op_sys_sites_dipo = None
+        norm = 0.0
+        for it in range(maxstep):
+            prev = mps.clone()
+            norm = mps.apply_dipole(init, O)
+            block = None
+            for b, k in zip(mps.sites, prev.sites, strict=True):
+                if block is None:
+                    block = self.eng.to_device(np.ones((1, 1), dtype=np.complex128))
+                block = self.eng.overlap_site(b.data, k.data, block, True)
+            ovlp = complex(block.cpu().numpy()[0, 0])
+            if log is not None:
+                log(f"iterations: {it} norm: {norm} convergence: {abs(ovlp)}")
+            if abs(1.0 - abs(ovlp)) < conv_tol:
+                break
+        else:
+            if log is not None:
+                log(f"Operate O|Psi> is not converged in {maxstep} iterations")
+        mps.op_sys_sites = None        # environments of a Hamiltonian, if any were cached, belong to the old state
+        return norm
+
     def propagate_SM(self, matH, stepsize: float, cfg: RunConfig, one_gate_to_apply=None, kraus_op=None):
         if one_gate_to_apply is None and kraus_op is None:
             self.ci_coef.propagate(stepsize, self.device_op(matH), cfg)
@@ -361,8 +388,30 @@ class Simulator:
                          display_time_unit=display_time_unit, conserve_norm=True, write_files=write_files,
                          record_trace=record_trace, suffix="_relax")
 
-    def operate(self, *args, **kwargs):
-        raise NotImplementedError("operator application is outside the TDVP hot-path scope")
+    def operate(self, maxstep: int = 10, restart: bool = False, savefile_ext: str = "_operate", loadfile_ext: str = "_gs",
+                verbose: int = 2, write_files: bool = True):
+        """Apply the model's ``hamiltonian`` entry -- in this mode an operator such as a dipole MPO -- to the wavefunction
+        (reference ``Simulator.operate``, simulator_cls.py:286-330, 356-361): |Psi'> = O|Psi> / |O|Psi>|.  Returns
+        ``(|O|Psi>|, wf)`` and writes ``wf_<jobname><savefile_ext>.pkl``, from which ``propagate(restart=True, loadfile_ext=
+        savefile_ext)`` continues -- the relax -> operate -> propagate workflow of the reference's spectra notebooks."""
+        if self.model.space != "hilbert":
+            raise NotImplementedError("operate is implemented for Hilbert-space MPS")
+        wf = self.get_initial_wavefunction(restart, loadfile_ext)
+        jobdir = self.jobname + "_operate"
+        log = None
+        f = None
+        if write_files:
+            os.makedirs(jobdir, exist_ok=True)
+            f = _DatFile(os.path.join(jobdir, "main.log"))
+            f.write("Start: apply operator to wave function")
+            if verbose > 1:
+                log = f.write
+        norm = wf.apply_dipole(self.model.hamiltonian, maxstep=maxstep, log=log)
+        if write_files:
+            self.save_wavefunction(wf, savefile_ext)
+            f.write(f"End  : apply operator to wave function, norm = {norm}")
+            f.close()
+        return (norm, wf)
 
     # -- output files in the reference's layout (properties.py:287-356) -----------------------------
     def _open_files(self, cfg: RunConfig) -> dict:
