@@ -52,6 +52,23 @@ class TensorOperator:
         return t[0, ..., 0]
 
 
+def construct_kinetic_operator(dvr_prims, coefs=None, forms: str = "mpo") -> dict:
+    """The kinetic energy operator as the ``{key: TensorOperator}`` dictionary ``TensorHamiltonian(kinetic=[[...]])`` takes
+    (reference ``construct_kinetic_operator``, dvr_operator_cls.py:1135-1196): ``forms="mpo"`` = one key over all modes holding
+    the bond-dimension-2 MPO of ``construct_kinetic_mpo``; ``forms="sop"`` = one single-site key per mode."""
+    n = len(dvr_prims)
+    coefs = [1.0] * n if coefs is None else list(coefs)
+    if forms.lower() == "mpo":
+        return {tuple((i, i) for i in range(n)): TensorOperator(mpo=construct_kinetic_mpo(dvr_prims, coefs))}
+    if forms.lower() == "sop":
+        out = {}
+        for i, (prim, c) in enumerate(zip(dvr_prims, coefs, strict=True)):
+            T = (-0.5 * c * prim.get_2nd_derivative_matrix_dvr()).astype(np.complex128)
+            out[((i, i),)] = TensorOperator(mpo=[T.reshape(1, *T.shape, 1)], legs=(i, i))
+        return out
+    raise ValueError("forms must be 'sop' or 'mpo'")
+
+
 def construct_kinetic_mpo(dvr_prims, coefs=None) -> list[np.ndarray]:
     """sum_i -1/2 c_i d^2/dQ_i^2 as a bond-dimension-2 MPO of full cores."""
     n = len(dvr_prims)

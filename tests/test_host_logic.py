@@ -225,3 +225,22 @@ def test_tensor_operator_restores_the_dense_operator():
     ref = (np.einsum("ab,cd,ef->abcdef", d[0], eye, eye) + np.einsum("ab,cd,ef->abcdef", eye, d[1], eye)
            + np.einsum("ab,cd,ef->abcdef", eye, eye, d[2]))
     np.testing.assert_allclose(dense, ref, atol=1e-14)
+
+
+def test_kinetic_operator_forms_are_the_same_operator():
+    """``construct_kinetic_operator`` (reference dvr_operator_cls.py:1135-1196): the one-key MPO form and the per-mode "sop" form
+    are both sum_i -c_i/2 d^2/dQ_i^2."""
+    ho = [tb.HarmonicOscillator(4, 1000.0 * (i + 1)) for i in range(3)]
+    coefs = [1.0, 0.5, 2.0]
+    mpo_form = tb.construct_kinetic_operator(ho, coefs)
+    sop_form = tb.construct_kinetic_operator(ho, coefs, forms="sop")
+    assert list(mpo_form) == [((0, 0), (1, 1), (2, 2))] and list(sop_form) == [((0, 0),), ((1, 1),), ((2, 2),)]
+    dense = next(iter(mpo_form.values())).restore_from_decoposed()
+    eye = np.eye(4)
+    d = [op.restore_from_decoposed() for op in sop_form.values()]
+    ref = (np.einsum("ab,cd,ef->abcdef", d[0], eye, eye) + np.einsum("ab,cd,ef->abcdef", eye, d[1], eye)
+           + np.einsum("ab,cd,ef->abcdef", eye, eye, d[2]))
+    np.testing.assert_allclose(dense, ref, atol=1e-14)
+    np.testing.assert_allclose(d[1], -0.25 * ho[1].get_2nd_derivative_matrix_dvr(), atol=1e-15)
+    with pytest.raises(ValueError):
+        tb.construct_kinetic_operator(ho, forms="dense")

@@ -71,8 +71,7 @@ def test_relax_operate_workflow_reproduces_the_reference_literal(tmp_path):
         q = np.array(p.get_grids())
         pot[(i,)] = tb.TensorOperator(mpo=[((w / tb.units.au_in_cm1) ** 2 / 2 * q**2).reshape(1, 5, 1)], legs=(i,))
         dms[(i,)] = tb.TensorOperator(mpo=[(0.1 * q).reshape(1, 5, 1)], legs=(i,))
-    kin = {tuple((i, i) for i in range(3)): tb.TensorOperator(mpo=tb.construct_kinetic_mpo(prim))}
-    ham = tb.TensorHamiltonian(ndof=3, potential=[[pot]], kinetic=[[kin]], backend="cuda")
+    ham = tb.TensorHamiltonian(ndof=3, potential=[[pot]], kinetic=[[tb.construct_kinetic_operator(dvr_prims=prim)]], backend="cuda")
     model = tb.Model(tb.BasInfo([prim]), {"hamiltonian": ham})
     model.m_aux_max = 4
     sim = tb.Simulator("harmonic_dvr", model, backend="cuda", verbose=0)
