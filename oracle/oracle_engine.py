@@ -86,7 +86,11 @@ def _chk_kterms(terms, sigma):
 
 
 class OracleEngine:
-    def __init__(self):
+    def __init__(self, strict: bool = True):
+        """``strict``: enforce the device engine's preconditions and verify the identity-channel promise (CPU host-logic tests).
+        ``tests/checked_engine.py`` replays calls the CUDA engine has ALREADY accepted and passes ``strict=False``: there the
+        checks would add nothing, and the replay must never be what makes a GPU test fail."""
+        self.strict = bool(strict)
         self.torch_device = torch.device("cpu")
         self._stats = {"solves": 0, "matvecs": 0, "flops": 0.0, "launches": 0}
 
@@ -107,16 +111,29 @@ class OracleEngine:
     def _wrap(self, a: np.ndarray) -> torch.Tensor:
         return torch.from_numpy(np.ascontiguousarray(a))
 
+    # -- precondition checks (strict mode only) ------------------------------------------------------------------
+    def _pre(self, *specs):
+        """specs: (tensor, name[, ndim]) triples checked against the device engine's contract."""
+        if self.strict:
+            for spec in specs:
+                _chk(*spec)
+
+    def _require(self, ok: bool, msg: str):
+        if self.strict and not ok:
+            raise ValueError(msg)
+
     def heff_apply(self, terms, psi):
-        _chk(psi, "psi", 3)
-        _chk_hterms(terms, psi)
+        if self.strict:
+            _chk(psi, "psi", 3)
+            _chk_hterms(terms, psi)
         out = self._heff_sum(terms, psi)
-        promised = [(L, c, R, coef) for (L, c, R, coef) in terms
-                    if c is not None and c.data is not None and ((L is not None and c.l_id >= 0) or (R is not None and c.r_id >= 0))]
-        if promised:
-            short = [(None if L is None else (_unit_channel(L, c.l_id) if c.l_id >= 0 else L), c,
-                      None if R is None else (_unit_channel(R, c.r_id) if c.r_id >= 0 else R), coef) for (L, c, R, coef) in promised]
-            _chk_shortcut(self._heff_sum(promised, psi), self._heff_sum(short, psi), "H_eff")
+        if self.strict:          # the identity-channel promise: the product must not change when the named channels are unit matrices
+            promised = [(L, c, R, coef) for (L, c, R, coef) in terms
+                        if c is not None and c.data is not None and ((L is not None and c.l_id >= 0) or (R is not None and c.r_id >= 0))]
+            if promised:
+                short = [(None if L is None else (_unit_channel(L, c.l_id) if c.l_id >= 0 else L), c,
+                          None if R is None else (_unit_channel(R, c.r_id) if c.r_id >= 0 else R), coef) for (L, c, R, coef) in promised]
+                _chk_shortcut(self._heff_sum(promised, psi), self._heff_sum(short, psi), "H_eff")
         return self._wrap(out)
 
     @staticmethod
@@ -130,14 +147,16 @@ class OracleEngine:
         return out
 
     def keff_apply(self, terms, sigma):
-        _chk(sigma, "sigma", 2)
-        _chk_kterms(terms, sigma)
+        if self.strict:
+            _chk(sigma, "sigma", 2)
+            _chk_kterms(terms, sigma)
         out = self._keff_sum(terms, sigma)
-        promised = [t for t in terms if len(t) > 3 and t[3] is not None and t[0] is not None and t[1] is not None]
-        if promised:
-            short = [(_unit_channel(L, ids[0]) if ids[0] >= 0 else L, _unit_channel(R, ids[1]) if ids[1] >= 0 else R, coef)
-                     for (L, R, coef, ids) in promised]
-            _chk_shortcut(self._keff_sum(promised, sigma), self._keff_sum(short, sigma), "K_eff")
+        if self.strict:
+            promised = [t for t in terms if len(t) > 3 and t[3] is not None and t[0] is not None and t[1] is not None]
+            if promised:
+                short = [(_unit_channel(L, ids[0]) if ids[0] >= 0 else L, _unit_channel(R, ids[1]) if ids[1] >= 0 else R, coef)
+                         for (L, R, coef, ids) in promised]
+                _chk_shortcut(self._keff_sum(promised, sigma), self._keff_sum(short, sigma), "K_eff")
         return self._wrap(out)
 
     @staticmethod
@@ -151,14 +170,10 @@ class OracleEngine:
         return out
 
     def env_update(self, gauge, bra, ket, E, core, out=None, accumulate=False):
-        _chk(bra, "bra", 3)
-        _chk(ket, "ket", 3)
-        _chk(E, "E", 3)
-        _chk(out, "out", 3)
-        if tuple(bra.shape) != tuple(ket.shape):
-            raise ValueError("tdvp_env_update takes bra and ket of one shape (rectangular blocks are zero-padded by the caller)")
-        if core is not None and core.data is not None:
-            _chk(core.data, "W")
+        self._pre((bra, "bra", 3), (ket, "ket", 3), (E, "E", 3), (out, "out", 3),
+                  (None if core is None else core.data, "W"))
+        self._require(tuple(bra.shape) == tuple(ket.shape),
+                      "tdvp_env_update takes bra and ket of one shape (rectangular blocks are zero-padded by the caller)")
         res = orc.env_update_term(gauge, bra.numpy(), ket.numpy(), _np(E), _core(core))
         if out is not None and accumulate:
             out += self._wrap(res)
@@ -166,11 +181,12 @@ class OracleEngine:
         return self._wrap(res)
 
     def krylov_expm(self, kind, scale, thresh, n_warmup, conserve_norm, psi, *, hterms=None, kterms=None, size_override=None):
-        _chk(psi, "psi")
-        if hterms is not None:
-            _chk_hterms(hterms, psi)
-        else:
-            _chk_kterms(kterms, psi)
+        if self.strict:
+            _chk(psi, "psi")
+            if hterms is not None:
+                _chk_hterms(hterms, psi)
+            else:
+                _chk_kterms(kterms, psi)
         last = n_warmup + 2 if n_warmup > 0 else 0
         if hterms is not None:
             mv = lambda x: self.heff_apply(hterms, self._wrap(x)).numpy()  # noqa: E731
@@ -185,20 +201,19 @@ class OracleEngine:
         return n
 
     def lanczos_eigvec(self, psi, hterms, root=0, thresh=1e-9):
-        _chk(psi, "psi", 3)
-        _chk_hterms(hterms, psi)
+        if self.strict:
+            _chk(psi, "psi", 3)
+            _chk_hterms(hterms, psi)
         mv = lambda x: self.heff_apply(hterms, self._wrap(x)).numpy()  # noqa: E731
         y, n = orc.lanczos_ground_state(mv, psi.numpy().copy(), root, thresh)
         psi.copy_(self._wrap(y / np.linalg.norm(y)))
         return n
 
     def qr_shift(self, gauge, psi, regularize=False):
-        _chk(psi, "psi", 3)
+        self._pre((psi, "psi", 3))
         Dl, d, Dr = psi.shape
-        if gauge == "A" and Dl * d < Dr:             # Engine.qr_shift / TDVP_ERR_SHAPE: tall matricisations only
-            raise ValueError("QR shift needs Dl*d >= Dr")
-        if gauge != "A" and Dr * d < Dl:
-            raise ValueError("LQ shift needs Dr*d >= Dl")
+        # Engine.qr_shift / TDVP_ERR_SHAPE: tall matricisations only (the reference's economic QR would shrink the bond)
+        self._require(Dl * d >= Dr if gauge == "A" else Dr * d >= Dl, "QR / LQ shift needs a tall matricisation")
         if gauge == "A":
             A, s = orc.shift_qr(psi.numpy(), regularize)
             return self._wrap(A), self._wrap(s)
@@ -206,27 +221,24 @@ class OracleEngine:
         return self._wrap(B), self._wrap(s)
 
     def svd(self, M):
-        _chk(M, "M", 2)
+        self._pre((M, "M", 2))
         U, s, Vh = np.linalg.svd(M.numpy(), full_matrices=False)
         return self._wrap(U), s, self._wrap(Vh)
 
     def svd_truncate(self, sigma, p, keepdim=False, regularize=False):
-        _chk(sigma, "sigma", 2)
-        if sigma.shape[0] != sigma.shape[1]:
-            raise ValueError("svd_truncate: the bond matrix must be square")        # tdvp_svd_truncate
+        self._pre((sigma, "sigma", 2))
+        self._require(sigma.shape[0] == sigma.shape[1], "svd_truncate: the bond matrix must be square")        # tdvp_svd_truncate
         U, S, Vh, rank = orc.truncate_bond(None, sigma.numpy(), None, p, regularize, keepdim)
         return self._wrap(U), self._wrap(S.astype(complex)), self._wrap(Vh), rank
 
     def pinv(self, X, rcond=1e-13):
-        _chk(X, "X", 2)
-        if X.shape[0] != X.shape[1]:
-            raise ValueError("pinv: square matrices only")                          # tdvp_pinv
+        self._pre((X, "X", 2))
+        self._require(X.shape[0] == X.shape[1], "pinv: square matrices only")                                # tdvp_pinv
         return self._wrap(np.linalg.pinv(X.numpy(), rcond=rcond))
 
     def zgemm(self, A, B, transA=0, transB=0, alpha=1.0, beta=0.0, C_out=None):
-        _chk(A, "A", 2)          # Engine.zgemm passes shape[1] as the leading dimension: row-major contiguous operands only
-        _chk(B, "B", 2)
-        _chk(C_out, "C", 2)
+        # Engine.zgemm passes shape[1] as the leading dimension: row-major contiguous operands only
+        self._pre((A, "A", 2), (B, "B", 2), (C_out, "C", 2))
         a = {0: A.numpy(), 1: A.numpy().T, 2: A.numpy().conj().T}[transA]
         b = {0: B.numpy(), 1: B.numpy().T, 2: B.numpy().conj().T}[transB]
         out = alpha * (a @ b)
@@ -236,26 +248,21 @@ class OracleEngine:
         return self._wrap(out)
 
     def absorb(self, gauge, sigma, site):
-        _chk(sigma, "sigma", 2)
-        _chk(site, "site", 3)
-        if (gauge == "A" and sigma.shape[1] != site.shape[0]) or (gauge != "A" and sigma.shape[0] != site.shape[2]):
-            raise ValueError("absorb: bond dimensions of the matrix and the site differ")
+        self._pre((sigma, "sigma", 2), (site, "site", 3))
+        self._require(sigma.shape[1] == site.shape[0] if gauge == "A" else sigma.shape[0] == site.shape[2],
+                      "absorb: bond dimensions of the matrix and the site differ")
         if gauge == "A":
             return self._wrap(np.tensordot(sigma.numpy(), site.numpy(), axes=(1, 0)))
         return self._wrap(np.tensordot(site.numpy(), sigma.numpy(), axes=(2, 0)))
 
     def inner(self, bra, ket, conj=True):
-        _chk(bra, "bra")
-        _chk(ket, "ket")
-        if bra.numel() != ket.numel():
-            raise ValueError("inner: sizes differ")
+        self._pre((bra, "bra"), (ket, "ket"))
+        self._require(bra.numel() == ket.numel(), "inner: sizes differ")
         a = bra.numpy().ravel()
         return complex(np.inner(np.conj(a) if conj else a, ket.numpy().ravel()))
 
     def overlap_site(self, bra, ket, block, conj_bra):
-        _chk(bra, "bra", 3)
-        _chk(ket, "ket", 3)
-        _chk(block, "block", 2)
+        self._pre((bra, "bra", 3), (ket, "ket", 3), (block, "block", 2))
         b = np.conj(bra.numpy()) if conj_bra else bra.numpy()
         return self._wrap(np.einsum("abc,abk->ck", b, np.einsum("ibk,ai->abk", ket.numpy(), block.numpy())))
 

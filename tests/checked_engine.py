@@ -23,7 +23,7 @@ def _core(c):
 class CheckedEngine:
     def __init__(self, eng):
         self.eng = eng
-        self.orc = OracleEngine()
+        self.orc = OracleEngine(strict=False)      # replays calls the CUDA engine has already accepted
         self.torch_device = eng.torch_device
         self.dev: dict[str, float] = {}
         self.worst: dict[str, tuple] = {}
