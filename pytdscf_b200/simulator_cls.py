@@ -248,9 +248,9 @@ class Simulator:
         # hands its host cores to every rank; nothing is exchanged when every rank built its own
         ham = self.model.hamiltonian
         if comm.allreduce_lor(bool(getattr(ham, "deferred", False))):
+            if comm.allreduce_lor(info.rank == 0 and ham.deferred):      # every rank learns it, so nobody is left waiting
+                raise ValueError("rank 0 must hold the Hamiltonian (potential=None is for the other ranks)")
             if info.rank == 0:
-                if ham.deferred:
-                    raise ValueError("rank 0 must hold the Hamiltonian (potential=None is for the other ranks)")
                 payload = ham.export_cores()
                 for r in range(1, info.world):
                     comm.send(payload, r)
