@@ -51,6 +51,21 @@ def test_reference_test_exiciton_propagate_runs_unmodified(monkeypatch, tmp_path
     out = sorted(os.listdir(tmp_path / "LVC_Exciton_test_prop"))
     assert {"main.log", "autocorr.dat", "populations.dat", "expectations.dat", "reduced_density.nc"} <= set(out)
     assert os.path.exists(tmp_path / "wf_LVC_Exciton_test.pkl")
+    # the reference's own post-processing reads the file: spectra.load_autocorr insists on the "fs" header, t[0] == 0 and
+    # autocorr[0] == 1.0 exactly (pytdscf/spectra.py); loaded from the reference tree under its import shims
+    import importlib.util as iu
+
+    spec = iu.spec_from_file_location("reference_spectra", "/root/reference/pytdscf/spectra.py")
+    try:
+        spectra = iu.module_from_spec(spec)
+        spec.loader.exec_module(spectra)
+    except ImportError:      # matplotlib etc. absent: the layout check below still runs
+        spectra = None
+    if spectra is not None:
+        t, a = spectra.load_autocorr(str(tmp_path / "LVC_Exciton_test_prop" / "autocorr.dat"))
+        assert len(t) == 20 and t[1] == pytest.approx(0.2) and abs(a[1]) < 1.0
+    first, second = open(tmp_path / "LVC_Exciton_test_prop" / "autocorr.dat").read().splitlines()[:2]
+    assert "fs" in first and second.split()[0] == "0.000000000" and complex(second.split()[1]) == 1.0
 
 
 def test_reference_backend_strings_are_refused(monkeypatch, tmp_path):
